@@ -1,0 +1,424 @@
+"""bench.py -- DGG forward+backward throughput (nodes/s) at Pubmed shape on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload pubmed]
+
+One "step" = one ``DGG.forward`` + backward (gradients for every DGG parameter) over one Pubmed-shape
+graph batch (N=19 717 nodes, F=500, h=64, E~108 k incl. self loops; BASELINE.json configs[2],
+SURVEY.md 8d).  At --gpus N > 1 (torchrun) every rank processes its own graph batch per step and the
+DGG weight gradients are all-reduced over NCCL (weak scaling, the way the reference's mini-batch
+drivers would be data-parallelised); value = nodes all ranks processed / max-over-ranks device time.
+
+Prints ONE JSON line (see the task contract): value (inputs resident in HBM), e2e (host buffers,
+H2D/D2H inside the timed region, through the public ``dgm.DGG`` module), roofline of the dominant
+kernel, cpu_baseline (the CPU oracle port timed on this box's host cores), clocks, gpu_launches.
+
+``--impl reference`` times the CPU oracle port of the reference algorithm (the reference itself is
+Python that cannot travel to the GPU box, and is the dense O(N^2 log N) algorithm) on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PUBMED = dict(n=19717, f=500, h=64, mean_deg=4.5, max_deg=171)
+METRIC = "dgg_fwd_bwd_nodes_per_s"
+N_SETS = 6  # rotating input sets: 6 x ~50 MB touched per step > 126 MB L2
+
+
+# --------------------------------------------------------------------------- synthetic workload
+def chung_lu_graph(n, mean_deg, max_deg, seed):
+    """Power-law (Chung-Lu) undirected graph + self loops -> coalesced COO (idx int64 [2,E], val).
+    SURVEY.md 8d: Pubmed-shape stand-in when the real ind.pubmed.graph is not on the box."""
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.rand(n, generator=g) * (1 - 1e-3) + 1e-3) ** (-1.0 / 1.6)      # Pareto tail
+    w = w.clamp(max=float(max_deg))
+    w = w * (mean_deg * n / w.sum())
+    m = int(mean_deg * n / 2)
+    p = w / w.sum()
+    src = torch.multinomial(p, m, replacement=True, generator=g)
+    dst = torch.multinomial(p, m, replacement=True, generator=g)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    loops = torch.arange(n)
+    i = torch.cat([src, dst, loops])
+    j = torch.cat([dst, src, loops])
+    a = torch.sparse_coo_tensor(torch.stack([i, j]), torch.ones(i.numel()), (n, n)).coalesce()
+    return a.indices().contiguous(), torch.ones(a._nnz())
+
+
+def make_set(shape, seed):
+    idx, val = chung_lu_graph(shape["n"], shape["mean_deg"], shape["max_deg"], seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    x = torch.rand(shape["n"], shape["f"], generator=g)
+    x = x / x.sum(-1, keepdim=True)                     # == T.NormalizeFeatures (train_small_graphs.py:345)
+    g_vals = torch.randn(idx.shape[1], generator=g)     # upstream gradient of the adjacency values
+    g_xenc = torch.randn(shape["n"], shape["h"], generator=g) * 0.01
+    return dict(idx=idx, val=val, x=x, g_vals=g_vals, g_xenc=g_xenc)
+
+
+def dgg_args():
+    return argparse.Namespace(extra_edge_dim=0)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------- CPU oracle leg
+def cpu_oracle_fwd_bwd(sets, state, n_sample):
+    """One DGG fwd+bwd of the CPU oracle (dense reference algorithm) on the first n_sample nodes'
+    induced subgraph of set 0.  Returns seconds."""
+    from oracle import dgg_oracle as O
+
+    s = sets[0]
+    idx = s["idx"]
+    if n_sample < s["x"].shape[0]:
+        keep = (idx[0] < n_sample) & (idx[1] < n_sample)
+        idx = idx[:, keep]
+        g_vals = s["g_vals"][keep]
+    else:
+        g_vals = s["g_vals"]
+    x = s["x"][:n_sample]
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in state.items()}
+    t0 = time.perf_counter()
+    r = O.dgg_forward(x, idx, n_sample, p)
+    vals = r["out"][idx[0], idx[1]]
+    torch.autograd.backward([vals, r["x_enc"]], [g_vals, s["g_xenc"][:n_sample]])
+    return time.perf_counter() - t0
+
+
+def pick_sample(sets, state, budget_s, n_full):
+    """Largest node count whose dense O(N^2) oracle step fits the time budget (calibrated live)."""
+    n0 = min(2048, n_full)
+    cpu_oracle_fwd_bwd(sets, state, min(512, n_full))          # warm the thread pool
+    t0 = cpu_oracle_fwd_bwd(sets, state, n0)
+    c = t0 / (n0 * n0)
+    n = int(min(n_full, (budget_s / c) ** 0.5))
+    return max(256, n)
+
+
+# --------------------------------------------------------------------------- main arms
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    shape = PUBMED
+    sets = [make_set(shape, 0)]
+    torch.manual_seed(0)
+    state = ref_state(shape)
+    total_budget = 150.0
+    n_s = pick_sample(sets, state, total_budget / max(1, args.steps + args.warmup), shape["n"])
+    for _ in range(args.warmup):
+        cpu_oracle_fwd_bwd(sets, state, n_s)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_oracle_fwd_bwd(sets, state, n_s)
+    value = n_s * args.steps / t
+    sample = (f"CPU oracle port of dgm.py:1758-1815 (dense N^2 scatter + row sort), fwd+bwd on the {n_s}-node "
+              f"induced subgraph of the Pubmed-shape graph; dense cost grows ~N^2 so nodes/s at the full "
+              f"{shape['n']} nodes is lower")
+    line = dict(metric=METRIC, value=value, unit="nodes/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="pubmed-shape DGG fwd+bwd", n=shape["n"], f=shape["f"], h=shape["h"]),
+                cpu_baseline=dict(value=value, unit="nodes/s", cores=os.cpu_count(), kind="port", sample=sample),
+                e2e=dict(value=value, unit="nodes/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def ref_state(shape):
+    """Random-init DGG weights with the reference's parameter names (dgm.py:1741-1752)."""
+    import torch.nn as nn
+
+    torch.manual_seed(0)
+    ne, ee, dd = nn.Linear(shape["f"], shape["h"]), nn.Linear(shape["h"], shape["h"]), nn.Linear(1, 1)
+    with torch.no_grad():
+        ne.weight.mul_(8.0)          # spread the scores (default init on row-normalised x is near-constant)
+        dd.weight.fill_(0.9)
+        dd.bias.fill_(0.4)
+    return {"node_encoder.0.weight": ne.weight.detach(), "node_encoder.0.bias": ne.bias.detach(),
+            "edge_encoder.0.weight": ee.weight.detach(), "edge_encoder.0.bias": ee.bias.detach(),
+            "degree_decoder.0.weight": dd.weight.detach(), "degree_decoder.0.bias": dd.bias.detach()}
+
+
+def time_region(fn, steps, world):
+    """barrier + sync, CUDA events around `steps` calls on the current stream, max over ranks -> ms."""
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+
+    import dgg_b200
+    import dgm
+    from dgg_b200 import CSRGraph
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shape = PUBMED
+    L = dgg_b200.lib()
+
+    host_sets = [make_set(shape, 100 * rank + s) for s in range(N_SETS)]
+    state = ref_state(shape)
+    m = dgm.DGG(in_dim=shape["f"], latent_dim=shape["h"], args=dgg_args())
+    m.load_state_dict(state)
+    m = m.to(dev)
+    params = [p for p in m.parameters()]
+
+    # ---- device-resident inputs (the `value` arm) ----
+    dsets = []
+    for s in host_sets:
+        adj = torch.sparse_coo_tensor(s["idx"].to(dev), s["val"].to(dev), (shape["n"], shape["n"]),
+                                      is_coalesced=True)
+        CSRGraph.from_coo(adj)  # CSR handle cached on the tensor, as a training loop holding adj would
+        dsets.append(dict(adj=adj, x=s["x"].to(dev), g_vals=s["g_vals"].to(dev), g_xenc=s["g_xenc"].to(dev)))
+    flat_grads = None
+
+    def step_resident(i):
+        s = dsets[i % N_SETS]
+        for p in params:
+            p.grad = None
+        out, x_enc = m(s["x"], s["adj"])
+        torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"], s["g_xenc"]])
+        if world > 1:
+            flat = torch.cat([p.grad.flatten() for p in params])
+            dist.all_reduce(flat)
+
+    # ---- host-buffer inputs (the `e2e` arm): what train_small_graphs.py does every call ----
+    pinned = [dict(idx=s["idx"].pin_memory(), val=s["val"].pin_memory(), x=s["x"].pin_memory()) for s in host_sets]
+    out_host = torch.empty(max(s["idx"].shape[1] for s in host_sets), dtype=torch.float32).pin_memory()
+    gsum_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in pinned[0].values())
+    d2h = pinned[0]["idx"].shape[1] * 4 + 4
+
+    def step_e2e(i):
+        s, hs = dsets[i % N_SETS], pinned[i % N_SETS]
+        for p in params:
+            p.grad = None
+        idx = hs["idx"].to(dev, non_blocking=True)
+        val = hs["val"].to(dev, non_blocking=True)
+        x = hs["x"].to(dev, non_blocking=True)
+        adj = torch.sparse_coo_tensor(idx, val, (shape["n"], shape["n"]), is_coalesced=True)
+        out, x_enc = m(x, adj)
+        torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"], s["g_xenc"]])
+        if world > 1:
+            flat = torch.cat([p.grad.flatten() for p in params])
+            dist.all_reduce(flat)
+        e = out._dgg_vals.numel()
+        out_host[:e].copy_(out._dgg_vals.detach(), non_blocking=True)
+        gsum_host.copy_(params[0].grad.sum().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller reads the result on the host
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = L.dggb_kernel_launches()
+    ms = time_region(step_resident, args.steps, world)
+    launches = int(L.dggb_kernel_launches() - l0)
+    for i in range(max(3, args.warmup)):
+        step_e2e(i)
+    ms_e2e = time_region(step_e2e, args.steps, world)
+    clocks = sampler.stop() if rank == 0 else None
+
+    nodes = shape["n"] * world * args.steps
+    value = nodes / (ms * 1e-3)
+    e2e_value = nodes / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    roofline = kernel_roofline(m, dsets, shape)
+    cpu = None
+    if world == 1:
+        torch.set_num_threads(os.cpu_count())
+        n_s = pick_sample(host_sets, state, 12.0, shape["n"])
+        t = cpu_oracle_fwd_bwd(host_sets, state, n_s)
+        cpu = dict(value=n_s / t, unit="nodes/s", cores=os.cpu_count(), kind="port",
+                   sample=f"CPU oracle (dense reference algorithm, dgm.py:1758-1815) fwd+bwd on the {n_s}-node "
+                          f"induced subgraph of set 0, 1 run, {t:.1f} s")
+
+    line = dict(metric=METRIC, value=value, unit="nodes/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic",
+                config=dict(workload="pubmed-shape DGG fwd+bwd", n=shape["n"], f=shape["f"], h=shape["h"],
+                            edges=int(host_sets[0]["idx"].shape[1]), graphs_per_step_per_gpu=1,
+                            l2=f"rotating {N_SETS} input sets (> 126 MB L2)",
+                            parallelism=(f"dp{world} (one graph batch per rank, NCCL all-reduce of DGG weight grads)"
+                                         if world > 1 else "single GPU")),
+                e2e=dict(value=e2e_value, unit="nodes/s", ms_per_step=ms_e2e / args.steps,
+                         h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(m, dsets, shape, iters=30):
+    """Time each hand-written kernel of the step alone (CUDA events on the launch stream, rotating
+    input sets) and report the dominant one against the measured HBM peak."""
+    import torch.nn.functional as F
+
+    from dgg_b200 import CSRGraph
+    from dgg_b200 import functional as K
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    lin, dd = m.edge_encoder[0], m.degree_decoder[0]
+    prepared = []
+    with torch.no_grad():
+        for s in dsets:
+            g, _ = CSRGraph.from_coo(s["adj"])
+            y = F.linear(m.node_encoder(s["x"]), lin.weight)
+            prepared.append((g, y, s["g_vals"]))
+    n, h = shape["n"], shape["h"]
+    E = prepared[0][0].nnz
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    saved = {}
+
+    def fwd(i):
+        g, y, _ = prepared[i % N_SETS]
+        with torch.no_grad():
+            saved[i % N_SETS] = K._DGGEdge.apply(y, lin.bias, dd.weight, dd.bias, g, None, -1)
+
+    t_fwd = timed(fwd)
+    from dgg_b200._lib import check, i32, lib, p, stream
+
+    dy = torch.zeros(n, h, device=prepared[0][1].device)
+    small = torch.zeros(h + 2, device=dy.device)
+    dw, db = dd.weight.detach().reshape(-1), dd.bias.detach().reshape(-1)
+    be = lin.bias.detach()
+
+    def bwd(i):
+        g, y, gv = prepared[i % N_SETS]
+        out, k, R, rank = saved[i % N_SETS]
+        # timing only: the row-sum input `s` is not returned by the autograd wrapper, `k` stands in
+        # for it (same size, same access pattern)
+        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.col), i32(n), i32(h), p(y), p(be), p(dw), p(db), p(None),
+                                      i32(-1), p(R), p(rank), p(k), p(k), p(gv), p(dy), p(small[:h]), p(small[h:]),
+                                      stream()), "bwd")
+
+    t_bwd = timed(bwd)
+    # algorithmic bytes (SURVEY 8d, int32 CSR): see DESIGN.md "dgg_edge"
+    b_fwd = E * (4 + 4 * h) + n * (4 * h + 12) + E * 12
+    b_bwd = E * (4 + 4 * h + 12) + E * 4 * h + n * (4 * h * 2 + 12)
+    name, t, b = ("dgg_edge_bwd_kernel", t_bwd, b_bwd) if t_bwd >= t_fwd else ("dgg_edge_fwd_kernel", t_fwd, b_fwd)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get(name)
+    return dict(bound="hbm", kernel=name, achieved=b / t / 1e9, peak=peak, unit="GB/s", frac=b / t / 1e9 / peak,
+                traffic=traffic, peak_source=peak_src, algorithmic_bytes=int(b), kernel_us=t * 1e6,
+                others={"dgg_edge_fwd_kernel_us": t_fwd * 1e6, "dgg_edge_bwd_kernel_us": t_bwd * 1e6})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pubmed", choices=["pubmed"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

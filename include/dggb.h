@@ -1,0 +1,129 @@
+/* dggb.h -- C-ABI of the B200-native DGG hot path (libdggb.so).
+ *
+ * The reference (avishkarsaha/learning-adaptive-neighborhoods-for-gnns) exposes no
+ * FFI of its own: its boundary is the Python nn.Module surface.
+ * These entry points are what a maintainer binds (ctypes / a torch extension) from
+ * inside the reference's dgm.py / model.py to replace the dense ATen pipeline; each
+ * one cites the reference lines it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - dense matrices are row-major fp32; graphs are int32 CSR (rowptr[N+1], col[nnz]),
+ *     rows sorted by column (== the order of a coalesced torch COO tensor);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises, nothing allocates (callers pass outputs/workspaces);
+ *   - return value: DGGB_OK (0) or a negative dggb_status; no C++ exceptions cross
+ *     the boundary; dggb_error_string() names a status;
+ *   - buffers documented "accumulated into" must be zeroed by the caller.
+ */
+#ifndef DGGB_H_
+#define DGGB_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dggb_status {
+  DGGB_OK = 0,
+  DGGB_ERR_BAD_ARG = -1,       /* null pointer / negative size */
+  DGGB_ERR_BAD_SHAPE = -2,     /* unsupported dimension (e.g. H % 4 != 0 where required) */
+  DGGB_ERR_UNSUPPORTED = -3,   /* unknown mode enum */
+  DGGB_ERR_K_OVERFLOW = -4,    /* a row needed more than Kcap selected entries */
+  DGGB_ERR_CUDA = -5,          /* a CUDA call failed; see dggb_last_cuda_error() */
+  DGGB_ERR_WORKSPACE = -6      /* workspace too small */
+} dggb_status;
+
+int dggb_version(void);                     /* ABI version, currently 1 */
+const char* dggb_error_string(int status);
+int dggb_last_cuda_error(void);             /* cudaError_t of the last DGGB_ERR_CUDA */
+int dggb_build_arch(void);                  /* 1000 == compiled for sm_100a */
+long long dggb_kernel_launches(void);       /* kernels launched by this library so far */
+
+/* ------------------------------------------------------------------------------------
+ * Graph plumbing.  Replaces (A.to_dense() + I).to_sparse().coalesce()
+ * (model.py:1249-1264, 171-176, 389-392, 710-715, 1381-1392) and the COO->dense
+ * scatters (dgm.py:1787-1788, 1626-1627).
+ * ---------------------------------------------------------------------------------- */
+
+/* rowptr[N+1] from the row indices of a COALESCED COO (int64, sorted). */
+int dggb_coo_rows_to_rowptr(const int64_t* row, int64_t nnz, int32_t n, int32_t* rowptr, void* stream);
+
+/* int64 -> int32 column indices. */
+int dggb_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, void* stream);
+
+/* CSR + I: per row, add 1.0 to an existing diagonal entry or insert a new one.
+ * Two phases so the caller can size the output: phase 1 writes out_rowptr[N+1];
+ * the caller reads out_rowptr[N] (nnz_out) and allocates; phase 2 fills col/val. */
+int dggb_add_self_loops_count(const int32_t* rowptr, const int32_t* col, int32_t n,
+                              int32_t* out_rowcount /* [N+1], exclusive-scanned in place */, void* stream);
+int dggb_add_self_loops_fill(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                             const int32_t* out_rowptr, int32_t* out_col, float* out_val, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * class DGG edge ranker + degree estimator + soft first-k (dgm.py:1781-1810; a4, A.1)
+ *
+ *   y      = x_enc * We^T            (the caller's GEMM; Linear(h,h) of dgm.py:1784 is
+ *                                     linear, so We(x_u - x_v) + be == y_u - y_v + be)
+ *   R_e    = sigmoid( sum_c LeakyReLU_0.01( y[u,c] - y[v,c] + be[c] ) )        (1783-1786)
+ *   [ablation: R_e = sigmoid(R_e + noise_e), noise_e in U(-1,1)]                (1933-1935)
+ *   s_i    = sum_{e in row i} R_e ;  k_i = LeakyReLU_0.01(deg_w * s_i + deg_b)   (1791-1792)
+ *   r_e    = 0-based descending rank of R_e inside its row (ties: lower column first)
+ *   out_e  = R_e * ( (1 - 0.5*(1 + tanh(r_e - k_i))) + 1 )                       (1798-1810)
+ *   [hard_k >= 0: out_e = r_e < hard_k ? R_e : 0 and k is not computed]          (1943-1945)
+ *
+ * The dense N x N scatter, the N-long row sort and the un-sort scatter of the reference
+ * are not performed: off-support entries are exact zeros that sort last, so the rank
+ * inside the row's own edges is the rank in the dense row.
+ * Requires H % 4 == 0.
+ * ---------------------------------------------------------------------------------- */
+int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* col, int32_t n, int32_t h,
+                      const float* y /* [N,H] */, const float* be /* [H] */,
+                      const float* deg_w /* [1] */, const float* deg_b /* [1] */,
+                      const float* ablation_noise /* [E] or NULL */, int32_t hard_k /* <0: soft */,
+                      float* R /* [E] out (post-noise value) */, int32_t* rank /* [E] out */,
+                      float* s /* [N] out */, float* k /* [N] out */, float* out /* [E] out */,
+                      void* stream);
+
+/* Backward of the above w.r.t. y, be, deg_w, deg_b given g_out = dL/d out.
+ * dy[N,H], dbe[H], ddeg[2] (= {d deg_w, d deg_b}) are ACCUMULATED INTO. */
+int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* col, int32_t n, int32_t h,
+                      const float* y, const float* be, const float* deg_w, const float* deg_b,
+                      const float* ablation_noise, int32_t hard_k,
+                      const float* R, const int32_t* rank, const float* s, const float* k,
+                      const float* g_out /* [E] */,
+                      float* dy, float* dbe, float* ddeg, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * normalize_adj: Ahat_ij = A_ij * s_i^-1/2 * s_j^-1/2 with s = ROW sums on both sides
+ * (model.py:1215-1218, 146-149, 687-690, 1347-1350; dgm.py:1172-1175; a13, A.6).
+ * Replaces diag + two dense N^3 torch.mm with O(nnz) work.
+ * ---------------------------------------------------------------------------------- */
+int dggb_sym_normalize_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                           float* dinv /* [N] out: s^-1/2 */, float* out /* [E] */, void* stream);
+/* dval_e = g_e*a_i*a_j - 0.5 * s_i^-3/2 * T_i,  T_i = sum over entries whose row OR column is i
+ * of g*val*a_other.  t_ws [N] is scratch and must be zeroed by the caller. */
+int dggb_sym_normalize_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                           const float* dinv, const float* g /* [E] */, float* t_ws /* [N] zeroed */,
+                           float* dval /* [E] out */, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * CSR SpMM  Y = A X  -- replaces torch.mm(adj_dense, x) (model.py:594, 67) and the
+ * dense adj @ x of PyG DenseGraphConv (model.py:128-129).  128-bit gathers when F%4==0.
+ * row_scale (may be NULL): Y_i *= row_scale[i]  (SAGE mean: 1/clamp(rowsum,1)).
+ * ---------------------------------------------------------------------------------- */
+int dggb_spmm_csr_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                      const float* x /* [Ncols,F] */, int32_t f, const float* row_scale,
+                      float* y /* [N,F] */, void* stream);
+/* Backward: dval_e = rs_i * <dY_i, X_j> (skipped if dval NULL); dX_j += val_e * rs_i * dY_i
+ * (dX ACCUMULATED INTO via vector atomics; skipped if NULL). */
+int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                      const float* x, int32_t f, const float* row_scale, const float* dy,
+                      float* dval, float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGGB_H_ */

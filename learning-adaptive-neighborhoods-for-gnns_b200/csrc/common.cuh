@@ -1,0 +1,73 @@
+// Shared device/host helpers for libdggb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dggb.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdggb is written for sm_100a only"
+#endif
+
+namespace dggb {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;           // B200
+constexpr float kLeaky = 0.01f;        // nn.LeakyReLU() default (dgm.py:1743, 1748, 1752)
+
+extern int g_last_cuda_error;
+extern long long g_kernel_launches;  // kernels this library has launched (bench.py's gpu_launches)
+
+inline int cuda_status(cudaError_t e) {
+  if (e == cudaSuccess) return DGGB_OK;
+  g_last_cuda_error = (int)e;
+  return DGGB_ERR_CUDA;
+}
+inline int launch_status(int kernels = 1) {
+  g_kernel_launches += kernels;
+  return cuda_status(cudaGetLastError());
+}
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// sum over the aligned group of `width` lanes (width = power of two <= 32)
+__device__ __forceinline__ float group_sum(float v, int width) {
+  for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeaky * v; }
+__device__ __forceinline__ float leaky_grad(float v) { return v > 0.f ? 1.f : kLeaky; }
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 128-bit vector reduction to global memory (sm_90+): one L2 atomic op for four floats.
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// largest power of two <= v (v >= 1), capped at 32
+__host__ __device__ inline int pow2_floor32(int v) {
+  int p = 1;
+  while (p * 2 <= v && p < 32) p *= 2;
+  return p;
+}
+
+// warp-per-row grids: rows are dealt to warps round-robin from a persistent grid
+inline int rows_grid(int n_rows, int warps_per_block, int blocks_per_sm) {
+  long long need = ((long long)n_rows + warps_per_block - 1) / warps_per_block;
+  long long cap = (long long)kNumSMs * blocks_per_sm;
+  long long g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace dggb

@@ -1,0 +1,198 @@
+// CSR SpMM Y = A X (+ optional per-row scale) and its backward (dX = A^T dY via vector reductions,
+// dA = SDDMM).  Replaces torch.mm(adj_dense, x) (model.py:594, 67) and PyG DenseGraphConv's adj @ x.
+// Warp per row; the 32 lanes split into G groups of L lanes, a group gathers one neighbour row at a
+// time with VEC-wide (128-bit when F % 4 == 0) coalesced loads.
+// HBM-bound: nnz*(8 + F*4 gathered) + N*F*4 bytes.
+#include "common.cuh"
+
+namespace dggb {
+
+constexpr int kSpmmWarps = 8;
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> {
+  float4 v;
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void fma(float a, const Vec& o) { v.x += a * o.v.x; v.y += a * o.v.y; v.z += a * o.v.z; v.w += a * o.v.w; }
+  __device__ __forceinline__ void scale(float a) { v.x *= a; v.y *= a; v.z *= a; v.w *= a; }
+  __device__ __forceinline__ float dot(const Vec& o) const { return v.x * o.v.x + v.y * o.v.y + v.z * o.v.z + v.w * o.v.w; }
+  __device__ __forceinline__ void xor_add(int o) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  __device__ __forceinline__ void red(float* p, float a) const { red_add4(p, make_float4(a * v.x, a * v.y, a * v.z, a * v.w)); }
+};
+template <> struct Vec<2> {
+  float2 v;
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float2*>(p)); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = v; }
+  __device__ __forceinline__ void fma(float a, const Vec& o) { v.x += a * o.v.x; v.y += a * o.v.y; }
+  __device__ __forceinline__ void scale(float a) { v.x *= a; v.y *= a; }
+  __device__ __forceinline__ float dot(const Vec& o) const { return v.x * o.v.x + v.y * o.v.y; }
+  __device__ __forceinline__ void xor_add(int o) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  __device__ __forceinline__ void red(float* p, float a) const {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a * v.x), "f"(a * v.y) : "memory");
+  }
+};
+template <> struct Vec<1> {
+  float v;
+  __device__ __forceinline__ void zero() { v = 0.f; }
+  __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+  __device__ __forceinline__ void store(float* p) const { *p = v; }
+  __device__ __forceinline__ void fma(float a, const Vec& o) { v += a * o.v; }
+  __device__ __forceinline__ void scale(float a) { v *= a; }
+  __device__ __forceinline__ float dot(const Vec& o) const { return v * o.v; }
+  __device__ __forceinline__ void xor_add(int o) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+  __device__ __forceinline__ void red(float* p, float a) const { atomicAdd(p, a * v); }
+};
+
+template <int VEC, int T>
+__global__ void __launch_bounds__(kSpmmWarps* kWarp)
+    spmm_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const float* __restrict__ val, int n, const float* __restrict__ x, int f, int L,
+                    const float* __restrict__ row_scale, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  const int W = VEC * L * T;  // columns covered per pass
+  for (int i = blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kSpmmWarps) {
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    const float rs = row_scale ? __ldg(row_scale + i) : 1.f;
+    for (int f0 = 0; f0 < f; f0 += W) {
+      Vec<VEC> acc[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) acc[t].zero();
+      for (int e0 = beg; e0 < end; e0 += G) {
+        const int e = e0 + grp;
+        const bool valid = e < end;
+        const int v = valid ? __ldg(col + e) : 0;
+        const float a = valid ? __ldg(val + e) : 0.f;
+        const float* xr = x + (size_t)v * f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = f0 + VEC * (lg + L * t);
+          if (c < f) {
+            Vec<VEC> xv;
+            xv.load(xr + c);
+            acc[t].fma(a, xv);
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        for (int o = L; o < kWarp; o <<= 1) acc[t].xor_add(o);
+        const int c = f0 + VEC * (lg + L * t);
+        if (grp == 0 && c < f) {
+          acc[t].scale(rs);
+          acc[t].store(y + (size_t)i * f + c);
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int T>
+__global__ void __launch_bounds__(kSpmmWarps* kWarp)
+    spmm_bwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const float* __restrict__ val, int n, const float* __restrict__ x, int f, int L,
+                    const float* __restrict__ row_scale, const float* __restrict__ dy, float* __restrict__ dval,
+                    float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  const int W = VEC * L * T;
+  for (int i = blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kSpmmWarps) {
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    const float rs = row_scale ? __ldg(row_scale + i) : 1.f;
+    for (int f0 = 0; f0 < f; f0 += W) {
+      Vec<VEC> g[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int c = f0 + VEC * (lg + L * t);
+        if (c < f) {
+          g[t].load(dy + (size_t)i * f + c);
+          g[t].scale(rs);
+        } else {
+          g[t].zero();
+        }
+      }
+      for (int e0 = beg; e0 < end; e0 += G) {
+        const int e = e0 + grp;
+        const bool valid = e < end;
+        const int v = valid ? __ldg(col + e) : 0;
+        const float a = valid ? __ldg(val + e) : 0.f;
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = f0 + VEC * (lg + L * t);
+          if (c < f && valid) {
+            if (dval) {
+              Vec<VEC> xv;
+              xv.load(x + (size_t)v * f + c);
+              dot += g[t].dot(xv);
+            }
+            if (dx) g[t].red(dx + (size_t)v * f + c, a);
+          }
+        }
+        if (dval) {
+          dot = group_sum(dot, L);
+          if (valid && lg == 0) dval[e] = (f0 == 0) ? dot : dval[e] + dot;  // same lane owns e in every pass
+        }
+      }
+    }
+  }
+}
+
+template <typename Fn>
+static int dispatch_vec(int f, Fn&& fn) {
+  // pick the widest vector the row stride allows, then lanes-per-row L and chunks-per-lane T
+  const int vec = (f % 4 == 0) ? 4 : (f % 2 == 0 ? 2 : 1);
+  const int chunks = (f + vec - 1) / vec;
+  const int L = pow2_floor32(chunks);
+  int T = (chunks + L - 1) / L;
+  T = T >= 4 ? 4 : (T >= 2 ? 2 : 1);
+  if (vec == 4) {
+    if (T == 1) return fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{}, L);
+    if (T == 2) return fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{}, L);
+    return fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}, L);
+  }
+  if (vec == 2) {
+    if (T == 1) return fn(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{}, L);
+    if (T == 2) return fn(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{}, L);
+    return fn(std::integral_constant<int, 2>{}, std::integral_constant<int, 4>{}, L);
+  }
+  if (T == 1) return fn(std::integral_constant<int, 1>{}, std::integral_constant<int, 1>{}, L);
+  if (T == 2) return fn(std::integral_constant<int, 1>{}, std::integral_constant<int, 2>{}, L);
+  return fn(std::integral_constant<int, 1>{}, std::integral_constant<int, 4>{}, L);
+}
+
+}  // namespace dggb
+using namespace dggb;
+
+extern "C" int dggb_spmm_csr_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                                 const float* x, int32_t f, const float* row_scale, float* y, void* stream) {
+  if (!rowptr || !col || !val || !x || !y || n < 0 || f <= 0) return DGGB_ERR_BAD_ARG;
+  if (n == 0) return DGGB_OK;
+  const int grid = rows_grid(n, kSpmmWarps, 8);
+  return dispatch_vec(f, [&](auto vc, auto tc, int L) {
+    spmm_fwd_kernel<decltype(vc)::value, decltype(tc)::value>
+        <<<grid, kSpmmWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, val, n, x, f, L, row_scale, y);
+    return launch_status();
+  });
+}
+
+extern "C" int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                                 const float* x, int32_t f, const float* row_scale, const float* dy, float* dval,
+                                 float* dx, void* stream) {
+  if (!rowptr || !col || !val || !x || !dy || n < 0 || f <= 0) return DGGB_ERR_BAD_ARG;
+  if (n == 0 || (!dval && !dx)) return DGGB_OK;
+  const int grid = rows_grid(n, kSpmmWarps, 8);
+  return dispatch_vec(f, [&](auto vc, auto tc, int L) {
+    spmm_bwd_kernel<decltype(vc)::value, decltype(tc)::value>
+        <<<grid, kSpmmWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, val, n, x, f, L, row_scale, dy, dval, dx);
+    return launch_status();
+  });
+}

@@ -1,0 +1,122 @@
+"""torch.autograd.Function wrappers over the C-ABI (include/dggb.h).  CUDA tensors only; there is no
+CPU path here by design (the CPU oracle lives under oracle/ and is test infrastructure)."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, i32, lib, p, stream
+from .graph import CSRGraph
+
+
+def _f32c(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.to(torch.float32).contiguous()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dgg_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+class _DGGEdge(torch.autograd.Function):
+    """dgm.py:1781-1810 on CSR: scores, degree estimate, in-row ranks, soft first-k."""
+
+    @staticmethod
+    def forward(ctx, y, be, deg_w, deg_b, graph: CSRGraph, noise, hard_k: int):
+        _require_cuda(y, be, deg_w, deg_b)
+        y, be = _f32c(y), _f32c(be)
+        deg_w, deg_b = _f32c(deg_w).reshape(-1), _f32c(deg_b).reshape(-1)
+        n, h = y.shape
+        E = graph.nnz
+        dev = y.device
+        R = torch.empty(E, dtype=torch.float32, device=dev)
+        rank = torch.empty(E, dtype=torch.int32, device=dev)
+        s = torch.empty(n, dtype=torch.float32, device=dev)
+        k = torch.empty(n, dtype=torch.float32, device=dev)
+        out = torch.empty(E, dtype=torch.float32, device=dev)
+        check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.col), i32(n), i32(h), p(y), p(be), p(deg_w),
+                                      p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k), p(out),
+                                      stream()), "dgg_edge_fwd")
+        ctx.graph, ctx.hard_k = graph, hard_k
+        ctx.save_for_backward(y, be, deg_w, deg_b, noise, R, rank, s, k)
+        ctx.mark_non_differentiable(k, R, rank)
+        return out, k, R, rank
+
+    @staticmethod
+    def backward(ctx, g_out, _gk, _gR, _grank):
+        y, be, deg_w, deg_b, noise, R, rank, s, k = ctx.saved_tensors
+        g = ctx.graph
+        n, h = y.shape
+        dy = torch.zeros_like(y)
+        small = torch.zeros(h + 2, dtype=torch.float32, device=y.device)
+        dbe, ddeg = small[:h], small[h:]
+        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.col), i32(n), i32(h), p(y), p(be), p(deg_w), p(deg_b),
+                                      p(noise), i32(ctx.hard_k), p(R), p(rank), p(s), p(k), p(_f32c(g_out)),
+                                      p(dy), p(dbe), p(ddeg), stream()), "dgg_edge_bwd")
+        return dy, dbe, ddeg[0:1].reshape(1, 1), ddeg[1:2], None, None, None
+
+
+def dgg_edge(y, be, deg_w, deg_b, graph, noise=None, hard_k=-1):
+    """-> (out_vals [E], k [N], R [E], rank [E] int32)"""
+    return _DGGEdge.apply(y, be, deg_w, deg_b, graph, noise, hard_k)
+
+
+class _SymNormalize(torch.autograd.Function):
+    """normalize_adj (model.py:1215-1218) on CSR values."""
+
+    @staticmethod
+    def forward(ctx, vals, graph: CSRGraph):
+        _require_cuda(vals)
+        vals = _f32c(vals)
+        dinv = torch.empty(graph.n, dtype=torch.float32, device=vals.device)
+        out = torch.empty_like(vals)
+        check(lib().dggb_sym_normalize_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(graph.n), p(dinv), p(out),
+                                           stream()), "sym_normalize_fwd")
+        ctx.graph = graph
+        ctx.save_for_backward(vals, dinv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        vals, dinv = ctx.saved_tensors
+        gr = ctx.graph
+        t_ws = torch.zeros(gr.n, dtype=torch.float32, device=vals.device)
+        dval = torch.empty_like(vals)
+        check(lib().dggb_sym_normalize_bwd(p(gr.rowptr), p(gr.col), p(vals), i32(gr.n), p(dinv), p(_f32c(g)),
+                                           p(t_ws), p(dval), stream()), "sym_normalize_bwd")
+        return dval, None
+
+
+def sym_normalize(vals, graph):
+    return _SymNormalize.apply(vals, graph)
+
+
+class _Spmm(torch.autograd.Function):
+    """Y = A X (optionally Y_i *= row_scale_i) on CSR (model.py:594, 67)."""
+
+    @staticmethod
+    def forward(ctx, vals, x, graph: CSRGraph, row_scale):
+        _require_cuda(vals, x)
+        vals, x = _f32c(vals), _f32c(x)
+        n, f = graph.n, x.shape[1]
+        y = torch.empty(n, f, dtype=torch.float32, device=x.device)
+        check(lib().dggb_spmm_csr_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(n), p(x), i32(f), p(row_scale),
+                                      p(y), stream()), "spmm_csr_fwd")
+        ctx.graph = graph
+        ctx.save_for_backward(vals, x, row_scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        vals, x, row_scale = ctx.saved_tensors
+        g = ctx.graph
+        need_v, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dval = torch.empty_like(vals) if need_v else None
+        dx = torch.zeros_like(x) if need_x else None
+        check(lib().dggb_spmm_csr_bwd(p(g.rowptr), p(g.col), p(vals), i32(g.n), p(x), i32(x.shape[1]),
+                                      p(row_scale), p(_f32c(gy)), p(dval), p(dx), stream()), "spmm_csr_bwd")
+        return dval, dx, None, None
+
+
+def spmm(vals, x, graph, row_scale=None):
+    return _Spmm.apply(vals, x, graph, row_scale)

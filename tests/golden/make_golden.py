@@ -190,6 +190,8 @@ def main():
     idx_ns, val_ns = make_graph(n, 6, seed=1, self_loops=False)
     out["graph_noself"] = dict(idx=idx_ns, val=val_ns)
     wl = torch.randn(n, nclass, generator=gx)
+    out["graph"]["wl"] = wl
+    out["graph"]["nclass"] = nclass
 
     def run_model(tag, cls, args, call, scale_names=()):
         torch.manual_seed(45)
