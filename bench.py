@@ -376,7 +376,7 @@ def kernel_roofline(m, dsets, shape, iters=30):
     from dgg_b200._lib import check, i32, lib, p, stream
 
     dy = torch.zeros(n, h, device=prepared[0][1].device)
-    small = torch.zeros(h + 2, device=dy.device)
+    small = torch.zeros(h + 4 + n, device=dy.device)
     dw, db = dd.weight.detach().reshape(-1), dd.bias.detach().reshape(-1)
     be = lin.bias.detach()
 
@@ -385,9 +385,9 @@ def kernel_roofline(m, dsets, shape, iters=30):
         out, k, R, rank = saved[i % N_SETS]
         # timing only: the row-sum input `s` is not returned by the autograd wrapper, `k` stands in
         # for it (same size, same access pattern)
-        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.col), i32(n), i32(h), p(y), p(be), p(dw), p(db), p(None),
-                                      i32(-1), p(R), p(rank), p(k), p(k), p(gv), p(dy), p(small[:h]), p(small[h:]),
-                                      stream()), "bwd")
+        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
+                                      p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(k), p(k), p(gv),
+                                      p(small[h + 4:]), p(dy), p(small[:h]), p(small[h:h + 2]), stream()), "bwd")
 
     t_bwd = timed(bwd)
     # algorithmic bytes (SURVEY 8d, int32 CSR): see DESIGN.md "dgg_edge"

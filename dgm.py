@@ -7,6 +7,8 @@ behind the C-ABI in include/dggb.h (bound in dgg_b200/functional.py).  CUDA tens
 """
 from __future__ import annotations
 
+import math
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -81,3 +83,103 @@ class DGG_Ablations(_EdgeRankerBase):
         keep = (out_vals != 0).nonzero().flatten()
         idx = graph.coo_indices()[:, keep]
         return torch.sparse_coo_tensor(idx, out_vals[keep], (graph.n, graph.n), is_coalesced=True), x_enc
+
+
+class LearnableKEncoder(nn.Module):
+    """Reference dgm.py:2029-2063: k = k_project(k_mu(x)), or a reparameterised latent sample when
+    ``args.stochastic_k`` and training."""
+
+    def __init__(self, in_dim, latent_dim, learn_k_bias=False, args=None):
+        super().__init__()
+        self.learn_k_bias = learn_k_bias
+        self.k_mu = nn.Linear(in_dim, latent_dim)
+        self.k_logvar = nn.Linear(in_dim, latent_dim)
+        self.k_project = nn.Linear(latent_dim, 1)
+        self.args = args
+
+    def latent_sample(self, mu, logvar):
+        if self.training:
+            std = logvar.mul(0.5).exp_()
+            return torch.empty_like(std).normal_().mul(std).add_(mu)
+        return mu
+
+    def forward(self, x):
+        if self.args.stochastic_k:
+            latent_k = self.latent_sample(self.k_mu(x), self.k_logvar(x))
+        else:
+            latent_k = self.k_mu(x)
+        return self.k_project(latent_k)
+
+
+class DGG_LearnableK_SDD(nn.Module):
+    """All-pairs DGG (reference dgm.py:185-351, ``dist_fn="metric"``), the north star's
+    "N x N pairwise score + Gumbel + soft top-k" path, without ever forming N x N:
+
+        z = softmax(LeakyReLU(x W + b));  y_ij = -t |z_i - z_j| + G_ij;  r = descending rank in row i;
+        k_i = k_net(x_i) + k_bias;        adj_ij = y_ij * sigmoid(hs_start - interval r + (k_i - 1) interval)
+
+    The first-k sigmoid is exactly 0 in fp32 for r > k + 11.96, so only the top ceil(k_max + 12.6)
+    entries per row can be non-zero: they are selected by a fused tcgen05 GEMM + streaming top-K kernel.
+    forward(x [B,N,F] or [N,F], temp, noise) -> (sparse COO adjacency [N,N] (list if B > 1), k [B,N,1]).
+    ``noise``: True -> Gumbel(0,1) noise (sampled on device, or the tensor set via ``set_noise``);
+    False -> softmax(log_p / temp) scores (evaluation branch, dgm.py:298)."""
+
+    K_WINDOW = 12.6   # fp32 saturation window of sigmoid(2 - 7 (r - k + 1)) (SURVEY 7.3)
+    KC_MAX = 64
+
+    def __init__(self, in_dim=32, latent_dim=64, k_bias=1.0, hard=False, self_loops_noise=False, dist_fn="metric",
+                 k_net_input="raw", hs_start=2, hs_end=-5, n_agents=None, learn_k_bias=None, args=None):
+        super().__init__()
+        torch.manual_seed(0)                                  # reference side effect (dgm.py:207)
+        if dist_fn != "metric":
+            raise NotImplementedError("only dist_fn='metric' is supported (the 'mlp' branch is log_p == 0)")
+        self.in_dim, self.latent_dim = in_dim, latent_dim
+        self.hard, self.self_loops_noise = hard, self_loops_noise
+        self.dist_fn, self.k_net_input = dist_fn, k_net_input
+        self.input_project = nn.Sequential(nn.Linear(in_dim, latent_dim), nn.LeakyReLU(), nn.Softmax(dim=-1))
+        self.t = nn.Parameter(torch.ones(1))
+        self.register_buffer("interval", torch.tensor(hs_start - hs_end))
+        self.register_buffer("k_bias", torch.tensor(k_bias))
+        self.register_buffer("hs_start", torch.tensor(hs_start))
+        self.register_buffer("hs_end", torch.tensor(hs_end))
+        import argparse
+        kargs = args if args is not None else argparse.Namespace(stochastic_k=False)
+        self.k_net = LearnableKEncoder(in_dim=in_dim if k_net_input == "raw" else latent_dim,
+                                       latent_dim=latent_dim, args=kargs)
+        self._noise = None
+        self.precision = 3
+
+    def set_noise(self, G):
+        """Inject the Gumbel tensor [N,N] used by the next forward (parity tests; the reference's
+        injection point is ``gumbel_sample``, dgm.py:14)."""
+        self._noise = G
+
+    def _one(self, x, temp, noise):
+        n = x.shape[0]
+        z = self.input_project(x)
+        k = self.k_net(x if self.k_net_input == "raw" else z) + self.k_bias          # [N,1]
+        k_max = float(k.detach().max())
+        kc = int(min(self.KC_MAX, n, max(1.0, math.ceil(k_max + self.K_WINDOW))))
+        if k_max + self.K_WINDOW > self.KC_MAX and n > self.KC_MAX:
+            raise RuntimeError("DGG_LearnableK_SDD: a row needs more than %d selected entries (k_max=%.1f)"
+                               % (self.KC_MAX, k_max))
+        if noise:
+            G = self._noise if self._noise is not None else sample_gumbel_from_uniform((n, n))
+            idx, y = K.allpairs_topk(z, self.t, G, kc, self.precision)
+        else:
+            raise NotImplementedError("evaluation (softmax) branch lands with the fused softmax epilogue")
+        r = torch.arange(kc, device=x.device, dtype=torch.float32).reshape(1, kc)
+        first_k = torch.sigmoid(self.hs_start - self.interval * r + (k - 1) * self.interval)   # dgm.py:315-326
+        vals = y * first_k
+        rows = torch.arange(n, device=x.device).reshape(n, 1).expand(n, kc)
+        keep = idx >= 0
+        adj = torch.sparse_coo_tensor(torch.stack([rows[keep], idx[keep].long()]), vals[keep], (n, n))
+        return adj, k
+
+    def forward(self, x, temp, noise=True):
+        if x.dim() == 2:
+            adj, k = self._one(x, temp, noise)
+            return adj, k.unsqueeze(0)
+        outs = [self._one(xb, temp, noise) for xb in x]
+        adjs = [a for a, _ in outs]
+        return (adjs[0] if len(adjs) == 1 else adjs), torch.stack([k for _, k in outs])

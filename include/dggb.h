@@ -54,6 +54,9 @@ int dggb_coo_rows_to_rowptr(const int64_t* row, int64_t nnz, int32_t n, int32_t*
 /* int64 -> int32 column indices. */
 int dggb_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, void* stream);
 
+/* erow[e] = row of CSR entry e (the COO row array, int32). */
+int dggb_csr_expand_rows(const int32_t* rowptr, int32_t n, int32_t* erow, void* stream);
+
 /* CSR + I: per row, add 1.0 to an existing diagonal entry or insert a new one.
  * Two phases so the caller can size the output: phase 1 writes out_rowptr[N+1];
  * the caller reads out_rowptr[N] (nnz_out) and allocates; phase 2 fills col/val. */
@@ -74,12 +77,14 @@ int dggb_add_self_loops_fill(const int32_t* rowptr, const int32_t* col, const fl
  *   out_e  = R_e * ( (1 - 0.5*(1 + tanh(r_e - k_i))) + 1 )                       (1798-1810)
  *   [hard_k >= 0: out_e = r_e < hard_k ? R_e : 0 and k is not computed]          (1943-1945)
  *
- * The dense N x N scatter, the N-long row sort and the un-sort scatter of the reference
+ * Two launches: an edge-parallel score pass (balanced under power-law degrees) and a
+ * warp-per-row rank pass.  The dense N x N scatter, the N-long row sort and the un-sort scatter of the reference
  * are not performed: off-support entries are exact zeros that sort last, so the rank
  * inside the row's own edges is the rank in the dense row.
  * Requires H % 4 == 0.
  * ---------------------------------------------------------------------------------- */
-int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* col, int32_t n, int32_t h,
+int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow /* [E] row of each entry */,
+                      const int32_t* col, int32_t n, int32_t nnz, int32_t h,
                       const float* y /* [N,H] */, const float* be /* [H] */,
                       const float* deg_w /* [1] */, const float* deg_b /* [1] */,
                       const float* ablation_noise /* [E] or NULL */, int32_t hard_k /* <0: soft */,
@@ -88,12 +93,14 @@ int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* col, int32_t n, int3
                       void* stream);
 
 /* Backward of the above w.r.t. y, be, deg_w, deg_b given g_out = dL/d out.
- * dy[N,H], dbe[H], ddeg[2] (= {d deg_w, d deg_b}) are ACCUMULATED INTO. */
-int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* col, int32_t n, int32_t h,
+ * dy[N,H], dbe[H], ddeg[2] (= {d deg_w, d deg_b}) are ACCUMULATED INTO; ds_ws[N] is scratch.
+ * The per-edge pre-activations are recomputed from y, never stored. */
+int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
+                      int32_t nnz, int32_t h,
                       const float* y, const float* be, const float* deg_w, const float* deg_b,
                       const float* ablation_noise, int32_t hard_k,
                       const float* R, const int32_t* rank, const float* s, const float* k,
-                      const float* g_out /* [E] */,
+                      const float* g_out /* [E] */, float* ds_ws /* [N] scratch */,
                       float* dy, float* dbe, float* ddeg, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -122,6 +129,35 @@ int dggb_spmm_csr_fwd(const int32_t* rowptr, const int32_t* col, const float* va
 int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
                       const float* x, int32_t f, const float* row_scale, const float* dy,
                       float* dval, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * All-pairs scoring + per-row streaming top-K (legacy all-pairs DGG, dgm.py:271-301; a15):
+ *
+ *   y_ij = -t * || z_i - z_j ||_2  [+ noise_ij]          (cdist -> exp -> log -> + Gumbel)
+ *   per query row: the Kc largest y_ij, sorted descending (ties: lower column first), i.e.
+ *   the first Kc columns of torch.sort(y, descending=True) -- the only ones the soft first-k
+ *   curve leaves non-zero.
+ *
+ * Z Z^T runs on the tcgen05 tensor cores (kind::tf32; precision = 3: 3xTF32 split, ~fp32
+ * accuracy; precision = 1: single TF32 pass), operands staged by TMA, accumulators in TMEM;
+ * the epilogue fuses norms, sqrt, temperature, noise and the selection.  No N x N matrix is
+ * written.  Rows [row_begin, row_begin+row_count) are scored against all n columns (row
+ * sharding across GPUs: every rank passes the all-gathered z and its own row block).
+ *   noise: NULL, or [row_count, noise_ld] fp32 (row r of it belongs to query row row_begin+r).
+ *   out_idx/out_val: [row_count, kc]; unused slots (n < kc) hold idx -1 / val 0.
+ *   workspace: dggb_allpairs_workspace_bytes(n, d) bytes (hi/lo split of z + squared norms).
+ * Requires d <= 128, kc <= 64.
+ * ---------------------------------------------------------------------------------- */
+int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d);
+int dggb_allpairs_topk_fwd(const float* z /* [n,d] */, int32_t n, int32_t d, int32_t row_begin,
+                           int32_t row_count, const float* t /* [1] device */, const float* noise,
+                           int64_t noise_ld, int32_t kc, int32_t precision, void* workspace,
+                           int64_t workspace_bytes, int32_t* out_idx, float* out_val, void* stream);
+/* Backward by recomputation over the selected pairs only (O(rows*kc*d)):
+ * dz[n,d] and dt[1] are ACCUMULATED INTO. */
+int dggb_allpairs_pair_bwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
+                           const int32_t* idx, const float* gy /* [row_count,kc] */, int32_t kc,
+                           const float* t, float* dz, float* dt, void* stream);
 
 #ifdef __cplusplus
 }

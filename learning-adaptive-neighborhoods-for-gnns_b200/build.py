@@ -38,10 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libdggb.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources() + ["-lcuda"]
-    stubs = "/usr/local/cuda/lib64/stubs"
-    if os.path.isdir(stubs):
-        cmd += ["-L", stubs]
+    # no -lcuda: the one driver call (cuTensorMapEncodeTiled) is resolved through cudaGetDriverEntryPoint
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

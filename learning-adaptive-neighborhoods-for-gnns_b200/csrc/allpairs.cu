@@ -1,0 +1,438 @@
+// All-pairs DGG scoring + per-row streaming top-K (north-star subsystems 1+2), and the sparse
+// recompute backward (subsystem 3).
+//
+// Replaces the reference's dense pipeline  torch.cdist(z, z) -> exp(-t D) -> log -> + Gumbel ->
+// torch.sort(N x N) (dgm.py:275-301)  with one kernel that never materialises N x N:
+//
+//   S = Z Z^T on the 5th-gen tensor cores (tcgen05.mma kind::tf32, 3xTF32 split => ~fp32 accuracy),
+//   operands staged by TMA (128-B swizzle), accumulators double-buffered in TMEM;
+//   epilogue (one thread per query row, TMEM lane == row):  d2 = |zi|^2 + |zj|^2 - 2 S,
+//   y = -t sqrt(max(d2,0)) [+ G_ij], threshold-pruned insertion into the row's sorted top-Kc list
+//   held in shared memory.  Output: idx/val [rows, Kc] sorted descending (rank == position).
+//
+// Per CTA: 128 query rows x all N columns in tiles of 64.  Warp roles: w0 TMA producer, w1 MMA issuer
+// (+ TMEM owner), w2..w5 epilogue.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace dggb {
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor map through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int make_tmap_2d_f32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                     uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return DGGB_ERR_CUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = (int)r;
+    return DGGB_ERR_CUDA;
+  }
+  return DGGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pre-pass: z -> (hi, lo) TF32 split + squared norms, padded to a multiple of 128 rows with zeros
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256)
+    split_tf32_kernel(const float* __restrict__ z, int n, int npad, int d, int dpad, float* __restrict__ hi,
+                      float* __restrict__ lo, float* __restrict__ nrm) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < npad; i += gridDim.x * 8) {
+    float acc = 0.f;
+    for (int c = lane; c < dpad; c += kWarp) {
+      const float v = (i < n && c < d) ? __ldg(z + (size_t)i * d + c) : 0.f;
+      const float h = to_tf32(v);
+      hi[(size_t)i * dpad + c] = h;
+      lo[(size_t)i * dpad + c] = to_tf32(v - h);
+      acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) nrm[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kBM = 128;  // query rows per CTA (== TMEM lanes)
+constexpr int kBN = 64;   // key columns per tile
+constexpr int kAPThreads = 192;
+
+struct APSmem {  // byte offsets from the 1024-aligned base
+  uint32_t a_hi, a_lo, b0, b_stage_bytes, nrm, vals, idx, bars, total;
+};
+
+__host__ __device__ inline APSmem ap_smem_layout(int kb, int split, int stages, int kc) {
+  APSmem L;
+  const uint32_t a_bytes = kb * kBM * 128;  // [128 rows][128 B] per k-block
+  const uint32_t b_bytes = kb * kBN * 128;
+  uint32_t off = 0;
+  L.a_hi = off; off += a_bytes;
+  L.a_lo = off; off += (split == 3 ? a_bytes : 0);
+  L.b0 = off;
+  L.b_stage_bytes = b_bytes * (split == 3 ? 2 : 1);
+  off += L.b_stage_bytes * stages;
+  L.nrm = off; off += stages * kBN * 4;
+  L.vals = off; off += kc * kBM * 4;
+  L.idx = off; off += kc * kBM * 4;
+  L.bars = off; off += 128;
+  L.total = off;
+  return L;
+}
+
+template <int KB, int SPLIT>
+__global__ void __launch_bounds__(kAPThreads, 1)
+    allpairs_topk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                         const float* __restrict__ nrm, int n, int row_begin, int row_count,
+                         const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
+                         int kc, int stages, int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const APSmem L = ap_smem_layout(KB, SPLIT, stages, kc);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* full = bars;            // [stages]  TMA -> MMA/epilogue
+  uint64_t* empty = bars + 4;       // [stages]  MMA + 4 epilogue warps -> TMA
+  uint64_t* tfull = bars + 8;       // [2]       MMA -> epilogue
+  uint64_t* tempty = bars + 10;     // [2]       epilogue -> MMA
+  uint64_t* afull = bars + 12;      // A tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (n + kBN - 1) / kBN;
+  const int row0 = row_begin + blockIdx.x * kBM;  // first global row of this CTA
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tm_hi);
+    if (SPLIT == 3) tc::tma_prefetch_desc(&tm_lo);
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 5);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tfull + b, 1);
+      tc::mbar_init(tempty + b, 4);
+    }
+    tc::mbar_init(afull, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 2 * kBN);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t a_bytes = KB * kBM * 128 * (SPLIT == 3 ? 2 : 1);
+      tc::mbar_arrive_expect_tx(afull, a_bytes);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int half = 0; half < 2; ++half) {
+          tc::tma_load_2d(smem + L.a_hi + (kb * kBM + half * 64) * 128, &tm_hi, afull, kb * 32, row0 + half * 64);
+          if (SPLIT == 3)
+            tc::tma_load_2d(smem + L.a_lo + (kb * kBM + half * 64) * 128, &tm_lo, afull, kb * 32, row0 + half * 64);
+        }
+      for (int jt = 0; jt < num_tiles; ++jt) {
+        const int s = jt % stages;
+        const uint32_t ph = (jt / stages) & 1;
+        tc::mbar_wait(empty + s, ph ^ 1);
+        tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes + kBN * 4);
+        uint8_t* bs = smem + L.b0 + s * L.b_stage_bytes;
+        for (int kb = 0; kb < KB; ++kb) {
+          tc::tma_load_2d(bs + kb * kBN * 128, &tm_hi, full + s, kb * 32, jt * kBN);
+          if (SPLIT == 3) tc::tma_load_2d(bs + (KB + kb) * kBN * 128, &tm_lo, full + s, kb * 32, jt * kBN);
+        }
+        tc::bulk_load_1d(smem + L.nrm + s * kBN * 4, nrm + (size_t)jt * kBN, kBN * 4, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_tf32(kBM, kBN);
+      tc::mbar_wait(afull, 0);
+      tc::fence_after_sync();
+      const uint32_t a_hi = tc::smem_u32(smem + L.a_hi), a_lo = tc::smem_u32(smem + L.a_lo);
+      for (int jt = 0; jt < num_tiles; ++jt) {
+        const int s = jt % stages;
+        const uint32_t ph = (jt / stages) & 1;
+        const int buf = jt & 1;
+        const uint32_t bph = (jt >> 1) & 1;
+        tc::mbar_wait(tempty + buf, bph ^ 1);
+        tc::mbar_wait(full + s, ph);
+        tc::fence_after_sync();
+        const uint32_t b_hi = tc::smem_u32(smem + L.b0 + s * L.b_stage_bytes);
+        const uint32_t b_lo = b_hi + KB * kBN * 128;
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int sp = 0; sp < SPLIT; ++sp) {
+          const uint32_t a = (sp == 2) ? a_lo : a_hi;   // hi*hi, hi*lo, lo*hi
+          const uint32_t b = (sp == 1) ? b_lo : b_hi;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc::mma_tf32(d_tmem, tc::smem_desc_k128(a + kb * kBM * 128 + ks * 32),
+                           tc::smem_desc_k128(b + kb * kBN * 128 + ks * 32), idesc, acc);
+              acc = 1;
+            }
+        }
+        tc::mma_commit(empty + s);     // smem stage reusable once these MMAs retire
+        tc::mma_commit(tfull + buf);   // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ================= epilogue: thread == query row =================
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int row_t = q * 32 + lane;                // row inside the CTA tile
+    const int lrow = blockIdx.x * kBM + row_t;      // row inside this launch's row block
+    const bool row_ok = lrow < row_count && (row_begin + lrow) < n;
+    const float ni = row_ok ? __ldg(nrm + row_begin + lrow) : 0.f;
+    const float t = __ldg(t_ptr);
+    float* vals = reinterpret_cast<float*>(smem + L.vals);   // [kc][128]
+    int32_t* idxs = reinterpret_cast<int32_t*>(smem + L.idx);
+    for (int r = 0; r < kc; ++r) {
+      vals[r * kBM + row_t] = -INFINITY;
+      idxs[r * kBM + row_t] = -1;
+    }
+    float thr = -INFINITY;
+    const float* nz = (noise && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
+    for (int jt = 0; jt < num_tiles; ++jt) {
+      const int s = jt % stages;
+      const uint32_t ph = (jt / stages) & 1;
+      const int buf = jt & 1;
+      const uint32_t bph = (jt >> 1) & 1;
+      tc::mbar_wait(full + s, ph);      // column norms of this tile are in smem
+      tc::mbar_wait(tfull + buf, bph);  // accumulator ready
+      tc::fence_after_sync();
+      const float* nj = reinterpret_cast<const float*>(smem + L.nrm + s * kBN * 4);
+      // the tile(s) that contain this CTA's own diagonal take the variant that pins d2(i,i) = 0 exactly
+      const bool diag_tile = (jt * kBN < row0 + kBM) && (jt * kBN + kBN > row0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBN; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + c0, r);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+          const int jbase = jt * kBN + c0;
+          auto body = [&](auto diag_c) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int j = jbase + c;
+              float d2 = fmaf(-2.f, __uint_as_float(r[c]), ni + nj[c0 + c]);
+              if (decltype(diag_c)::value && j == row_begin + lrow) d2 = 0.f;
+              float y = -t * sqrtf(fmaxf(d2, 0.f));
+              if (nz != nullptr && j < n) y += __ldg(nz + j);
+              if (j < n && y > thr) {
+                int pos = kc - 1;
+                while (pos > 0 && vals[(pos - 1) * kBM + row_t] < y) {
+                  vals[pos * kBM + row_t] = vals[(pos - 1) * kBM + row_t];
+                  idxs[pos * kBM + row_t] = idxs[(pos - 1) * kBM + row_t];
+                  --pos;
+                }
+                vals[pos * kBM + row_t] = y;
+                idxs[pos * kBM + row_t] = j;
+                thr = vals[(kc - 1) * kBM + row_t];
+              }
+            }
+          };
+          if (diag_tile) body(std::true_type{});
+          else body(std::false_type{});
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(tempty + buf);
+        tc::mbar_arrive(empty + s);
+      }
+    }
+    // ---- write the sorted lists: lanes sweep the list positions of one row at a time ----
+    __syncwarp();
+    for (int rr = 0; rr < 32; ++rr) {
+      const int rt = q * 32 + rr;
+      const int lr = blockIdx.x * kBM + rt;
+      if (lr < row_count && (row_begin + lr) < n) {
+        for (int r = lane; r < kc; r += kWarp) {
+          const int32_t id = idxs[r * kBM + rt];
+          out_idx[(size_t)lr * kc + r] = id;
+          out_val[(size_t)lr * kc + r] = id < 0 ? 0.f : vals[r * kBM + rt];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 2 * kBN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse recompute backward: for every selected pair (i, j) with upstream gy = dL/dy_ij,
+//   y = -t |z_i - z_j|  =>  dt += -D gy ;  g = -t gy / D ;  dz_i += g (z_i - z_j) ;  dz_j -= g (z_i - z_j)
+// (zero gradient at D == 0, like torch.cdist's backward).  O(rows * Kc * d), no N^2 work.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairWarps = 8;
+
+__global__ void __launch_bounds__(kPairWarps* kWarp)
+    allpairs_pair_grad_kernel(const float* __restrict__ z, int n, int d, int L, int row_begin, int row_count,
+                              const int32_t* __restrict__ idx, const float* __restrict__ gy, int kc,
+                              const float* __restrict__ t_ptr, float* __restrict__ dz, float* __restrict__ dt) {
+  const int lane = threadIdx.x & 31;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  const float t = __ldg(t_ptr);
+  float dt_acc = 0.f;
+  for (int lr = blockIdx.x * kPairWarps + (threadIdx.x >> 5); lr < row_count; lr += gridDim.x * kPairWarps) {
+    const int i = row_begin + lr;
+    if (i >= n) continue;
+    const float* zi = z + (size_t)i * d;
+    for (int c0 = 0; c0 < d; c0 += 4 * L) {   // feature chunks of 4*L columns (one float4 per lane)
+      const int c = c0 + 4 * lg;
+      const bool cok = c < d;
+      const float4 a = cok ? ldg4(zi + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r0 = 0; r0 < kc; r0 += G) {
+        const int r = r0 + grp;
+        const int j = (r < kc) ? __ldg(idx + (size_t)lr * kc + r) : -1;
+        const float g_up = (j >= 0) ? __ldg(gy + (size_t)lr * kc + r) : 0.f;
+        // full squared distance needs every chunk: recompute it over all of d (d is small)
+        float dist2 = 0.f;
+        if (j >= 0)
+          for (int cc = 4 * lg; cc < d; cc += 4 * L) {
+            const float4 p = ldg4(zi + cc), qv = ldg4(z + (size_t)j * d + cc);
+            const float dx = p.x - qv.x, dy_ = p.y - qv.y, dz_ = p.z - qv.z, dw = p.w - qv.w;
+            dist2 += dx * dx + dy_ * dy_ + dz_ * dz_ + dw * dw;
+          }
+        dist2 = group_sum(dist2, L);
+        const float dist = sqrtf(dist2);
+        if (c0 == 0 && lg == 0) dt_acc += -dist * g_up;
+        const float g = (dist > 0.f) ? (-t * g_up / dist) : 0.f;
+        if (j >= 0 && cok && g != 0.f) {
+          const float4 b = ldg4(z + (size_t)j * d + c);
+          const float4 dd = make_float4(g * (a.x - b.x), g * (a.y - b.y), g * (a.z - b.z), g * (a.w - b.w));
+          acc.x += dd.x; acc.y += dd.y; acc.z += dd.z; acc.w += dd.w;
+          red_add4(dz + (size_t)j * d + c, make_float4(-dd.x, -dd.y, -dd.z, -dd.w));
+        }
+      }
+      for (int o = L; o < kWarp; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      if (grp == 0 && cok) red_add4(dz + (size_t)i * d + c, acc);
+    }
+  }
+  dt_acc = warp_sum(dt_acc);
+  if (lane == 0 && dt_acc != 0.f) atomicAdd(dt, dt_acc);
+}
+
+}  // namespace dggb
+using namespace dggb;
+
+extern "C" int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d) {
+  if (n < 0 || d <= 0) return DGGB_ERR_BAD_ARG;
+  const int64_t npad = ((int64_t)n + 127) / 128 * 128;
+  const int64_t dpad = ((int64_t)d + 31) / 32 * 32;
+  return npad * dpad * 4 * 2 + npad * 4;
+}
+
+extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
+                                      const float* t, const float* noise, int64_t noise_ld, int32_t kc,
+                                      int32_t precision, void* workspace, int64_t workspace_bytes, int32_t* out_idx,
+                                      float* out_val, void* stream) {
+  if (!z || !t || !workspace || !out_idx || !out_val || n <= 0 || d <= 0 || row_begin < 0 || row_count < 0 || kc <= 0)
+    return DGGB_ERR_BAD_ARG;
+  if (d > 128 || kc > 64) return DGGB_ERR_BAD_SHAPE;
+  if (precision != 1 && precision != 3) return DGGB_ERR_UNSUPPORTED;
+  if (workspace_bytes < dggb_allpairs_workspace_bytes(n, d)) return DGGB_ERR_WORKSPACE;
+  if (row_count == 0) return DGGB_OK;
+  const int npad = (n + 127) / 128 * 128;
+  const int dpad = (d + 31) / 32 * 32;
+  float* hi = reinterpret_cast<float*>(workspace);
+  float* lo = hi + (size_t)npad * dpad;
+  float* nrm = lo + (size_t)npad * dpad;
+  cudaStream_t st = as_stream(stream);
+  split_tf32_kernel<<<rows_grid(npad, 8, 8), 256, 0, st>>>(z, n, npad, d, dpad, hi, lo, nrm);
+  int rc = launch_status();
+  if (rc != DGGB_OK) return rc;
+
+  CUtensorMap tm_hi, tm_lo;
+  rc = make_tmap_2d_f32(&tm_hi, hi, npad, dpad, 64, 32);
+  if (rc != DGGB_OK) return rc;
+  rc = make_tmap_2d_f32(&tm_lo, lo, npad, dpad, 64, 32);
+  if (rc != DGGB_OK) return rc;
+
+  const int kb = dpad / 32;
+  int stages = 4;
+  APSmem L = ap_smem_layout(kb, precision, stages, kc);
+  while (stages > 2 && L.total + 1024 > 227 * 1024) L = ap_smem_layout(kb, precision, --stages, kc);
+  if (L.total + 1024 > 227 * 1024) return DGGB_ERR_BAD_SHAPE;
+  const size_t smem_bytes = L.total + 1024;
+  const int grid = (row_count + kBM - 1) / kBM;
+
+#define DGGB_AP_LAUNCH(KB_, SP_)                                                                                  \
+  do {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(allpairs_topk_kernel<KB_, SP_>,                                          \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);           \
+    if (e != cudaSuccess) return cuda_status(e);                                                                  \
+    allpairs_topk_kernel<KB_, SP_><<<grid, kAPThreads, smem_bytes, st>>>(tm_hi, tm_lo, nrm, n, row_begin,         \
+                                                                         row_count, t, noise, (long long)noise_ld, \
+                                                                         kc, stages, out_idx, out_val);           \
+  } while (0)
+
+  if (kb == 1 && precision == 3) DGGB_AP_LAUNCH(1, 3);
+  else if (kb == 1) DGGB_AP_LAUNCH(1, 1);
+  else if (kb == 2 && precision == 3) DGGB_AP_LAUNCH(2, 3);
+  else if (kb == 2) DGGB_AP_LAUNCH(2, 1);
+  else if (kb == 4 && precision == 1) DGGB_AP_LAUNCH(4, 1);
+  else return DGGB_ERR_BAD_SHAPE;
+#undef DGGB_AP_LAUNCH
+  return launch_status();
+}
+
+extern "C" int dggb_allpairs_pair_bwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
+                                      const int32_t* idx, const float* gy, int32_t kc, const float* t, float* dz,
+                                      float* dt, void* stream) {
+  if (!z || !idx || !gy || !t || !dz || !dt || n <= 0 || d <= 0 || row_count < 0 || kc <= 0) return DGGB_ERR_BAD_ARG;
+  if (d % 4 != 0) return DGGB_ERR_BAD_SHAPE;
+  if (row_count == 0) return DGGB_OK;
+  const int L = pow2_floor32(d / 4);
+  allpairs_pair_grad_kernel<<<rows_grid(row_count, kPairWarps, 8), kPairWarps * kWarp, 0, as_stream(stream)>>>(
+      z, n, d, L, row_begin, row_count, idx, gy, kc, t, dz, dt);
+  return launch_status();
+}

@@ -20,6 +20,16 @@ __global__ void cast_i64_i32(const int64_t* __restrict__ src, int32_t* __restric
     dst[p] = (int32_t)src[p];
 }
 
+// erow[e] = i for every e in [rowptr[i], rowptr[i+1])
+__global__ void csr_expand_rows(const int32_t* __restrict__ rowptr, int n, int32_t* __restrict__ erow) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    for (int e = beg + lane; e < end; e += kWarp) erow[e] = i;
+  }
+}
+
 // out_count[i] = deg_i + (row i has no diagonal entry); out_count[n] = 0 (slot for the scan total)
 __global__ void self_loop_count(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n,
                                 int32_t* __restrict__ out_count) {
@@ -117,6 +127,13 @@ extern "C" int dggb_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, vo
   long long g = (n + block - 1) / block;
   if (g > kNumSMs * 8) g = kNumSMs * 8;
   cast_i64_i32<<<(int)g, block, 0, as_stream(stream)>>>(src, dst, n);
+  return launch_status();
+}
+
+extern "C" int dggb_csr_expand_rows(const int32_t* rowptr, int32_t n, int32_t* erow, void* stream) {
+  if (!rowptr || !erow || n < 0) return DGGB_ERR_BAD_ARG;
+  if (n == 0) return DGGB_OK;
+  csr_expand_rows<<<rows_grid(n, 8, 8), 256, 0, as_stream(stream)>>>(rowptr, n, erow);
   return launch_status();
 }
 

@@ -34,7 +34,7 @@ class _DGGEdge(torch.autograd.Function):
         s = torch.empty(n, dtype=torch.float32, device=dev)
         k = torch.empty(n, dtype=torch.float32, device=dev)
         out = torch.empty(E, dtype=torch.float32, device=dev)
-        check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.col), i32(n), i32(h), p(y), p(be), p(deg_w),
+        check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(h), p(y), p(be), p(deg_w),
                                       p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k), p(out),
                                       stream()), "dgg_edge_fwd")
         ctx.graph, ctx.hard_k = graph, hard_k
@@ -48,11 +48,11 @@ class _DGGEdge(torch.autograd.Function):
         g = ctx.graph
         n, h = y.shape
         dy = torch.zeros_like(y)
-        small = torch.zeros(h + 2, dtype=torch.float32, device=y.device)
-        dbe, ddeg = small[:h], small[h:]
-        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.col), i32(n), i32(h), p(y), p(be), p(deg_w), p(deg_b),
-                                      p(noise), i32(ctx.hard_k), p(R), p(rank), p(s), p(k), p(_f32c(g_out)),
-                                      p(dy), p(dbe), p(ddeg), stream()), "dgg_edge_bwd")
+        small = torch.zeros(h + 4 + n, dtype=torch.float32, device=y.device)   # dbe | ddeg (+pad) | ds scratch
+        dbe, ddeg, ds_ws = small[:h], small[h:h + 2], small[h + 4:]
+        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
+                                      p(deg_w), p(deg_b), p(noise), i32(ctx.hard_k), p(R), p(rank), p(s), p(k),
+                                      p(_f32c(g_out)), p(ds_ws), p(dy), p(dbe), p(ddeg), stream()), "dgg_edge_bwd")
         return dy, dbe, ddeg[0:1].reshape(1, 1), ddeg[1:2], None, None, None
 
 
@@ -120,3 +120,47 @@ class _Spmm(torch.autograd.Function):
 
 def spmm(vals, x, graph, row_scale=None):
     return _Spmm.apply(vals, x, graph, row_scale)
+
+
+class _AllPairsTopK(torch.autograd.Function):
+    """y_ij = -t |z_i - z_j| [+ noise], top-Kc per row, sorted descending (dgm.py:275-301 without N x N)."""
+
+    @staticmethod
+    def forward(ctx, z, t, noise, kc: int, precision: int, row_begin: int, row_count: int):
+        from ._lib import i64
+        _require_cuda(z, t, noise)
+        z, t = _f32c(z), _f32c(t).reshape(-1)
+        n, d = z.shape
+        L = lib()
+        ws_bytes = int(L.dggb_allpairs_workspace_bytes(i32(n), i32(d)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+        idx = torch.empty(row_count, kc, dtype=torch.int32, device=z.device)
+        val = torch.empty(row_count, kc, dtype=torch.float32, device=z.device)
+        if noise is not None:
+            noise = _f32c(noise)
+            assert noise.dim() == 2 and noise.shape[0] == row_count and noise.shape[1] >= n
+        check(L.dggb_allpairs_topk_fwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(t), p(noise),
+                                       i64(0 if noise is None else noise.stride(0)), i32(kc), i32(precision), p(ws),
+                                       i64(ws_bytes), p(idx), p(val), stream()), "allpairs_topk_fwd")
+        ctx.meta = (kc, row_begin, row_count)
+        ctx.save_for_backward(z, t, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx, val
+
+    @staticmethod
+    def backward(ctx, _gidx, gy):
+        z, t, idx = ctx.saved_tensors
+        kc, row_begin, row_count = ctx.meta
+        n, d = z.shape
+        dz = torch.zeros_like(z)
+        dt = torch.zeros(1, dtype=torch.float32, device=z.device)
+        check(lib().dggb_allpairs_pair_bwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(idx),
+                                           p(_f32c(gy)), i32(kc), p(t), p(dz), p(dt), stream()), "allpairs_pair_bwd")
+        return dz, dt, None, None, None, None, None
+
+
+def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=None):
+    """-> (idx int32 [rows,kc], y fp32 [rows,kc]) sorted descending per row; differentiable in z and t."""
+    if row_count is None:
+        row_count = z.shape[0] - row_begin
+    return _AllPairsTopK.apply(z, t, noise, int(kc), int(precision), int(row_begin), int(row_count))

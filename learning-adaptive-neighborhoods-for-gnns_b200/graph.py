@@ -16,7 +16,7 @@ from ._lib import check, i32, i64, lib, p, stream
 class CSRGraph:
     """rowptr int32 [n+1], col int32 [nnz]; rows sorted by column (coalesced COO order)."""
 
-    __slots__ = ("n", "nnz", "rowptr", "col", "indices", "_loops")
+    __slots__ = ("n", "nnz", "rowptr", "col", "indices", "_loops", "_erow")
 
     def __init__(self, n, rowptr, col, indices=None):
         self.n = int(n)
@@ -25,6 +25,15 @@ class CSRGraph:
         self.col = col
         self.indices = indices  # int64 [2, nnz] (built lazily for COO export)
         self._loops = None
+        self._erow = None
+
+    @property
+    def erow(self) -> torch.Tensor:
+        """int32 [nnz] row index of every entry (built once per structure)."""
+        if self._erow is None:
+            self._erow = torch.empty(self.nnz, dtype=torch.int32, device=self.col.device)
+            check(lib().dggb_csr_expand_rows(p(self.rowptr), i32(self.n), p(self._erow), stream()), "csr_expand_rows")
+        return self._erow
 
     # ------------------------------------------------------------------ construction
     @staticmethod

@@ -24,5 +24,5 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     assert L.dggb_spmm_csr_fwd(null, null, null, i32(4), null, i32(8), null, null, null) == -1
     assert L.dggb_sym_normalize_fwd(null, null, null, i32(4), null, null, null) == -1
     one = ctypes.c_void_p(16)  # never dereferenced: shape check fires first
-    assert L.dggb_dgg_edge_fwd(one, one, i32(4), i32(6), one, one, one, one, null, i32(-1), one, one, one, one,
-                               one, null) == -2
+    assert L.dggb_dgg_edge_fwd(one, one, one, i32(4), i32(9), i32(6), one, one, one, one, null, i32(-1), one, one,
+                               one, one, one, null) == -2
