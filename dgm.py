@@ -183,3 +183,164 @@ class DGG_LearnableK_SDD(nn.Module):
         outs = [self._one(xb, temp, noise) for xb in x]
         adjs = [a for a, _ in outs]
         return (adjs[0] if len(adjs) == 1 else adjs), torch.stack([k for _, k in outs])
+
+
+class DGG_LearnableK_debug(nn.Module):
+    """Reference dgm.py:1077-1727, CSR-resident.  Same parameters (every sub-module of the reference
+    exists, used or not, so ``state_dict`` round-trips), same ``args`` surface, same modes:
+
+    edge net (dgm.py:1596-1727): u-v-dist, u-v-A_uv, u-v-deg, u-v-deg-dist, edge_conv, A_uv
+    k net    (dgm.py:1472-1586): pass, learn_normalized_degree, input_deg, gcn-x-deg, x
+    select   (dgm.py:1352-1435): k_times_edge_prob, edge_p-cdf (identity on the edge probabilities)
+
+    The dense [N,N] scatter / sort / un-sort of the reference is replaced by in-row ranking on the CSR
+    support (off-support entries are exact zeros that sort last).  Entries whose soft first-k weight
+    saturates to exactly 0 stay in the returned support as explicit zeros (``to_dense()`` and all
+    gradients are identical to the reference, which drops them in ``to_sparse()``).
+    Not covered in this round: ``perturb_edge_prob=True`` (needs the N-wide noise scan), ``k_only``
+    and ``dgg_hard`` (buggy / nondeterministic in the reference) -- they raise."""
+
+    def __init__(self, in_dim=32, latent_dim=64, args=None):
+        super().__init__()
+        self.in_dim, self.latent_dim = in_dim, latent_dim
+        self.extra_edge_dim = args.extra_edge_dim
+        self.extra_k_dim = args.extra_k_dim
+        self.hard = args.dgg_hard
+        self.deg_mean, self.deg_std = args.deg_mean, args.deg_std
+        self.node_encode_for_edges = nn.Sequential(nn.Linear(in_dim, latent_dim), nn.LeakyReLU())
+        self.edge_encode = nn.Sequential(
+            nn.Linear(latent_dim * 2 + self.extra_edge_dim, latent_dim), nn.LeakyReLU(), nn.Linear(latent_dim, 1))
+        self.t = nn.Parameter(torch.tensor(-0.1))
+        self.edge_conv_phi = nn.Linear(latent_dim, latent_dim // 2)
+        self.edge_conv_theta = nn.Linear(latent_dim, latent_dim // 2)
+        self.edge_conv_encode = nn.Linear(latent_dim // 2, 1)
+        self.edge_prob_net_mode = args.dgg_mode_edge_net
+        self.input_degree_decode = nn.Linear(3, 1, bias=True)
+        self.combine_input_degree = nn.Sequential(nn.Linear(latent_dim + 3, latent_dim), nn.LeakyReLU())
+        self.adj_project = nn.Linear(1, 1)
+        self.k_net_mode = args.dgg_mode_k_net
+        self.signal_project = nn.Linear(256, 1, bias=True)
+        self.input_degree_project = nn.Linear(1, 3, bias=True)
+        self.node_encode_for_k = nn.Sequential(nn.Linear(in_dim, latent_dim), nn.LeakyReLU())
+        self.k_embed = nn.Sequential(nn.Linear(latent_dim + self.extra_k_dim, latent_dim // 2), nn.LeakyReLU())
+        self.k_W = nn.Parameter(torch.rand(latent_dim, latent_dim, requires_grad=True))
+        if self.k_net_mode in ("input_deg", "learn_normalized_degree"):
+            self.k_net = LearnableKEncoder(in_dim=3, latent_dim=latent_dim // 4, args=args)
+        else:
+            self.k_net = LearnableKEncoder(in_dim=latent_dim // 2, latent_dim=latent_dim // 4, args=args)
+        self.k_select_mode = args.dgg_mode_k_select
+        self.gumbel = torch.distributions.Gumbel(loc=torch.tensor(0.0), scale=torch.tensor(0.3))
+        self.var_grads = {"edge_p": [], "first_k": [], "out_adj": []}
+        self.args = args
+
+    def hook(self, grad):
+        return grad
+
+    def normalize_adj(self, A_hat):
+        if A_hat.is_sparse:
+            g, v = CSRGraph.from_coo(A_hat)
+            return g.to_coo(K.sym_normalize(v, g))
+        row_sum = A_hat.sum(-1) ** -0.5
+        return row_sum.unsqueeze(-1) * A_hat * row_sum.unsqueeze(0)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, in_adj, noise=True, writer=None, epoch=None):
+        assert x.ndim == 2
+        assert len(in_adj.shape) == 2
+        graph, vals = CSRGraph.from_coo(in_adj)
+        n = x.shape[-2]
+        edge_p = self.edge_prob_net(graph, vals, x, mode=self.edge_prob_net_mode)         # [E]
+        if self.args.debug_step == 0:
+            return self.return_hard_or_soft(graph, edge_p)
+        if self.args.perturb_edge_prob:
+            raise NotImplementedError("perturb_edge_prob=True is not covered yet (see class docstring)")
+        pert = edge_p
+        if self.args.debug_step == 1:
+            return self.return_hard_or_soft(graph, pert)
+        k = self.k_estimate_net(n, graph, vals, x, pert, mode=self.k_net_mode)             # [N] or None
+        out = self.select_top_k(graph, k, pert, mode=self.k_select_mode, writer=writer, epoch=epoch)
+        if writer is not None:
+            self.get_adj_diff_stats(graph, vals, out, k, writer=writer, epoch=epoch)
+        self.last_k = k
+        return self.return_hard_or_soft(graph, out)
+
+    def return_hard_or_soft(self, graph, edge_vals, idxs=None, k=None, threshold=0.8):
+        if self.hard:
+            raise NotImplementedError("dgg_hard: the reference's hard branch scatters un-sorted values through "
+                                      "sorted indices (SURVEY 2.3); it is fenced off, not reproduced")
+        return graph.to_coo(edge_vals)
+
+    def get_adj_diff_stats(self, graph, in_vals, out_vals, k=None, writer=None, epoch=None):
+        """TensorBoard stats of dgm.py:1313-1350 computed on the support only (the reference builds ~8
+        dense N x N temporaries for them on every forward, even with writer=None)."""
+        diff = (in_vals - out_vals).detach()
+        diff = diff[diff != 0]
+        if self.training and writer is not None:
+            writer.add_scalar("train_stats/on_edge_mean", diff.mean(), epoch)
+            writer.add_scalar("train_stats/on_edge_std", diff.std(), epoch)
+            deg = K.row_sum(in_vals.detach(), graph)
+            writer.add_scalar("train_stats/in_deg_mean", deg.mean(), epoch)
+            if k is not None:
+                writer.add_scalar("train_stats/k_diff_mean", (k.detach().flatten() - deg).mean(), epoch)
+                writer.add_scalar("train_stats/k_mean", k.detach().mean(), epoch)
+
+    # ------------------------------------------------------------------ top-k selector (dgm.py:1352-1435)
+    def select_top_k(self, graph, k, pert_edge_p, mode="k_times_edge_prob", writer=None, epoch=None):
+        if mode == "edge_p-cdf":
+            # the reference scatters the *unweighted* sorted values back (dgm.py:1400): identity
+            return pert_edge_p
+        if mode == "k_times_edge_prob":
+            if k is None:
+                raise TypeError("unsupported operand type(s) for -: 'Tensor' and 'NoneType'")  # dgm.py:1413
+            return K.row_firstk(pert_edge_p, k.reshape(-1), graph)
+        raise NotImplementedError("dgg_mode_k_select=%r is not covered (see class docstring)" % (mode,))
+
+    # ------------------------------------------------------------------ degree estimator (dgm.py:1472-1586)
+    def k_estimate_net(self, N, graph, vals, x, edge_p, mode="calculate"):
+        if mode == "pass":
+            return None
+        in_deg = K.row_sum(vals, graph).reshape(-1, 1)                                     # [N,1]
+        if mode == "learn_normalized_degree":
+            mu, var = in_deg.mean(), in_deg.std()
+            d = self.k_net(self.input_degree_project((in_deg - mu) / var))
+            return F.relu(d * var + mu) + 1.0
+        if mode == "input_deg":
+            mu, var = self.deg_mean, self.deg_std
+            d = self.k_net(self.input_degree_project((in_deg - mu) / (var + 1e-5)))
+            return F.relu(d * var + mu) + 1.0
+        if mode in ("gcn-x-deg", "x"):
+            xe = self.node_encode_for_k(x)
+            if mode == "gcn-x-deg":
+                nv = K.sym_normalize(vals, graph)
+                xe = torch.relu(K.spmm(nv, xe, graph) @ self.k_W)
+            mu, var = in_deg.mean(), in_deg.std()
+            feats = torch.cat([xe, (in_deg - mu) / (var + 1e-5)], dim=-1)
+            d = self.k_net(self.k_embed(feats))
+            return F.relu(d * var + mu) + 1.0
+        if mode == "calculate":
+            return (in_deg / N) * 2 - 1
+        raise Exception("mode not found")
+
+    # ------------------------------------------------------------------ edge probabilities (dgm.py:1596-1727)
+    def edge_prob_net(self, graph, vals, x, mode=None):
+        if mode == "A_uv":
+            return torch.sigmoid(self.adj_project(vals.unsqueeze(-1)).flatten())
+        if mode not in ("u-v-dist", "u-v-A_uv", "u-v-deg", "u-v-deg-dist", "edge_conv"):
+            raise Exception("mode not found")
+        idx = graph.coo_indices()
+        xe = self.node_encode_for_edges(x)
+        u, v = xe[idx[0]], xe[idx[1]]
+        if mode == "u-v-dist":
+            return torch.exp(-0.05 * torch.linalg.vector_norm(u - v, dim=-1, ord=2))
+        if mode == "edge_conv":
+            feat = self.edge_conv_theta(v - u) + self.edge_conv_phi(u)
+            return torch.sigmoid(self.edge_conv_encode(feat).flatten())
+        if mode == "u-v-A_uv":
+            feat = torch.cat([u, v, vals.unsqueeze(-1)], dim=-1)
+        else:
+            deg = K.row_sum(vals, graph).reshape(-1, 1)                                    # raw degrees (1653)
+            extra = [deg[idx[0]], deg[idx[1]]]
+            if mode == "u-v-deg-dist":
+                extra.append(torch.exp(-1.0 * torch.linalg.vector_norm(u - v, dim=-1, ord=2)).unsqueeze(-1))
+            feat = torch.cat([u, v] + extra, dim=-1)
+        return torch.sigmoid(self.edge_encode(feat).flatten())

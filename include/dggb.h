@@ -104,6 +104,20 @@ int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, const int32_t*
                       float* dy, float* dbe, float* ddeg, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * select_top_k of DGG_LearnableK_debug, mode "k_times_edge_prob" (dgm.py:1402-1421; a10, A.2)
+ * on CSR rows with an externally estimated k [N]:
+ *   out_e = score_e * (1 - 0.5*(1 + tanh(r_e - k_i))),  r_e = descending in-row rank of score_e.
+ * Exact zeros (tanh saturated) stay in the support as explicit zeros.
+ * bwd: dscore_e = g_e * fk_e;  dk_i = 0.5 * sum_e g_e score_e sech^2(r_e - k_i)  (both OVERWRITTEN).
+ * ---------------------------------------------------------------------------------- */
+int dggb_row_firstk_fwd(const int32_t* rowptr, int32_t n, const float* score /* [E] */,
+                        const float* k /* [N] */, int32_t* rank /* [E] out */, float* out /* [E] out */,
+                        void* stream);
+int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float* score, const float* k,
+                        const int32_t* rank, const float* g_out, float* dscore /* [E] */,
+                        float* dk /* [N] */, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * normalize_adj: Ahat_ij = A_ij * s_i^-1/2 * s_j^-1/2 with s = ROW sums on both sides
  * (model.py:1215-1218, 146-149, 687-690, 1347-1350; dgm.py:1172-1175; a13, A.6).
  * Replaces diag + two dense N^3 torch.mm with O(nnz) work.

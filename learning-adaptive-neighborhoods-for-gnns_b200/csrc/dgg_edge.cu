@@ -274,6 +274,51 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// select_top_k of DGG_LearnableK_debug on CSR rows (dgm.py:1402-1421, A.2): k is an input,
+//   fk(r) = 1 - 0.5 * (1 + tanh(r - k_i));  mode 0: out = score * fk (k_times_edge_prob)
+// Off-support entries are exact zeros that sort after every positive score, so in-row ranks are exact.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float first_k_tanh(float r, float k) { return 1.f - 0.5f * (1.f + tanhf(r - k)); }
+
+__global__ void __launch_bounds__(kEdgeWarps* kWarp)
+    row_firstk_fwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
+                          const float* __restrict__ k_in, int32_t* __restrict__ rank, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kEdgeWarps) {
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1), deg = end - beg;
+    const float k = __ldg(k_in + i);
+    for (int mb = 0; mb < deg; mb += kWarp) {
+      const int m = mb + lane;
+      const int r = warp_rank(score, beg, deg, m, lane);
+      if (m < deg) {
+        rank[beg + m] = r;
+        out[beg + m] = __ldg(score + beg + m) * first_k_tanh((float)r, k);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kEdgeWarps* kWarp)
+    row_firstk_bwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
+                          const float* __restrict__ k_in, const int32_t* __restrict__ rank,
+                          const float* __restrict__ g_out, float* __restrict__ dscore, float* __restrict__ dk) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kEdgeWarps) {
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    const float k = __ldg(k_in + i);
+    float acc = 0.f;
+    for (int e = beg + lane; e < end; e += kWarp) {
+      const float th = tanhf((float)__ldg(rank + e) - k);
+      const float g = __ldg(g_out + e);
+      dscore[e] = g * (1.f - 0.5f * (1.f + th));
+      acc += g * __ldg(score + e) * 0.5f * (1.f - th * th);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dk[i] = acc;
+  }
+}
+
 template <typename F>
 static int dispatch_T(int h, int L, F&& f) {
   const int T = (h + 4 * L - 1) / (4 * L);
@@ -342,4 +387,23 @@ extern "C" int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, con
         erow, col, nnz, h, L, y, be, ablation_noise, hard_k, R, rank, k, ds_ws, g_out, dy, dbe);
     return launch_status();
   });
+}
+
+extern "C" int dggb_row_firstk_fwd(const int32_t* rowptr, int32_t n, const float* score, const float* k,
+                                   int32_t* rank, float* out, void* stream) {
+  if (!rowptr || !score || !k || !rank || !out || n < 0) return DGGB_ERR_BAD_ARG;
+  if (n == 0) return DGGB_OK;
+  row_firstk_fwd_kernel<<<rows_grid(n, kEdgeWarps, 8), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(rowptr, n, score,
+                                                                                                 k, rank, out);
+  return launch_status();
+}
+
+extern "C" int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float* score, const float* k,
+                                   const int32_t* rank, const float* g_out, float* dscore, float* dk,
+                                   void* stream) {
+  if (!rowptr || !score || !k || !rank || !g_out || !dscore || !dk || n < 0) return DGGB_ERR_BAD_ARG;
+  if (n == 0) return DGGB_OK;
+  row_firstk_bwd_kernel<<<rows_grid(n, kEdgeWarps, 8), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(
+      rowptr, n, score, k, rank, g_out, dscore, dk);
+  return launch_status();
 }

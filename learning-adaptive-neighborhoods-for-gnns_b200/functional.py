@@ -164,3 +164,41 @@ def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=N
     if row_count is None:
         row_count = z.shape[0] - row_begin
     return _AllPairsTopK.apply(z, t, noise, int(kc), int(precision), int(row_begin), int(row_count))
+
+
+class _RowFirstK(torch.autograd.Function):
+    """select_top_k(mode="k_times_edge_prob") on CSR rows (dgm.py:1402-1421)."""
+
+    @staticmethod
+    def forward(ctx, score, k, graph: CSRGraph):
+        _require_cuda(score, k)
+        score, k = _f32c(score), _f32c(k).reshape(-1)
+        rank = torch.empty(graph.nnz, dtype=torch.int32, device=score.device)
+        out = torch.empty_like(score)
+        check(lib().dggb_row_firstk_fwd(p(graph.rowptr), i32(graph.n), p(score), p(k), p(rank), p(out), stream()),
+              "row_firstk_fwd")
+        ctx.graph = graph
+        ctx.save_for_backward(score, k, rank)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        score, k, rank = ctx.saved_tensors
+        gr = ctx.graph
+        dscore = torch.empty_like(score)
+        dk = torch.empty_like(k)
+        check(lib().dggb_row_firstk_bwd(p(gr.rowptr), i32(gr.n), p(score), p(k), p(rank), p(_f32c(g)), p(dscore),
+                                        p(dk), stream()), "row_firstk_bwd")
+        return dscore, dk, None
+
+
+def row_firstk(score, k, graph):
+    """out_e = score_e * (1 - 0.5 (1 + tanh(rank_e - k_row)))"""
+    return _RowFirstK.apply(score, k, graph)
+
+
+def row_sum(vals, graph):
+    """Row sums of a CSR matrix (in_adj.to_dense().sum(-1), dgm.py:1568) without densifying."""
+    ones = torch.ones(graph.n, 1, dtype=torch.float32, device=vals.device)
+    # every column index is < n, so A @ 1 with the SpMM kernel is the row sum
+    return spmm(vals, ones, graph).reshape(-1)

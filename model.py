@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from dgg_b200 import CSRGraph
 from dgg_b200 import functional as K
-from dgm import DGG, DGG_Ablations
+from dgm import DGG, DGG_Ablations, DGG_LearnableK_debug
 
 
 # --------------------------------------------------------------------------- helpers
@@ -61,6 +61,9 @@ class GCNConv(nn.Module):
         self.W = nn.Parameter(torch.rand(in_channels, out_channels, requires_grad=True))
 
     def forward(self, x, adj):
+        if x.shape[1] > self.W.shape[1]:
+            # (A x) W == A (x W): aggregate in the narrower space (model.py:594-596 order otherwise)
+            return torch.relu(_aggregate(adj, torch.mm(x, self.W)))
         return torch.relu(torch.mm(_aggregate(adj, x), self.W))
 
 
@@ -112,3 +115,400 @@ class GCN_DGG_Ablations(GCN_DGG_00):
 
     def dgg_net(self, x, i, unnorm_adj, writer, epoch):
         return self.dggs[i](x=x, adj=unnorm_adj, writer=writer, epoch=epoch)
+
+
+class GCN_DGG_00_LargeGraphs(GCN_DGG_00):
+    """Reference model.py:1691-1798: as GCN_DGG_00 with a sigmoid head and (out, adj, None)."""
+
+    def forward(self, x, in_adj, noise=True, epoch=None, writer=None, **kwargs):
+        in_adj = add_self_loops_coo(in_adj)
+        unnorm_adj = in_adj
+        for i, conv in enumerate(self.convs):
+            if i < len(self.dggs):
+                src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
+                unnorm_adj, x_dgg = self.dgg_net(x, i, src, writer, epoch)
+                norm_adj = self.normalize_adj(unnorm_adj)
+                x = x_dgg
+            x = conv(x + x_dgg, norm_adj)
+            if i < len(self.convs) - 1:
+                x = F.dropout(x, training=self.training)
+            if writer is not None:
+                writer.add_histogram("gcn_conv{}_dist".format(i + 1), x, epoch)
+        return torch.sigmoid(x), unnorm_adj, None
+
+
+class GCN_DGG(torch.nn.Module, _NormalizeMixin):
+    """Reference model.py:1183-1311 (DGG_LearnableK_debug inside, convs on the raw features)."""
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, args=None, **kwargs):
+        super().__init__()
+        self.convs = nn.ModuleList()
+        self.conv1 = GCNConv(nfeat, nhidden)
+        self.conv2 = GCNConv(nhidden, nclass)
+        self.convs.append(self.conv1)
+        self.convs.append(self.conv2)
+        self.dgg_adj_input = args.dgg_adj_input
+        self.dggs = nn.ModuleList()
+        self.dggs.append(DGG_LearnableK_debug(in_dim=nfeat, latent_dim=nhidden, args=args))
+        self.params1 = list(self.conv1.parameters())
+        self.params2 = list(self.conv2.parameters())
+        self.params2.extend(list(self.dggs.parameters()))
+
+    def forward(self, x, in_adj, noise=True, epoch=None, writer=None):
+        in_adj = add_self_loops_coo(in_adj)
+        unnorm_adj = in_adj
+        for i, conv in enumerate(self.convs):
+            if i < len(self.dggs):
+                src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
+                unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
+                norm_adj = self.normalize_adj(unnorm_adj)
+            x = conv(x, norm_adj)
+            if i < len(self.convs) - 1:
+                x = F.dropout(x, training=self.training)
+            if writer is not None:
+                writer.add_histogram("gcn_conv{}_dist".format(i + 1), x, epoch)
+        return F.log_softmax(x, dim=-1), unnorm_adj, None
+
+    def dgg_net(self, x, i, unnorm_adj, writer, epoch):
+        return self.dggs[i](x=x, in_adj=unnorm_adj, noise=False, writer=writer, epoch=epoch)
+
+
+# --------------------------------------------------------------------------- GCNII + DGG
+class GraphConvolution(nn.Module):
+    """Reference model.py:14-44 (sparse adj) / DenseGraphConvolution 47-77 (dense adj): one body."""
+
+    def __init__(self, in_features, out_features, residual=False, variant=False):
+        super().__init__()
+        self.variant = variant
+        self.in_features = 2 * in_features if variant else in_features
+        self.out_features = out_features
+        self.residual = residual
+        self.weight = nn.Parameter(torch.FloatTensor(self.in_features, self.out_features))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.out_features)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, input, adj, h0, lamda, alpha, l):
+        theta = math.log(lamda / l + 1)
+        hi = _aggregate(adj, input)
+        if self.variant:
+            support = torch.cat([hi, h0], 1)
+            r = (1 - alpha) * hi + alpha * h0
+        else:
+            support = (1 - alpha) * hi + alpha * h0
+            r = support
+        output = theta * torch.mm(support, self.weight) + (1 - theta) * r
+        if self.residual:
+            output = output + input
+        return output
+
+
+class DenseGraphConvolution(GraphConvolution):
+    pass
+
+
+class GCNII_DGG(nn.Module, _NormalizeMixin):
+    """Reference model.py:649-740."""
+
+    def __init__(self, nfeat, nlayers, nhidden, nclass, dropout, lamda, alpha, variant, args):
+        super().__init__()
+        self.convs = nn.ModuleList()
+        for _ in range(nlayers):
+            self.convs.append(DenseGraphConvolution(nhidden, nhidden, variant=variant))
+        self.fcs = nn.ModuleList()
+        self.fcs.append(nn.Linear(nfeat, nhidden))
+        self.fcs.append(nn.Linear(nhidden, nclass))
+        self.dgg_adj_input = args.dgg_adj_input
+        self.dggs = nn.ModuleList()
+        for _ in range(args.n_dgg_layers):
+            self.dggs.append(DGG_LearnableK_debug(in_dim=nfeat, latent_dim=nhidden, args=args))
+        self.params1 = list(self.convs.parameters())
+        self.params1.extend(list(self.dggs.parameters()))
+        self.params2 = list(self.fcs.parameters())
+        self.act_fn = nn.ReLU()
+        self.dropout = dropout
+        self.alpha = alpha
+        self.lamda = lamda
+
+    def forward(self, x, in_adj, epoch=None, writer=None):
+        _layers = []
+        x = F.dropout(x, self.dropout, training=self.training)
+        layer_inner = self.act_fn(self.fcs[0](x))
+        _layers.append(layer_inner)
+        in_adj = add_self_loops_coo(in_adj)
+        unnorm_adj = in_adj
+        for i, con in enumerate(self.convs):
+            if i < len(self.dggs):
+                src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
+                unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
+                norm_adj = self.normalize_adj(unnorm_adj)
+            layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+            layer_inner = self.act_fn(con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1))
+        layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+        layer_inner = self.fcs[-1](layer_inner)
+        return F.log_softmax(layer_inner, dim=1)
+
+    def dgg_net(self, x, i, unnorm_adj, writer, epoch):
+        return self.dggs[i](x=x, in_adj=unnorm_adj, noise=self.training, writer=writer, epoch=epoch)
+
+
+# --------------------------------------------------------------------------- SAGE + DGG
+class DenseGraphConv(nn.Module):
+    """PyG 2.1.0 ``DenseGraphConv`` (used at reference model.py:128-129, 202-203; its source is not in
+    the reference tree): out = lin_rel(aggr(adj @ x)) + lin_root(x), aggr="mean" divides by
+    clamp(rowsum(adj), min=1); the result carries a leading batch dimension [1, N, F_out]."""
+
+    def __init__(self, in_channels, out_channels, aggr="add", bias=True):
+        super().__init__()
+        assert aggr in ("add", "mean")
+        self.aggr = aggr
+        self.lin_rel = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin_root = nn.Linear(in_channels, out_channels, bias=False)
+
+    def forward(self, x, adj, mask=None):
+        x = x.squeeze(0) if x.dim() == 3 else x
+        if adj.is_sparse:
+            g, v = CSRGraph.from_coo(adj)
+            scale = None
+            if self.aggr == "mean":
+                scale = 1.0 / K.row_sum(v, g).clamp(min=1)
+                agg = K.spmm(v, x, g) * scale.unsqueeze(-1)
+            else:
+                agg = K.spmm(v, x, g)
+        else:
+            agg = torch.mm(adj, x)
+            if self.aggr == "mean":
+                agg = agg / adj.sum(-1, keepdim=True).clamp(min=1)
+        return (self.lin_rel(agg) + self.lin_root(x)).unsqueeze(0)
+
+
+class SAGE_DGG(torch.nn.Module, _NormalizeMixin):
+    """Reference model.py:122-193: returns the log-probabilities tensor only."""
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, args=None, **kwargs):
+        super().__init__()
+        self.convs = torch.nn.ModuleList()
+        self.convs.append(DenseGraphConv(nfeat, nhidden, aggr="mean"))
+        self.convs.append(DenseGraphConv(nhidden, nclass, aggr="mean"))
+        self.dgg_adj_input = args.dgg_adj_input
+        self.dggs = nn.ModuleList()
+        self.dggs.append(DGG_LearnableK_debug(in_dim=nfeat, latent_dim=nhidden, args=args))
+
+    def dgg_net(self, x, i, unnorm_adj, writer, epoch):
+        return self.dggs[i](x=x, in_adj=unnorm_adj, noise=False, writer=writer, epoch=epoch)
+
+    def forward(self, x, in_adj, noise=True, epoch=None, writer=None, **kwargs):
+        in_adj = add_self_loops_coo(in_adj)
+        unnorm_adj = in_adj
+        for i, conv in enumerate(self.convs):
+            if i < len(self.dggs):
+                src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
+                unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
+                norm_adj = self.normalize_adj(unnorm_adj)
+            x = conv(x, norm_adj)
+            if i < len(self.convs) - 1:
+                x = x.relu_()
+                x = F.dropout(x, p=0.5, training=self.training)
+        x = F.log_softmax(x, dim=-1)
+        return x.squeeze(0)
+
+
+class SAGE_DGG_00(torch.nn.Module, _NormalizeMixin):
+    """Reference model.py:196-283."""
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, args=None, **kwargs):
+        super().__init__()
+        self.convs = torch.nn.ModuleList()
+        self.convs.append(DenseGraphConv(nhidden, nhidden, aggr="mean"))
+        self.convs.append(DenseGraphConv(nhidden, nclass, aggr="mean"))
+        self.dgg_adj_input = args.dgg_adj_input
+        self.dggs = nn.ModuleList()
+        self.dggs.append(DGG(in_dim=nfeat, latent_dim=nhidden, args=args))
+
+    def forward(self, x, in_adj, noise=True, epoch=None, writer=None, **kwargs):
+        in_adj = add_self_loops_coo(in_adj)
+        unnorm_adj = in_adj
+        for i, conv in enumerate(self.convs):
+            if i < len(self.dggs):
+                src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
+                unnorm_adj, x_dgg = self.dgg_net(x, i, src, writer, epoch)
+                norm_adj = self.normalize_adj(unnorm_adj)
+                x = x_dgg
+            x = conv(x, norm_adj)
+            if i < len(self.convs) - 1:
+                x = x.relu_()
+                x = F.dropout(x, p=0.5, training=self.training)
+        x = F.log_softmax(x, dim=-1)
+        return x.squeeze(0), unnorm_adj, x_dgg
+
+    def dgg_net(self, x, i, unnorm_adj, writer, epoch):
+        return self.dggs[i](x=x, adj=unnorm_adj, noise=False, writer=writer, epoch=epoch)
+
+
+# --------------------------------------------------------------------------- GAT + DGG
+def remove_self_loops(edge_index, edge_attr=None):
+    keep = edge_index[0] != edge_index[1]
+    return edge_index[:, keep], (None if edge_attr is None else edge_attr[keep])
+
+
+def add_self_loops(edge_index, edge_attr=None, fill_value=None, num_nodes=None):
+    n = int(edge_index.max()) + 1 if num_nodes is None else num_nodes
+    loops = torch.arange(n, dtype=edge_index.dtype, device=edge_index.device)
+    return torch.cat([edge_index, torch.stack([loops, loops])], dim=1), edge_attr
+
+
+class _GATPlan:
+    """How the attention edge list relates to the stored entries of the DGG adjacency:
+    (a) listed and stored, (b) listed but not stored (logit e*0 = 0: part of the background),
+    (d) stored but not listed (logit -1e20*A -> weight exactly 0: removed from the background)."""
+
+    def __init__(self, edge_list, graph: CSRGraph):
+        n = graph.n
+        aidx = graph.coo_indices()
+        akey = aidx[0] * n + aidx[1]                               # sorted (coalesced)
+        ekey = edge_list[0] * n + edge_list[1]
+        pos = torch.searchsorted(akey, ekey).clamp(max=max(akey.numel() - 1, 0))
+        hit = akey[pos] == ekey if akey.numel() else torch.zeros_like(ekey, dtype=torch.bool)
+        self.e_sel = hit.nonzero().flatten()                        # edges of class (a)
+        self.a_sel = pos[self.e_sel]                                # their slots in the adjacency values
+        stored_listed = torch.zeros(akey.numel(), dtype=torch.bool, device=akey.device)
+        stored_listed[self.a_sel] = True
+        self.d_sel = (~stored_listed).nonzero().flatten()           # class (d)
+        self.rows_a, self.cols_a = aidx[0][self.a_sel], aidx[1][self.a_sel]
+        self.rows_d, self.cols_d = aidx[0][self.d_sel], aidx[1][self.d_sel]
+        # same support, same order => the (a) entries ARE the CSR, and SpMM kernels apply directly
+        self.csr_aligned = (self.d_sel.numel() == 0 and self.a_sel.numel() == akey.numel()
+                            and bool((self.a_sel[1:] > self.a_sel[:-1]).all()))
+        if not self.csr_aligned and self.d_sel.numel() == 0 and self.a_sel.numel() == akey.numel():
+            order = torch.argsort(self.a_sel)                       # same support, edge list in another order
+            self.e_sel, self.a_sel = self.e_sel[order], self.a_sel[order]
+            self.rows_a, self.cols_a = aidx[0][self.a_sel], aidx[1][self.a_sel]
+            self.csr_aligned = True
+        self.graph = graph
+
+
+def _gat_plan(edge_list, adj):
+    graph, vals = CSRGraph.from_coo(adj)
+    cache = getattr(adj, "_gat_plan", None)
+    if cache is None or cache[0] != (edge_list.data_ptr(), edge_list.shape[1]):
+        plan = _GATPlan(edge_list, graph)
+        try:
+            adj._gat_plan = ((edge_list.data_ptr(), edge_list.shape[1]), plan)
+        except Exception:
+            pass
+        return plan, vals
+    return cache[1], vals
+
+
+class GATConv_DGG(nn.Module):
+    """Reference model.py:534-577.  The reference masks by MULTIPLICATION: non-listed pairs get logit
+    -1e20 * A_ij, which is -0.0 wherever A_ij is not stored, so every row's softmax runs over all N
+    columns ("dense background").  That is the parity spec; it is evaluated in closed form:
+
+        m_i  = max(0, max_(a) s_ij),  s_ij = e_ij A_ij,  w_ij = exp(s_ij - m_i) - exp(-m_i)
+        out_i = [ sum_(a) w_ij h_j + exp(-m_i) (sum_j h_j - sum_(d) h_j) ] / [ sum_(a) w_ij + exp(-m_i) (N - |d_i|) ]
+
+    an O(E F) edge softmax + SpMM plus one rank-1 background term, instead of 5 dense N x N temporaries.
+    Training-mode attention dropout is applied to the listed entries; the background term keeps its
+    expectation (the reference draws an N x N mask) -- parity is asserted in eval mode."""
+
+    def __init__(self, in_features, out_features, dropout, alpha, bias=True):
+        super().__init__()
+        self.dropout = dropout
+        self.in_features = in_features
+        self.out_features = out_features
+        self.alpha = alpha
+        self.weight = nn.Parameter(torch.FloatTensor(in_features, out_features))
+        self.a = nn.Parameter(torch.zeros(size=(2 * out_features, 1)))
+        if bias:
+            self.bias = nn.Parameter(torch.FloatTensor(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.weight.data, gain=1.414)
+        if self.bias is not None:
+            self.bias.data.fill_(0)
+        nn.init.xavier_uniform_(self.a.data, gain=1.414)
+
+    def forward(self, x, edge_list, adj):
+        x = F.dropout(x, self.dropout, training=self.training)
+        h = torch.matmul(x, self.weight)
+        n, f = h.shape
+        plan, avals = _gat_plan(edge_list, adj)
+        # e_ij = LeakyReLU(a^T [h_i || h_j]) = LeakyReLU(p_i + q_j): two N-vectors instead of an E x 2F gather
+        pq = torch.mm(h, torch.cat([self.a[:f], self.a[f:]], dim=1))                       # [N,2]
+        src, dst = edge_list[0][plan.e_sel], edge_list[1][plan.e_sel]
+        e = F.leaky_relu(pq[src, 0] + pq[dst, 1], negative_slope=self.alpha)
+        s = e * avals[plan.a_sel]
+        m = torch.zeros(n, device=h.device).scatter_reduce(0, plan.rows_a, s.detach(), "amax", include_self=True)
+        em = torch.exp(-m)
+        w = torch.exp(s - m[plan.rows_a]) - em[plan.rows_a]
+        hd = F.dropout(h, self.dropout, training=self.training)
+        if self.training and self.dropout > 0:
+            w = F.dropout(w, self.dropout, training=True)
+        htot = hd.sum(0, keepdim=True)
+        bg_cnt = torch.full((n,), float(n), device=h.device)
+        if plan.d_sel.numel():
+            bg_cnt = bg_cnt.index_add(0, plan.rows_d, -torch.ones(plan.d_sel.numel(), device=h.device))
+            hbg = htot - torch.zeros_like(hd).index_add(0, plan.rows_d, hd[plan.cols_d])
+        else:
+            hbg = htot
+        denom = em * bg_cnt + torch.zeros(n, device=h.device).index_add(0, plan.rows_a, w)
+        if plan.csr_aligned:
+            num = K.spmm(w, hd, plan.graph)
+        else:
+            num = torch.zeros_like(hd).index_add(0, plan.rows_a, w.unsqueeze(-1) * hd[plan.cols_a])
+        h_prime = (num + em.unsqueeze(-1) * hbg) / denom.unsqueeze(-1)
+        if self.bias is not None:
+            h_prime = h_prime + self.bias
+        return h_prime
+
+
+class GAT_DGG_00(nn.Module, _NormalizeMixin):
+    """Reference model.py:323-403."""
+
+    _dgg_cls = DGG
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, args=None, nhead=8, nhead_out=1, alpha=0.2,
+                 dropout=0.6, **kwargs):
+        super().__init__()
+        self.attentions = [GATConv_DGG(nhidden, nhidden, dropout=dropout, alpha=alpha) for _ in range(nhead)]
+        self.out_atts = [GATConv_DGG(nhidden * nhead, nclass, dropout=dropout, alpha=alpha)
+                         for _ in range(nhead_out)]
+        self.dgg = self._dgg_cls(in_dim=nfeat, latent_dim=nhidden, args=args)
+        for i, attention in enumerate(self.attentions):
+            self.add_module("attention_{}".format(i), attention)
+        for i, attention in enumerate(self.out_atts):
+            self.add_module("out_att{}".format(i), attention)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for att in self.attentions:
+            att.reset_parameters()
+        for att in self.out_atts:
+            att.reset_parameters()
+
+    def forward(self, x, in_adj=None, edge_index=None, epoch=None, writer=None):
+        edge_index, _ = remove_self_loops(edge_index)
+        edge_index, _ = add_self_loops(edge_index, num_nodes=x.size(0))
+        in_adj = add_self_loops_coo(in_adj)
+        unnorm_adj, x_dgg = self.dgg(x=x, adj=in_adj)
+        x = x_dgg
+        x = torch.cat([att(x, edge_index, unnorm_adj) for att in self.attentions], dim=1)
+        x = F.elu(x)
+        x = torch.sum(torch.stack([att(x, edge_index, unnorm_adj) for att in self.out_atts]), dim=0) / len(
+            self.out_atts)
+        return F.log_softmax(x, dim=1), unnorm_adj, x_dgg
+
+
+class GAT_DGG_Ablations(GAT_DGG_00):
+    """Reference model.py:406-486."""
+
+    _dgg_cls = DGG_Ablations
+
+
+GAT_DGG = GAT_DGG_00   # the north star's name for it; the reference only has GAT_DGG_00 (SURVEY 2.4)
