@@ -164,8 +164,11 @@ class DGG_LearnableK_SDD(nn.Module):
             raise RuntimeError("DGG_LearnableK_SDD: a row needs more than %d selected entries (k_max=%.1f)"
                                % (self.KC_MAX, k_max))
         if noise:
-            G = self._noise if self._noise is not None else sample_gumbel_from_uniform((n, n))
-            idx, y = K.allpairs_topk(z, self.t, G, kc, self.precision)
+            if self._noise is not None:
+                idx, y = K.allpairs_topk(z, self.t, self._noise, kc, self.precision)
+            else:   # Gumbel(0,1) generated inside the kernel (counter-based): no N x N noise tensor
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                idx, y = K.allpairs_topk(z, self.t, None, kc, self.precision, seed=seed, noise_scale=1.0)
         else:
             raise NotImplementedError("evaluation (softmax) branch lands with the fused softmax epilogue")
         r = torch.arange(kc, device=x.device, dtype=torch.float32).reshape(1, kc)

@@ -157,7 +157,12 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
  * the epilogue fuses norms, sqrt, temperature, noise and the selection.  No N x N matrix is
  * written.  Rows [row_begin, row_begin+row_count) are scored against all n columns (row
  * sharding across GPUs: every rank passes the all-gathered z and its own row block).
- *   noise: NULL, or [row_count, noise_ld] fp32 (row r of it belongs to query row row_begin+r).
+ *   noise: [row_count, noise_ld] fp32 (row r of it belongs to query row row_begin+r) for parity
+ *          runs with an injected tensor; or NULL, in which case noise_scale != 0 selects
+ *          counter-based Gumbel(0, noise_scale) noise generated in the epilogue: Philox4x32-7,
+ *          key = seed, counter = (global row, col >> 2), output lane col & 3; the same (row, col)
+ *          always regenerates the same value, so shards and recomputation agree without
+ *          communication (tests/philox_ref.py is the host restatement).
  *   out_idx/out_val: [row_count, kc]; unused slots (n < kc) hold idx -1 / val 0.
  *   workspace: dggb_allpairs_workspace_bytes(n, d) bytes (hi/lo split of z + squared norms).
  * Requires d <= 128, kc <= 64.
@@ -165,7 +170,8 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
 int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d);
 int dggb_allpairs_topk_fwd(const float* z /* [n,d] */, int32_t n, int32_t d, int32_t row_begin,
                            int32_t row_count, const float* t /* [1] device */, const float* noise,
-                           int64_t noise_ld, int32_t kc, int32_t precision, void* workspace,
+                           int64_t noise_ld, uint64_t seed, float noise_scale, int32_t kc,
+                           int32_t precision, void* workspace,
                            int64_t workspace_bytes, int32_t* out_idx, float* out_val, void* stream);
 /* Backward by recomputation over the selected pairs only (O(rows*kc*d)):
  * dz[n,d] and dt[1] are ACCUMULATED INTO. */

@@ -7,5 +7,6 @@ from . import build  # noqa: F401
 from ._lib import DggbError, declared_symbols, lib  # noqa: F401
 from .graph import CSRGraph  # noqa: F401
 from . import functional  # noqa: F401
+from . import sharding  # noqa: F401
 
-__all__ = ["CSRGraph", "functional", "lib", "build", "DggbError", "declared_symbols"]
+__all__ = ["CSRGraph", "functional", "sharding", "lib", "build", "DggbError", "declared_symbols"]

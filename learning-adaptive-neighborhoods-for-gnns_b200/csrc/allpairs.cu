@@ -82,6 +82,30 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// counter-based Gumbel noise: Philox4x32-7 keyed by the 64-bit seed, counter = (row, col >> 2, 0, 0);
+// lane (col & 3) of the 4 outputs belongs to column col.  Any tile regenerates identically (no N x N
+// noise tensor in HBM) and a host implementation can materialise the same matrix for small N
+// (tests/philox_ref.py).  u = ((x >> 8) + 0.5) * 2^-24 in (0,1);  g = -scale * log(-log(u)).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+  uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+    const uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(x0, x1, x2, x3);
+}
+__device__ __forceinline__ float gumbel_from_bits(uint32_t x, float scale) {
+  const float u = ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+  return -scale * __logf(-__logf(u));
+}
+
+// ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kBM = 128;  // query rows per CTA (== TMEM lanes)
@@ -110,12 +134,14 @@ __host__ __device__ inline APSmem ap_smem_layout(int kb, int split, int stages, 
   return L;
 }
 
-template <int KB, int SPLIT>
+// NOISE: 0 none, 1 injected tensor, 2 Philox Gumbel(0, noise_scale)
+template <int KB, int SPLIT, int NOISE>
 __global__ void __launch_bounds__(kAPThreads, 1)
     allpairs_topk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                          const float* __restrict__ nrm, int n, int row_begin, int row_count,
                          const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
-                         int kc, int stages, int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                         unsigned long long seed, float noise_scale, int kc, int stages,
+                         int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const APSmem L = ap_smem_layout(KB, SPLIT, stages, kc);
@@ -229,7 +255,8 @@ __global__ void __launch_bounds__(kAPThreads, 1)
       idxs[r * kBM + row_t] = -1;
     }
     float thr = -INFINITY;
-    const float* nz = (noise && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
+    const float* nz = (NOISE == 1 && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     for (int jt = 0; jt < num_tiles; ++jt) {
       const int s = jt % stages;
       const uint32_t ph = (jt / stages) & 1;
@@ -249,13 +276,20 @@ __global__ void __launch_bounds__(kAPThreads, 1)
         if (row_ok) {
           const int jbase = jt * kBN + c0;
           auto body = [&](auto diag_c) {
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const int j = jbase + c;
               float d2 = fmaf(-2.f, __uint_as_float(r[c]), ni + nj[c0 + c]);
               if (decltype(diag_c)::value && j == row_begin + lrow) d2 = 0.f;
               float y = -t * sqrtf(fmaxf(d2, 0.f));
-              if (nz != nullptr && j < n) y += __ldg(nz + j);
+              if (NOISE == 1) {
+                if (j < n) y += __ldg(nz + j);
+              } else if (NOISE == 2) {
+                if ((c & 3) == 0) bits = philox4x32_7((uint32_t)(row_begin + lrow), (uint32_t)(j >> 2), key0, key1);
+                const uint32_t b = (c & 3) == 0 ? bits.x : ((c & 3) == 1 ? bits.y : ((c & 3) == 2 ? bits.z : bits.w));
+                y += gumbel_from_bits(b, noise_scale);
+              }
               if (j < n && y > thr) {
                 int pos = kc - 1;
                 while (pos > 0 && vals[(pos - 1) * kBM + row_t] < y) {
@@ -372,9 +406,9 @@ extern "C" int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d) {
 }
 
 extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
-                                      const float* t, const float* noise, int64_t noise_ld, int32_t kc,
-                                      int32_t precision, void* workspace, int64_t workspace_bytes, int32_t* out_idx,
-                                      float* out_val, void* stream) {
+                                      const float* t, const float* noise, int64_t noise_ld, uint64_t seed,
+                                      float noise_scale, int32_t kc, int32_t precision, void* workspace,
+                                      int64_t workspace_bytes, int32_t* out_idx, float* out_val, void* stream) {
   if (!z || !t || !workspace || !out_idx || !out_val || n <= 0 || d <= 0 || row_begin < 0 || row_count < 0 || kc <= 0)
     return DGGB_ERR_BAD_ARG;
   if (d > 128 || kc > 64) return DGGB_ERR_BAD_SHAPE;
@@ -405,14 +439,22 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   const size_t smem_bytes = L.total + 1024;
   const int grid = (row_count + kBM - 1) / kBM;
 
-#define DGGB_AP_LAUNCH(KB_, SP_)                                                                                  \
+  // noise mode: injected tensor if given, else Philox when noise_scale != 0, else none
+  const int nmode = noise ? 1 : (noise_scale != 0.f ? 2 : 0);
+#define DGGB_AP_LAUNCH1(KB_, SP_, NM_)                                                                            \
   do {                                                                                                            \
-    cudaError_t e = cudaFuncSetAttribute(allpairs_topk_kernel<KB_, SP_>,                                          \
+    cudaError_t e = cudaFuncSetAttribute(allpairs_topk_kernel<KB_, SP_, NM_>,                                     \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);           \
     if (e != cudaSuccess) return cuda_status(e);                                                                  \
-    allpairs_topk_kernel<KB_, SP_><<<grid, kAPThreads, smem_bytes, st>>>(tm_hi, tm_lo, nrm, n, row_begin,         \
-                                                                         row_count, t, noise, (long long)noise_ld, \
-                                                                         kc, stages, out_idx, out_val);           \
+    allpairs_topk_kernel<KB_, SP_, NM_><<<grid, kAPThreads, smem_bytes, st>>>(                                    \
+        tm_hi, tm_lo, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld, (unsigned long long)seed,      \
+        noise_scale, kc, stages, out_idx, out_val);                                                               \
+  } while (0)
+#define DGGB_AP_LAUNCH(KB_, SP_)                                                                                  \
+  do {                                                                                                            \
+    if (nmode == 0) DGGB_AP_LAUNCH1(KB_, SP_, 0);                                                                 \
+    else if (nmode == 1) DGGB_AP_LAUNCH1(KB_, SP_, 1);                                                            \
+    else DGGB_AP_LAUNCH1(KB_, SP_, 2);                                                                            \
   } while (0)
 
   if (kb == 1 && precision == 3) DGGB_AP_LAUNCH(1, 3);
@@ -422,6 +464,7 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   else if (kb == 4 && precision == 1) DGGB_AP_LAUNCH(4, 1);
   else return DGGB_ERR_BAD_SHAPE;
 #undef DGGB_AP_LAUNCH
+#undef DGGB_AP_LAUNCH1
   return launch_status();
 }
 

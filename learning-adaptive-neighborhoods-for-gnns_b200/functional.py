@@ -126,7 +126,10 @@ class _AllPairsTopK(torch.autograd.Function):
     """y_ij = -t |z_i - z_j| [+ noise], top-Kc per row, sorted descending (dgm.py:275-301 without N x N)."""
 
     @staticmethod
-    def forward(ctx, z, t, noise, kc: int, precision: int, row_begin: int, row_count: int):
+    def forward(ctx, z, t, noise, kc: int, precision: int, row_begin: int, row_count: int, seed: int,
+                noise_scale: float):
+        import ctypes
+
         from ._lib import i64
         _require_cuda(z, t, noise)
         z, t = _f32c(z), _f32c(t).reshape(-1)
@@ -140,7 +143,8 @@ class _AllPairsTopK(torch.autograd.Function):
             noise = _f32c(noise)
             assert noise.dim() == 2 and noise.shape[0] == row_count and noise.shape[1] >= n
         check(L.dggb_allpairs_topk_fwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(t), p(noise),
-                                       i64(0 if noise is None else noise.stride(0)), i32(kc), i32(precision), p(ws),
+                                       i64(0 if noise is None else noise.stride(0)), ctypes.c_uint64(seed),
+                                       ctypes.c_float(noise_scale), i32(kc), i32(precision), p(ws),
                                        i64(ws_bytes), p(idx), p(val), stream()), "allpairs_topk_fwd")
         ctx.meta = (kc, row_begin, row_count)
         ctx.save_for_backward(z, t, idx)
@@ -156,14 +160,16 @@ class _AllPairsTopK(torch.autograd.Function):
         dt = torch.zeros(1, dtype=torch.float32, device=z.device)
         check(lib().dggb_allpairs_pair_bwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(idx),
                                            p(_f32c(gy)), i32(kc), p(t), p(dz), p(dt), stream()), "allpairs_pair_bwd")
-        return dz, dt, None, None, None, None, None
+        return dz, dt, None, None, None, None, None, None, None
 
 
-def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=None):
-    """-> (idx int32 [rows,kc], y fp32 [rows,kc]) sorted descending per row; differentiable in z and t."""
+def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=None, seed=0, noise_scale=0.0):
+    """-> (idx int32 [rows,kc], y fp32 [rows,kc]) sorted descending per row; differentiable in z and t.
+    noise: injected [rows, n] tensor, or None with noise_scale != 0 for in-kernel Philox Gumbel noise."""
     if row_count is None:
         row_count = z.shape[0] - row_begin
-    return _AllPairsTopK.apply(z, t, noise, int(kc), int(precision), int(row_begin), int(row_count))
+    return _AllPairsTopK.apply(z, t, noise, int(kc), int(precision), int(row_begin), int(row_count), int(seed),
+                               float(noise_scale))
 
 
 class _RowFirstK(torch.autograd.Function):
