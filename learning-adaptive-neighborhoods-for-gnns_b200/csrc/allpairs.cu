@@ -14,6 +14,7 @@
 // (+ TMEM owner), w2..w5 epilogue.
 #include "common.cuh"
 #include "tc05.cuh"
+#include <climits>
 
 namespace dggb {
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256)
 // counter-based Gumbel noise: Philox4x32-7 keyed by the 64-bit seed, counter = (row, col >> 2, 0, 0);
 // lane (col & 3) of the 4 outputs belongs to column col.  Any tile regenerates identically (no N x N
 // noise tensor in HBM) and a host implementation can materialise the same matrix for small N
-// (tests/philox_ref.py).  u = ((x >> 8) + 0.5) * 2^-24 in (0,1);  g = -scale * log(-log(u)).
+// (tests/philox_ref.py).  v = ((x >> 8) + 0.5) * 2^-24 in (0,1);  g = -scale * log(-log1p(-v)).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
   uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
@@ -100,9 +101,20 @@ __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t
   }
   return make_uint4(x0, x1, x2, x3);
 }
+// sqrt.approx (MUFU, <= 2 ulp, no slow-path call): the distance already carries ~1e-6 of GEMM rounding
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// g = -scale * log(E), E = -log1p(-v) ~ Exp(1), v = ((x >> 8) + 0.5) 2^-24 in (0,1).
+// The LARGE Gumbel values (small v, small E) are the ones top-k keeps, so E must be accurate exactly
+// there: series for v < 2^-6, fast log otherwise (|dg| <~ 2e-5 either way).
 __device__ __forceinline__ float gumbel_from_bits(uint32_t x, float scale) {
-  const float u = ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
-  return -scale * __logf(-__logf(u));
+  const float v = ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f;  // 2^-24
+  const float series = v * fmaf(v, fmaf(v, fmaf(v, 0.25f, 0.33333334f), 0.5f), 1.0f);
+  const float e = (v < 0.015625f) ? series : -__logf(1.0f - v);
+  return -scale * __logf(e);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -112,8 +124,12 @@ constexpr int kBM = 128;  // query rows per CTA (== TMEM lanes)
 constexpr int kBN = 64;   // key columns per tile
 constexpr int kAPThreads = 192;
 
+constexpr int kQCap = 32;    // per-row candidate queue slots (flushed when >= kQFlush are pending)
+constexpr int kQFlush = 16;  // == columns per epilogue chunk, so a chunk can never overflow the queue
+constexpr int kChunk = 16;
+
 struct APSmem {  // byte offsets from the 1024-aligned base
-  uint32_t a_hi, a_lo, b0, b_stage_bytes, nrm, vals, idx, bars, total;
+  uint32_t a_hi, a_lo, b0, b_stage_bytes, nrm, vals, idx, qv, qi, bars, total;
 };
 
 __host__ __device__ inline APSmem ap_smem_layout(int kb, int split, int stages, int kc) {
@@ -129,9 +145,112 @@ __host__ __device__ inline APSmem ap_smem_layout(int kb, int split, int stages, 
   L.nrm = off; off += stages * kBN * 4;
   L.vals = off; off += kc * kBM * 4;
   L.idx = off; off += kc * kBM * 4;
+  L.qv = off; off += kQCap * kBM * 4;
+  L.qi = off; off += kQCap * kBM * 4;
   L.bars = off; off += 128;
   L.total = off;
   return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative merge of one row's pending candidates into its sorted top-Kc list.
+// Threads append candidates (score above the row's current K-th value) to a per-row queue with two
+// predicated stores -- no per-thread insertion loop, hence no divergence in the streaming loop.  When
+// a row has >= kQFlush pending, the whole warp sorts {list (kc) + queue (<= kQCap)} with a bitonic
+// network (M slots per lane, shuffles for strides < 32) and writes the best kc back.
+// Order: value descending, column ascending among equal values (== stable descending sort).
+// ------------------------------------------------------------------------------------------------
+struct Cand {
+  float v;
+  int id;
+};
+__device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
+  return (a.v > b.v) || (a.v == b.v && a.id < b.id);
+}
+
+__device__ __forceinline__ Cand cand_shfl_xor(const Cand& c, int j) {
+  Cand o;
+  o.v = __shfl_xor_sync(0xffffffffu, c.v, j);
+  o.id = __shfl_xor_sync(0xffffffffu, c.id, j);
+  return o;
+}
+
+// M = list slots per lane (1: kc <= 32, 2: kc <= 64).  The list is kept sorted (descending); the queue
+// (<= 32 entries, one per lane) is bitonic-sorted ASCENDING so that list ++ queue is a bitonic sequence,
+// which log2(#slots) half-cleaner stages then sort -- far fewer exchanges than re-sorting everything.
+template <int M>
+__device__ __forceinline__ float merge_row(float* Lv, int32_t* Li, const float* Qv, const int32_t* Qi, int kc,
+                                           int row_t, int n_q, int lane) {
+  constexpr int T = (M == 1) ? 2 : 4;     // total slots per lane, padded to a power of two
+  Cand c[T];
+#pragma unroll
+  for (int m = 0; m < T; ++m) {
+    c[m].v = -INFINITY;
+    c[m].id = INT_MAX;
+  }
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int slot = lane + 32 * m;
+    if (slot < kc) {
+      c[m].v = Lv[slot * kBM + row_t];
+      const int id = Li[slot * kBM + row_t];
+      c[m].id = id < 0 ? INT_MAX : id;    // empty list slot (-inf): sorts after everything
+    }
+  }
+  Cand qd;
+  qd.v = lane < n_q ? Qv[lane * kBM + row_t] : -INFINITY;
+  qd.id = lane < n_q ? Qi[lane * kBM + row_t] : INT_MAX;
+  // sort the queue ascending ("worst first") across the 32 lanes
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const Cand o = cand_shfl_xor(qd, j);
+      const bool asc_block = ((lane & k) == 0);
+      const bool lower = ((lane & j) == 0);
+      const bool keep_worse = (asc_block == lower);
+      const bool mine_first = cand_before(qd, o);   // "first" == better
+      qd = (mine_first != keep_worse) ? qd : o;
+    }
+  }
+  // slots [0, 32 M) hold the descending list, the LAST 32 slots hold the ascending queue => bitonic
+  // (for M == 2 slot block 2 is -inf padding: descending, then flat, then ascending: still bitonic)
+  c[T - 1] = qd;
+  // bitonic merge (descending): strides >= 32 are in-lane exchanges, 16 ... 1 are shuffles
+#pragma unroll
+  for (int j = (32 * T) >> 1; j >= 32; j >>= 1) {
+#pragma unroll
+    for (int m = 0; m < T; ++m) {
+      if ((m & (j >> 5)) == 0) {
+        const Cand a = c[m], bb = c[m ^ (j >> 5)];
+        const bool a_first = cand_before(a, bb);
+        c[m] = a_first ? a : bb;
+        c[m ^ (j >> 5)] = a_first ? bb : a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+#pragma unroll
+    for (int m = 0; m < T; ++m) {
+      const Cand o = cand_shfl_xor(c[m], j);
+      const bool lower = ((lane & j) == 0);
+      const bool mine_first = cand_before(c[m], o);
+      c[m] = (mine_first == lower) ? c[m] : o;
+    }
+  }
+  float kth = -INFINITY;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int slot = lane + 32 * m;
+    if (slot < kc) {
+      Lv[slot * kBM + row_t] = c[m].v;
+      Li[slot * kBM + row_t] = (c[m].id == INT_MAX) ? -1 : c[m].id;
+    }
+    const float cand_kth = __shfl_sync(0xffffffffu, c[m].v, (kc - 1) & 31);
+    if (m == ((kc - 1) >> 5)) kth = cand_kth;
+  }
+  return kth;
 }
 
 // NOISE: 0 none, 1 injected tensor, 2 Philox Gumbel(0, noise_scale)
@@ -143,7 +262,9 @@ __global__ void __launch_bounds__(kAPThreads, 1)
                          unsigned long long seed, float noise_scale, int kc, int stages,
                          int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-B align WITHOUT laundering the pointer through an integer (keeps it a shared-space pointer, so
+  // every access below compiles to LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const APSmem L = ap_smem_layout(KB, SPLIT, stages, kc);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;            // [stages]  TMA -> MMA/epilogue
@@ -191,10 +312,10 @@ __global__ void __launch_bounds__(kAPThreads, 1)
           if (SPLIT == 3)
             tc::tma_load_2d(smem + L.a_lo + (kb * kBM + half * 64) * 128, &tm_lo, afull, kb * 32, row0 + half * 64);
         }
-      for (int jt = 0; jt < num_tiles; ++jt) {
-        const int s = jt % stages;
-        const uint32_t ph = (jt / stages) & 1;
-        tc::mbar_wait(empty + s, ph ^ 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
+        tc::mbar_wait_backoff(empty + s, ph ^ 1);
         tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes + kBN * 4);
         uint8_t* bs = smem + L.b0 + s * L.b_stage_bytes;
         for (int kb = 0; kb < KB; ++kb) {
@@ -208,16 +329,16 @@ __global__ void __launch_bounds__(kAPThreads, 1)
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(kBM, kBN);
-      tc::mbar_wait(afull, 0);
+      tc::mbar_wait_backoff(afull, 0);
       tc::fence_after_sync();
       const uint32_t a_hi = tc::smem_u32(smem + L.a_hi), a_lo = tc::smem_u32(smem + L.a_lo);
-      for (int jt = 0; jt < num_tiles; ++jt) {
-        const int s = jt % stages;
-        const uint32_t ph = (jt / stages) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
         const int buf = jt & 1;
         const uint32_t bph = (jt >> 1) & 1;
-        tc::mbar_wait(tempty + buf, bph ^ 1);
-        tc::mbar_wait(full + s, ph);
+        tc::mbar_wait_backoff(tempty + buf, bph ^ 1);
+        tc::mbar_wait_backoff(full + s, ph);
         tc::fence_after_sync();
         const uint32_t b_hi = tc::smem_u32(smem + L.b0 + s * L.b_stage_bytes);
         const uint32_t b_lo = b_hi + KB * kBN * 128;
@@ -254,12 +375,31 @@ __global__ void __launch_bounds__(kAPThreads, 1)
       vals[r * kBM + row_t] = -INFINITY;
       idxs[r * kBM + row_t] = -1;
     }
-    float thr = -INFINITY;
+    float* qv = reinterpret_cast<float*>(smem + L.qv);       // [kQCap][128]
+    int32_t* qi = reinterpret_cast<int32_t*>(smem + L.qi);
+    float thr = -INFINITY;   // this row's current K-th best value (stale between merges: only admits extras)
+    int qn = 0;              // pending candidates of this row
     const float* nz = (NOISE == 1 && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
-    for (int jt = 0; jt < num_tiles; ++jt) {
-      const int s = jt % stages;
-      const uint32_t ph = (jt / stages) & 1;
+    const bool wide = kc > 32;
+    auto flush = [&](unsigned need) {
+      __syncwarp();   // queue entries were written by their owner lanes; the whole warp reads them below
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n_q = __shfl_sync(0xffffffffu, qn, src);
+        const float kth = wide ? merge_row<2>(vals, idxs, qv, qi, kc, q * 32 + src, n_q, lane)
+                               : merge_row<1>(vals, idxs, qv, qi, kc, q * 32 + src, n_q, lane);
+        if (lane == src) {
+          thr = kth;
+          qn = 0;
+        }
+      }
+      __syncwarp();
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
       const int buf = jt & 1;
       const uint32_t bph = (jt >> 1) & 1;
       tc::mbar_wait(full + s, ph);      // column norms of this tile are in smem
@@ -269,43 +409,55 @@ __global__ void __launch_bounds__(kAPThreads, 1)
       // the tile(s) that contain this CTA's own diagonal take the variant that pins d2(i,i) = 0 exactly
       const bool diag_tile = (jt * kBN < row0 + kBM) && (jt * kBN + kBN > row0);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kBN; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + c0, r);
+      for (int c0 = 0; c0 < kBN; c0 += kChunk) {
+        uint32_t r[kChunk];
+        tc::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kBN + c0, r);
         tc::tmem_ld_wait();
         if (row_ok) {
           const int jbase = jt * kBN + c0;
           auto body = [&](auto diag_c) {
-            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            // phase 1: straight-line scores for the 16 columns of this chunk (no branches => ILP)
+            float y[kChunk];
+            float njv[kChunk];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
+            for (int c = 0; c < kChunk; c += 4) {
+              const float4 v4 = *reinterpret_cast<const float4*>(nj + c0 + c);
+              njv[c] = v4.x; njv[c + 1] = v4.y; njv[c + 2] = v4.z; njv[c + 3] = v4.w;
+            }
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            unsigned pass = 0u;
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c) {
               const int j = jbase + c;
-              float d2 = fmaf(-2.f, __uint_as_float(r[c]), ni + nj[c0 + c]);
+              float d2 = fmaf(-2.f, __uint_as_float(r[c]), ni + njv[c]);
               if (decltype(diag_c)::value && j == row_begin + lrow) d2 = 0.f;
-              float y = -t * sqrtf(fmaxf(d2, 0.f));
+              float yy = -t * sqrt_fast(fmaxf(d2, 0.f));
               if (NOISE == 1) {
-                if (j < n) y += __ldg(nz + j);
+                if (j < n) yy += __ldg(nz + j);
               } else if (NOISE == 2) {
                 if ((c & 3) == 0) bits = philox4x32_7((uint32_t)(row_begin + lrow), (uint32_t)(j >> 2), key0, key1);
                 const uint32_t b = (c & 3) == 0 ? bits.x : ((c & 3) == 1 ? bits.y : ((c & 3) == 2 ? bits.z : bits.w));
-                y += gumbel_from_bits(b, noise_scale);
+                yy += gumbel_from_bits(b, noise_scale);
               }
-              if (j < n && y > thr) {
-                int pos = kc - 1;
-                while (pos > 0 && vals[(pos - 1) * kBM + row_t] < y) {
-                  vals[pos * kBM + row_t] = vals[(pos - 1) * kBM + row_t];
-                  idxs[pos * kBM + row_t] = idxs[(pos - 1) * kBM + row_t];
-                  --pos;
+              y[c] = yy;
+              pass |= (j < n && yy > thr) ? (1u << c) : 0u;
+            }
+            // phase 2 (rare once the list is warm): append the survivors to this row's queue
+            if (pass) {
+#pragma unroll
+              for (int c = 0; c < kChunk; ++c) {
+                if (pass & (1u << c)) {
+                  qv[qn * kBM + row_t] = y[c];
+                  qi[qn * kBM + row_t] = jbase + c;
+                  ++qn;
                 }
-                vals[pos * kBM + row_t] = y;
-                idxs[pos * kBM + row_t] = j;
-                thr = vals[(kc - 1) * kBM + row_t];
               }
             }
           };
           if (diag_tile) body(std::true_type{});
           else body(std::false_type{});
         }
+        flush(__ballot_sync(0xffffffffu, qn >= kQFlush));
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -314,6 +466,7 @@ __global__ void __launch_bounds__(kAPThreads, 1)
         tc::mbar_arrive(empty + s);
       }
     }
+    flush(__ballot_sync(0xffffffffu, qn > 0));
     // ---- write the sorted lists: lanes sweep the list positions of one row at a time ----
     __syncwarp();
     for (int rr = 0; rr < 32; ++rr) {

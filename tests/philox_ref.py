@@ -43,5 +43,5 @@ def gumbel_matrix(n_rows, n_cols, seed, scale, row_begin=0):
     outs = philox4x32_7(c0, c1, seed)
     lane = (cols & 3).expand(n_rows, n_cols)
     bits = torch.where(lane == 0, outs[0], torch.where(lane == 1, outs[1], torch.where(lane == 2, outs[2], outs[3])))
-    u = ((bits >> 8).to(torch.float32) + 0.5) * (2.0 ** -24)
-    return -scale * torch.log(-torch.log(u))
+    v = ((bits >> 8).to(torch.float64) + 0.5) * (2.0 ** -24)
+    return (-scale * torch.log(-torch.log1p(-v))).to(torch.float32)
