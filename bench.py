@@ -248,12 +248,29 @@ def run_ours(args, rank, local_rank, world):
         dsets.append(dict(adj=adj, x=s["x"].to(dev), g_vals=s["g_vals"].to(dev), g_xenc=s["g_xenc"].to(dev)))
     flat_grads = None
 
-    def step_resident(i):
-        s = dsets[i % N_SETS]
+    def eager_step(s, static_grads=False):
         for p in params:
-            p.grad = None
+            if static_grads:
+                p.grad.zero_()      # graphs share ONE set of static .grad buffers, accumulated in place
+            else:
+                p.grad = None
         out, x_enc = m(s["x"], s["adj"])
         torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"], s["g_xenc"]])
+        return out._dgg_vals
+
+    # one captured CUDA graph per resident input set (a training loop that holds its mini-batches on the
+    # device replays its step); --no-graph times the eager path instead
+    graphed = None
+    if not args.no_graph:
+        for p in params:
+            p.grad = torch.zeros_like(p)
+        graphed = [dgg_b200.GraphedStep(lambda s=s: eager_step(s, True)) for s in dsets]
+
+    def step_resident(i):
+        if graphed is not None:
+            graphed[i % N_SETS]()
+        else:
+            eager_step(dsets[i % N_SETS])
         if world > 1:
             flat = torch.cat([p.grad.flatten() for p in params])
             dist.all_reduce(flat)
@@ -321,6 +338,7 @@ def run_ours(args, rank, local_rank, world):
                 config=dict(workload="pubmed-shape DGG fwd+bwd", n=shape["n"], f=shape["f"], h=shape["h"],
                             edges=int(host_sets[0]["idx"].shape[1]), graphs_per_step_per_gpu=1,
                             l2=f"rotating {N_SETS} input sets (> 126 MB L2)",
+                            launch=("eager" if args.no_graph else "CUDA-graph replay of the captured fwd+bwd step"),
                             parallelism=(f"dp{world} (one graph batch per rank, NCCL all-reduce of DGG weight grads)"
                                          if world > 1 else "single GPU")),
                 e2e=dict(value=e2e_value, unit="nodes/s", ms_per_step=ms_e2e / args.steps,
@@ -366,42 +384,44 @@ def kernel_roofline(m, dsets, shape, iters=30):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters * 1e-3
 
-    saved = {}
-
-    def fwd(i):
-        g, y, _ = prepared[i % N_SETS]
-        with torch.no_grad():
-            saved[i % N_SETS] = K._DGGEdge.apply(y, lin.bias, dd.weight, dd.bias, g, None, -1)
-
-    t_fwd = timed(fwd)
     from dgg_b200._lib import check, i32, lib, p, stream
 
-    dy = torch.zeros(n, h, device=prepared[0][1].device)
-    small = torch.zeros(h + 4 + n, device=dy.device)
+    dev = prepared[0][1].device
+    R = torch.empty(E + 64, device=dev)
+    rank = torch.empty(E + 64, dtype=torch.int32, device=dev)
+    s_row, k_row = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    out = torch.empty(E + 64, device=dev)
+    dy = torch.zeros(n, h, device=dev)
+    small = torch.zeros(h + 4 + n, device=dev)
     dw, db = dd.weight.detach().reshape(-1), dd.bias.detach().reshape(-1)
     be = lin.bias.detach()
 
-    def bwd(i):
+    def fwd(i):   # the two forward launches (edge_score + row_rank) through the C-ABI, outputs preallocated
+        g, y, _ = prepared[i % N_SETS]
+        check(lib().dggb_dgg_edge_fwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
+                                      p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out),
+                                      stream()), "fwd")
+
+    def bwd(i):   # the two backward launches (row_dk + edge_grad); R/rank/s/k of the last forward stand in
         g, y, gv = prepared[i % N_SETS]
-        out, k, R, rank = saved[i % N_SETS]
-        # timing only: the row-sum input `s` is not returned by the autograd wrapper, `k` stands in
-        # for it (same size, same access pattern)
         check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
-                                      p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(k), p(k), p(gv),
+                                      p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(s_row), p(k_row), p(gv),
                                       p(small[h + 4:]), p(dy), p(small[:h]), p(small[h:h + 2]), stream()), "bwd")
 
+    t_fwd = timed(fwd)
     t_bwd = timed(bwd)
     # algorithmic bytes (SURVEY 8d, int32 CSR): see DESIGN.md "dgg_edge"
     b_fwd = E * (4 + 4 * h) + n * (4 * h + 12) + E * 12
     b_bwd = E * (4 + 4 * h + 12) + E * 4 * h + n * (4 * h * 2 + 12)
-    name, t, b = ("dgg_edge_bwd_kernel", t_bwd, b_bwd) if t_bwd >= t_fwd else ("dgg_edge_fwd_kernel", t_fwd, b_fwd)
+    name, t, b = (("dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd) if t_bwd >= t_fwd
+                  else ("dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get(name)
     return dict(bound="hbm", kernel=name, achieved=b / t / 1e9, peak=peak, unit="GB/s", frac=b / t / 1e9 / peak,
                 traffic=traffic, peak_source=peak_src, algorithmic_bytes=int(b), kernel_us=t * 1e6,
-                others={"dgg_edge_fwd_kernel_us": t_fwd * 1e6, "dgg_edge_bwd_kernel_us": t_bwd * 1e6})
+                others={"dgg_edge_fwd_pair_us": t_fwd * 1e6, "dgg_edge_bwd_pair_us": t_bwd * 1e6})
 
 
 # --------------------------------------------------------------------------- Reddit-shape all-pairs arm
@@ -532,6 +552,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pubmed", choices=["pubmed", "reddit"])
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of CUDA-graph replay")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -8,5 +8,6 @@ from ._lib import DggbError, declared_symbols, lib  # noqa: F401
 from .graph import CSRGraph  # noqa: F401
 from . import functional  # noqa: F401
 from . import sharding  # noqa: F401
+from .graphed import GraphedStep  # noqa: F401
 
-__all__ = ["CSRGraph", "functional", "sharding", "lib", "build", "DggbError", "declared_symbols"]
+__all__ = ["CSRGraph", "functional", "sharding", "GraphedStep", "lib", "build", "DggbError", "declared_symbols"]

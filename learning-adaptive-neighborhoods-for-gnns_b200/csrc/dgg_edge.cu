@@ -87,21 +87,47 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
 }
 
 // 0-based descending rank of element m inside R[beg, beg+deg): ties broken by lower position first.
-// All 32 lanes call this together (shuffles); lanes with m >= deg get garbage they ignore.
-__device__ __forceinline__ int warp_rank(const float* __restrict__ R, int beg, int deg, int m, int lane) {
+// All 32 lanes call this together; lanes with m >= deg get garbage they ignore.
+//   deg <= 32 : one register per lane + 32 shuffles
+//   deg <= kRankCap : the row is staged in this warp's shared-memory slice; every lane then sweeps it with
+//                broadcast LDS (independent iterations, throughput- not latency-bound)
+//   longer rows: same sweep straight from global/L1
+constexpr int kRankCap = 1024;  // floats of shared memory per warp
+
+__device__ __forceinline__ int warp_rank(const float* __restrict__ R, float* srow, bool staged, int beg, int deg,
+                                         int m, int lane) {
   const float mine = (m < deg) ? __ldg(R + beg + m) : -INFINITY;
   int cnt = 0;
-  for (int jb = 0; jb < deg; jb += kWarp) {
-    const int jm = jb + lane;
-    const float other = (jm < deg) ? __ldg(R + beg + jm) : -INFINITY;
-    const int lim = min(kWarp, deg - jb);
-    for (int jj = 0; jj < lim; ++jj) {
-      const float rj = __shfl_sync(0xffffffffu, other, jj);
-      const int j = jb + jj;
+  if (deg <= kWarp) {
+    for (int jj = 0; jj < deg; ++jj) {
+      const float rj = __shfl_sync(0xffffffffu, mine, jj);   // m == lane here
+      cnt += (rj > mine) || (rj == mine && jj < m);
+    }
+    return cnt;
+  }
+  if (staged) {
+#pragma unroll 4
+    for (int j = 0; j < deg; ++j) {
+      const float rj = srow[j];
+      cnt += (rj > mine) || (rj == mine && j < m);
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < deg; ++j) {
+      const float rj = __ldg(R + beg + j);
       cnt += (rj > mine) || (rj == mine && j < m);
     }
   }
   return cnt;
+}
+
+// stage R[beg, beg+deg) into the warp's shared slice (deg <= kRankCap)
+__device__ __forceinline__ bool stage_row(const float* __restrict__ R, float* srow, int beg, int deg, int lane) {
+  if (deg <= kWarp || deg > kRankCap) return false;
+  __syncwarp();
+  for (int j = lane; j < deg; j += kWarp) srow[j] = __ldg(R + beg + j);
+  __syncwarp();
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -112,6 +138,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
                         const float* __restrict__ deg_w, const float* __restrict__ deg_b, int hard_k,
                         int32_t* __restrict__ rank, float* __restrict__ s_out, float* __restrict__ k_out,
                         float* __restrict__ out) {
+  __shared__ float srow_all[kEdgeWarps * kRankCap];
+  float* srow = srow_all + (threadIdx.x >> 5) * kRankCap;
   const int lane = threadIdx.x & 31;
   const float w = __ldg(deg_w), b = __ldg(deg_b);
   for (int i = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kEdgeWarps) {
@@ -120,9 +148,10 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     for (int e = beg + lane; e < end; e += kWarp) s += __ldg(R + e);
     s = warp_sum(s);
     const float k = leaky(w * s + b);  // dgm.py:1791-1792
+    const bool staged = stage_row(R, srow, beg, deg, lane);
     for (int mb = 0; mb < deg; mb += kWarp) {
       const int m = mb + lane;
-      const int r = warp_rank(R, beg, deg, m, lane);
+      const int r = warp_rank(R, srow, staged, beg, deg, m, lane);
       if (m < deg) {
         const float val = __ldg(R + beg + m);
         rank[beg + m] = r;
@@ -163,9 +192,18 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     dw_acc += dk * lr * s;
     db_acc += dk * lr;
   }
+  // one pair of atomics per block, not per warp: every warp in the grid targets the same two addresses
+  __shared__ float red[2][kEdgeWarps];
   if (lane == 0) {
-    atomicAdd(ddeg + 0, dw_acc);
-    atomicAdd(ddeg + 1, db_acc);
+    red[0][threadIdx.x >> 5] = dw_acc;
+    red[1][threadIdx.x >> 5] = db_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kEdgeWarps; ++wv) t += red[threadIdx.x][wv];
+    atomicAdd(ddeg + threadIdx.x, t);
   }
 }
 
@@ -189,6 +227,9 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
   load_slice<T>(bias, be, h, lg, L);
 #pragma unroll
   for (int t = 0; t < T; ++t) dbe_acc.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ float dbe_s[512];   // block-level bias-gradient accumulator (h <= 512)
+  for (int c = threadIdx.x; c < h; c += blockDim.x) dbe_s[c] = 0.f;
+  __syncthreads();
   const int warps_total = gridDim.x * kEdgeWarps;
   for (int base = (blockIdx.x * kEdgeWarps + (threadIdx.x >> 5)) * kWarp; base < nnz; base += warps_total * kWarp) {
     const int e_l = base + lane;
@@ -270,8 +311,15 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
       dbe_acc.v[t].w += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].w, o);
     }
     const int c = 4 * (lg + L * t);
-    if (grp == 0 && c < h) red_add4(dbe + c, dbe_acc.v[t]);
+    if (grp == 0 && c < h) {
+      atomicAdd(&dbe_s[c + 0], dbe_acc.v[t].x);
+      atomicAdd(&dbe_s[c + 1], dbe_acc.v[t].y);
+      atomicAdd(&dbe_s[c + 2], dbe_acc.v[t].z);
+      atomicAdd(&dbe_s[c + 3], dbe_acc.v[t].w);
+    }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < h; c += blockDim.x) atomicAdd(dbe + c, dbe_s[c]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -284,13 +332,16 @@ __device__ __forceinline__ float first_k_tanh(float r, float k) { return 1.f - 0
 __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     row_firstk_fwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
                           const float* __restrict__ k_in, int32_t* __restrict__ rank, float* __restrict__ out) {
+  __shared__ float srow_all[kEdgeWarps * kRankCap];
+  float* srow = srow_all + (threadIdx.x >> 5) * kRankCap;
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kEdgeWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1), deg = end - beg;
     const float k = __ldg(k_in + i);
+    const bool staged = stage_row(score, srow, beg, deg, lane);
     for (int mb = 0; mb < deg; mb += kWarp) {
       const int m = mb + lane;
-      const int r = warp_rank(score, beg, deg, m, lane);
+      const int r = warp_rank(score, srow, staged, beg, deg, m, lane);
       if (m < deg) {
         rank[beg + m] = r;
         out[beg + m] = __ldg(score + beg + m) * first_k_tanh((float)r, k);

@@ -208,3 +208,46 @@ def row_sum(vals, graph):
     ones = torch.ones(graph.n, 1, dtype=torch.float32, device=vals.device)
     # every column index is < n, so A @ 1 with the SpMM kernel is the row sum
     return spmm(vals, ones, graph).reshape(-1)
+
+
+class _TallLinear(torch.autograd.Function):
+    """y = act(x W^T + b) for TALL x ([N, F] with N >> F, out): the weight gradient dW = dpre^T x is a GEMM whose
+    reduction runs over the N nodes and whose output is tiny, which cuBLAS runs on a handful of CTAs; it is
+    evaluated split-K (batched over row chunks, then summed) so all SMs take part.  act = LeakyReLU(slope)
+    (slope = 1: identity)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, slope: float):
+        pre = torch.nn.functional.linear(x, w, b)
+        out = pre if slope == 1.0 else torch.nn.functional.leaky_relu(pre, slope)
+        ctx.slope = slope
+        ctx.save_for_backward(x, w, out)
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        dpre = g if ctx.slope == 1.0 else torch.ops.aten.leaky_relu_backward(g, out, ctx.slope, True)
+        dx = dpre @ w if ctx.needs_input_grad[0] else None
+        dw = splitk_tn(dpre, x)
+        db = dpre.sum(0) if ctx.has_bias else None
+        return dx, dw, db, None
+
+
+def splitk_tn(a, b, chunk=1024):
+    """a^T b for a [N, P], b [N, Q] with N large: batched over row chunks so the reduction is split."""
+    n = a.shape[0]
+    s = n // chunk
+    if s < 4:
+        return a.t() @ b
+    main = s * chunk
+    part = torch.bmm(a[:main].view(s, chunk, a.shape[1]).transpose(1, 2), b[:main].view(s, chunk, b.shape[1]))
+    out = part.sum(0)
+    if main < n:
+        out = out + a[main:].t() @ b[main:]
+    return out
+
+
+def tall_linear(x, w, b=None, slope=1.0):
+    return _TallLinear.apply(x, w, b, float(slope))

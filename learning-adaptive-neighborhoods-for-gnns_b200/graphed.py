@@ -1,0 +1,29 @@
+"""CUDA-graph capture of a whole forward+backward step.
+
+At citation-graph sizes the DGG step moves ~0.1 GB (~20 us at the HBM roofline) but is ~30 kernel
+launches; eager launches leave the GPU idle between them.  ``GraphedStep`` captures ``fn(*static_inputs)``
+(forward, backward, gradient writes) once and replays it: every libdggb entry point only enqueues on the
+caller's stream and never allocates or synchronises, so the path is capture-safe.  Input tensors are static
+(refill them in place between replays); outputs and ``.grad`` buffers are static too."""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedStep:
+    def __init__(self, fn, warmup: int = 3):
+        """fn() -> tensor or tuple of tensors; it must read its inputs from tensors that stay alive."""
+        self.fn = fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.outputs
