@@ -308,6 +308,8 @@ def run_ours(args, rank, local_rank, world):
     l0 = L.dggb_kernel_launches()
     ms = time_region(step_resident, args.steps, world)
     launches = int(L.dggb_kernel_launches() - l0)
+    if graphed is not None:   # replayed graphs launch the kernels recorded at capture time
+        launches = sum(graphed[i % N_SETS].dggb_launches_per_replay for i in range(args.steps))
     for i in range(max(3, args.warmup)):
         step_e2e(i)
     ms_e2e = time_region(step_e2e, args.steps, world)

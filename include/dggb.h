@@ -145,6 +145,16 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
                       float* dval, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Weight gradients of the tall node encoders (nn.Linear of dgm.py:1741-1744 / 1097-1100 /
+ * 1123-1126 applied to [N, F] features):  out[P,Q] += a[N,P]^T b[N,Q]  (dW = dpre^T x) and
+ * colsum_a[P] += column sums of a (db); split over the N rows so every SM streams a slab.
+ * out / colsum_a are ACCUMULATED INTO (zero them first); colsum_a may be NULL.  fp32 SIMT.
+ * ---------------------------------------------------------------------------------- */
+int dggb_gemm_tn_splitk(const float* a /* [N,P] */, const float* b /* [N,Q] */, int32_t n, int32_t p,
+                        int32_t q, float* out /* [P,Q] */, float* colsum_a /* [P] or NULL */,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------
  * All-pairs scoring + per-row streaming top-K (legacy all-pairs DGG, dgm.py:271-301; a15):
  *
  *   y_ij = -t * || z_i - z_j ||_2  [+ noise_ij]          (cdist -> exp -> log -> + Gumbel)

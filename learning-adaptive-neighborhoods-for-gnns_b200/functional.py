@@ -230,9 +230,20 @@ class _TallLinear(torch.autograd.Function):
         x, w, out = ctx.saved_tensors
         dpre = g if ctx.slope == 1.0 else torch.ops.aten.leaky_relu_backward(g, out, ctx.slope, True)
         dx = dpre @ w if ctx.needs_input_grad[0] else None
-        dw = splitk_tn(dpre, x)
-        db = dpre.sum(0) if ctx.has_bias else None
+        dw, db = gemm_tn(dpre, x, ctx.has_bias)
         return dx, dw, db, None
+
+
+def gemm_tn(a, b, want_colsum=False):
+    """(a^T b [P,Q], column sums of a [P] or None) for tall a [N,P], b [N,Q] via dggb_gemm_tn_splitk."""
+    a, b = _f32c(a), _f32c(b)
+    n, pp = a.shape
+    q = b.shape[1]
+    buf = torch.zeros(pp * q + (pp if want_colsum else 0), dtype=torch.float32, device=a.device)
+    out = buf[:pp * q].view(pp, q)
+    cs = buf[pp * q:] if want_colsum else None
+    check(lib().dggb_gemm_tn_splitk(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), stream()), "gemm_tn_splitk")
+    return out, cs
 
 
 def splitk_tn(a, b, chunk=1024):

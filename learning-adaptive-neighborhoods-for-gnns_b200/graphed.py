@@ -20,9 +20,14 @@ class GraphedStep:
             for _ in range(warmup):
                 fn()
         torch.cuda.current_stream().wait_stream(side)
+        from ._lib import lib
+
         self.graph = torch.cuda.CUDAGraph()
+        before = lib().dggb_kernel_launches()
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
+        # libdggb kernels recorded in the graph == launched again by every replay
+        self.dggb_launches_per_replay = int(lib().dggb_kernel_launches() - before)
 
     def __call__(self):
         self.graph.replay()
