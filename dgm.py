@@ -201,8 +201,9 @@ class DGG_LearnableK_debug(nn.Module):
     support (off-support entries are exact zeros that sort last).  Entries whose soft first-k weight
     saturates to exactly 0 stay in the returned support as explicit zeros (``to_dense()`` and all
     gradients are identical to the reference, which drops them in ``to_sparse()``).
-    Not covered in this round: ``perturb_edge_prob=True`` (needs the N-wide noise scan), ``k_only``
-    and ``dgg_hard`` (buggy / nondeterministic in the reference) -- they raise."""
+    ``perturb_edge_prob=True`` (Gumbel noise on all N^2 entries) is evaluated exactly on the union of each
+    row's edges and its best off-support entries (see ``_perturb``).
+    Not covered: ``k_only`` and ``dgg_hard`` (nondeterministic / buggy in the reference) -- they raise."""
 
     def __init__(self, in_dim=32, latent_dim=64, args=None):
         super().__init__()
@@ -256,17 +257,69 @@ class DGG_LearnableK_debug(nn.Module):
         edge_p = self.edge_prob_net(graph, vals, x, mode=self.edge_prob_net_mode)         # [E]
         if self.args.debug_step == 0:
             return self.return_hard_or_soft(graph, edge_p)
-        if self.args.perturb_edge_prob:
-            raise NotImplementedError("perturb_edge_prob=True is not covered yet (see class docstring)")
+        # k does not depend on the (perturbed) edge probabilities in any mode (dgm.py:1472-1586)
+        k = self.k_estimate_net(n, graph, vals, x, edge_p, mode=self.k_net_mode)           # [N,1] or None
         pert = edge_p
-        if self.args.debug_step == 1:
+        if self.args.perturb_edge_prob:
+            if self.args.debug_step == 1 or self.k_select_mode != "k_times_edge_prob":
+                raise NotImplementedError("perturb_edge_prob is covered for debug_step=3 / k_times_edge_prob only")
+            graph, vals, pert = self._perturb(graph, vals, edge_p, k, n)
+        elif self.args.debug_step == 1:
             return self.return_hard_or_soft(graph, pert)
-        k = self.k_estimate_net(n, graph, vals, x, pert, mode=self.k_net_mode)             # [N] or None
         out = self.select_top_k(graph, k, pert, mode=self.k_select_mode, writer=writer, epoch=epoch)
         if writer is not None:
             self.get_adj_diff_stats(graph, vals, out, k, writer=writer, epoch=epoch)
         self.last_k = k
         return self.return_hard_or_soft(graph, out)
+
+    # ------------------------------------------------------------------ Gumbel perturbation (dgm.py:1211-1229)
+    def _sample_noise(self, n, device):
+        """Dense [N,N] Gumbel(0, 0.3) noise laid out exactly like the reference: symmetric = n(n-1)/2 draws
+        on triu_indices(n,n,1) mirrored, zero diagonal (1216-1223); asymmetric = one [1,N,N] draw (1226).
+        ``self.gumbel`` stays the injection point (tests replace it with a fixed-tensor sampler)."""
+        if self.args.symmetric_noise:
+            G = torch.zeros(n, n, device=device)
+            i, j = torch.triu_indices(n, n, 1, device=device)
+            g = self.gumbel.sample([len(i)]).to(device)
+            G[i, j] = g
+            G[j, i] = g
+            return G
+        return self.gumbel.sample([1, n, n]).to(device).squeeze(0)
+
+    def _perturb(self, graph, vals, edge_p, k, n):
+        """pert = exp(log(P + 1e-8) + G) on ALL N^2 entries: off-support ones become 1e-8 e^G and are ranked
+        by G.  Only entries ranked inside the soft first-k window (r < k_i + 8.47) can be
+        non-zero, so per row the union of its edges and its W = ceil(k_max + 8.47) + 1 best non-edges (by G) is
+        exact: any excluded non-edge is out-ranked by W included ones.  The best non-edges come from the
+        streaming top-K selector (all-pairs kernel with t = 0 and the edge positions masked to -inf)."""
+        if k is None:
+            raise TypeError("unsupported operand type(s) for -: 'Tensor' and 'NoneType'")     # dgm.py:1413
+        dev = edge_p.device
+        G = self._sample_noise(n, dev)
+        idx = graph.coo_indices()
+        g_edge = G[idx[0], idx[1]]
+        pert_edge = torch.exp(torch.log(edge_p + 1e-8) + g_edge)                               # 1213-1229
+        w = int(math.ceil(float(k.detach().max()) + 8.47)) + 1
+        if w > 64 and n > 64:
+            raise RuntimeError("perturb_edge_prob: window %d exceeds the selector's 64 entries per row" % w)
+        w = min(w, n)
+        masked = G.clone()
+        masked[idx[0], idx[1]] = float("-inf")
+        zero = torch.zeros(n, 32, device=dev)
+        sel_idx, sel_g = K.allpairs_topk(zero, torch.zeros(1, device=dev), masked, w, 1)
+        keep = torch.isfinite(sel_g) & (sel_idx >= 0)
+        rows = torch.arange(n, device=dev).reshape(n, 1).expand(n, w)[keep]
+        cols = sel_idx[keep].long()
+        pert_non = torch.exp(torch.log(torch.full_like(sel_g[keep], 1e-8)) + sel_g[keep])
+        # union structure, coalesced order (row-major, columns ascending)
+        key = torch.cat([idx[0] * n + idx[1], rows * n + cols])
+        order = torch.argsort(key)
+        key = key[order]
+        u_idx = torch.stack([key // n, key % n])
+        u_graph = CSRGraph.from_indices(u_idx, n)
+        u_pert = torch.cat([pert_edge, pert_non])[order]
+        u_vals = torch.cat([vals, torch.zeros_like(pert_non)])[order]
+        return u_graph, u_vals, u_pert
 
     def return_hard_or_soft(self, graph, edge_vals, idxs=None, k=None, threshold=0.8):
         if self.hard:

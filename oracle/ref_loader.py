@@ -135,6 +135,8 @@ def load_reference(names=("dgm", "model")):
             for n in ("dgm", "utils", "model"):
                 if n in names or (n == "utils" and "model" in names):
                     out[n] = importlib.import_module(n)
+            if "utils" in out and not hasattr(out["utils"].np, "float"):
+                out["utils"].np.float = float      # numpy >= 1.24 removed np.float (utils.py:99)
     finally:
         sys.path.remove(REFERENCE_ROOT)
         for n in ("dgm", "model", "utils"):

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 FWD = dict(rtol=1e-4, atol=1e-5)
 BWD = dict(rtol=2e-3, atol=2e-4)
 
-LK = ["lk_dist_x", "lk_deg_x", "lk_auv_inputdeg", "lk_degdist_lnd", "lk_edgeconv_gcn", "lk_Auv_x", "lk_dist_x_cdf"]
+LK = ["lk_dist_x", "lk_deg_x", "lk_auv_inputdeg", "lk_degdist_lnd", "lk_edgeconv_gcn", "lk_Auv_x", "lk_dist_x_cdf",
+      "lk_dist_x_pert_sym", "lk_deg_x_pert_asym"]
 
 
 @pytest.mark.parametrize("tag", LK)
@@ -26,6 +27,9 @@ def test_learnable_k_matches_reference_golden(golden, tag):
     m = dgm.DGG_LearnableK_debug(in_dim=g["f"], latent_dim=g["h"], args=a)
     m.load_state_dict(c["state"])
     m = m.cuda().eval()
+    if c["noise"] is not None:          # same injection point as the reference: module.gumbel.sample(shape)
+        from oracle.ref_loader import FixedGumbel
+        m.gumbel = FixedGumbel(c["noise"])
     x = g["x"].cuda().requires_grad_(True)
     out = m(x, coo(g["idx"], c["val"], g["n"]).cuda())
     assert out.is_sparse
@@ -47,7 +51,7 @@ def test_learnable_k_matches_reference_golden(golden, tag):
 def test_learnable_k_unsupported_modes_raise(golden):
     import dgm
 
-    g, c = golden["graph"], golden["cases"]["lk_dist_x_pert_sym"]
+    g, c = golden["graph"], golden["cases"]["lk_dist_x_konly"]
     a = argparse.Namespace(**c["args"])
     m = dgm.DGG_LearnableK_debug(in_dim=g["f"], latent_dim=g["h"], args=a).cuda()
     with pytest.raises(NotImplementedError):
