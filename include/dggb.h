@@ -145,6 +145,17 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
                       float* dval, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)
+ * -- nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126 and the
+ * y = x_enc We^T product.  tcgen05 tensor cores with an in-kernel 3xTF32 split (fp32-level
+ * accuracy, fp32 accumulate in TMEM), operands by TMA; x is read from HBM once.
+ * Requires F % 4 == 0 and H in {16, 32, 64, 128} (else DGGB_ERR_BAD_SHAPE: use a library GEMM).
+ * b may be NULL.
+ * ---------------------------------------------------------------------------------- */
+int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
+                        int32_t f, int32_t h, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Weight gradients of the tall node encoders (nn.Linear of dgm.py:1741-1744 / 1097-1100 /
  * 1123-1126 applied to [N, F] features):  out[P,Q] += a[N,P]^T b[N,Q]  (dW = dpre^T x) and
  * colsum_a[P] += column sums of a (db); split over the N rows so every SM streams a slab.

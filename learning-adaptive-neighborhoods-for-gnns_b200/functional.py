@@ -218,8 +218,10 @@ class _TallLinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, slope: float):
-        pre = torch.nn.functional.linear(x, w, b)
-        out = pre if slope == 1.0 else torch.nn.functional.leaky_relu(pre, slope)
+        out = _linear_act_tc(x, w, b, slope)
+        if out is None:      # shapes the tensor-core kernel does not take (e.g. F % 4 != 0): library GEMM
+            pre = torch.nn.functional.linear(x, w, b)
+            out = pre if slope == 1.0 else torch.nn.functional.leaky_relu(pre, slope)
         ctx.slope = slope
         ctx.save_for_backward(x, w, out)
         ctx.has_bias = b is not None
@@ -232,6 +234,26 @@ class _TallLinear(torch.autograd.Function):
         dx = dpre @ w if ctx.needs_input_grad[0] else None
         dw, db = gemm_tn(dpre, x, ctx.has_bias)
         return dx, dw, db, None
+
+
+def _linear_act_tc(x, w, b, slope):
+    """act(x W^T + b) through dggb_linear_act_fwd (tcgen05, 3xTF32); None if the shape is not supported."""
+    import ctypes
+
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 4 == 0
+            and w.shape[0] in (16, 32, 64, 128) and x.shape[0] >= 512):
+        return None
+    x, w = x.contiguous(), w.contiguous()
+    n, f_in = x.shape
+    h = w.shape[0]
+    out = torch.empty(n, h, dtype=torch.float32, device=x.device)
+    bb = None if b is None else b.contiguous()
+    rc = lib().dggb_linear_act_fwd(p(x), p(w), p(bb), ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out),
+                                   stream())
+    if rc == -2:
+        return None
+    check(rc, "linear_act_fwd")
+    return out
 
 
 def gemm_tn(a, b, want_colsum=False):

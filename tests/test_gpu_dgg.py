@@ -219,3 +219,26 @@ def test_gemm_tn_splitk(n, p, q):
     want = (a.double().t() @ b.double()).float()
     torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(cs, a.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,f,h,slope", [(19717, 500, 64, 0.01), (1000, 64, 64, 1.0), (4097, 128, 16, 0.01),
+                                         (777, 36, 32, 0.2), (2500, 600, 128, 0.01)])
+def test_linear_act_tensor_core(n, f, h, slope):
+    """tcgen05 3xTF32 node-encoder GEMM vs an fp64 reference: relative error <= 3e-6 of |x||w| (fp32 level)."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(n + f)
+    x = torch.randn(n, f, generator=gen).cuda()
+    w = (torch.randn(h, f, generator=gen) / f ** 0.5).cuda()
+    b = torch.randn(h, generator=gen).cuda()
+    got = K._linear_act_tc(x, w, b, slope)
+    assert got is not None
+    pre = x.double() @ w.double().t() + b.double()
+    want = torch.where(pre > 0, pre, pre * slope).float()
+    scale = (x.double().abs() @ w.double().abs().t()).float() + 1.0
+    assert float(((got - want).abs() / scale).max()) < 3e-6
+    # and it matches torch's fp32 linear at fp32 tolerance
+    ref = torch.nn.functional.linear(x, w, b)
+    if slope != 1.0:
+        ref = torch.nn.functional.leaky_relu(ref, slope)
+    torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-5)
