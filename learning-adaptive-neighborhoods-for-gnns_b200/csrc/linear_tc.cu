@@ -6,15 +6,18 @@
 // is accumulated as hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (3xTF32).  x is read from HBM exactly
 // once (no pre-split copy): HBM-bound, N*F*4 + N*H*4 bytes.
 //
-// CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32, W box Hx32 per k-block, ring of kStages),
-// warps 2-5: converters, then epilogue (tcgen05.ld -> bias -> LeakyReLU -> global), warp 1: MMA issuer + TMEM.
+// CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32, W box Hx32 per k-block, 4-deep raw ring so ~100 KB
+// are in flight per SM), warps 2-5: converters (raw -> hi/lo double buffer), then epilogue (tcgen05.ld -> bias
+// -> LeakyReLU -> global), warp 1: MMA issuer + TMEM owner.
 #include "common.cuh"
 #include "tc05.cuh"
 
 namespace dggb {
 
 constexpr int kLinBM = 128;
-constexpr int kLinStages = 2;       // 2 stages x (2 x 16 KB + 2 x H*128 B): two CTAs fit per SM at H = 64
+constexpr int kLinConv = 2;         // converted (hi/lo) double buffer feeding the tensor core
+// raw TMA ring depth (x 16 KB + W H*128 B per stage): deep enough to keep ~100 KB in flight per SM
+template <int H> struct LinRaw { static constexpr int value = (H <= 64) ? 4 : 2; };
 constexpr int kLinThreads = 192;
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -23,21 +26,31 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
+__device__ __forceinline__ void split4(const float4 r, float4& h, float4& l) {
+  h.x = tf32_rna(r.x); h.y = tf32_rna(r.y); h.z = tf32_rna(r.z); h.w = tf32_rna(r.w);
+  l.x = tf32_rna(r.x - h.x); l.y = tf32_rna(r.y - h.y); l.z = tf32_rna(r.z - h.z); l.w = tf32_rna(r.w - h.w);
+}
+
 template <int H>   // output width (UMMA N), multiple of 16, <= 128
-__global__ void __launch_bounds__(kLinThreads, 2)
+__global__ void __launch_bounds__(kLinThreads, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                          const float* __restrict__ bias, float slope, int n, int f, float* __restrict__ out) {
+  constexpr int kLinRaw = LinRaw<H>::value;
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats]
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W: [H rows][32 floats]
-  constexpr uint32_t kStageBytes = 2 * kXBytes + 2 * kWBytes;   // x hi | x lo | w hi | w lo
+  constexpr uint32_t kRawBytes = kXBytes + kWBytes;             // x | w   (as landed by TMA)
+  constexpr uint32_t kConvBytes = 2 * kXBytes + 2 * kWBytes;    // x hi | x lo | w hi | w lo
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLinStages * kStageBytes);
-  uint64_t* raw_full = bars;                  // [stages] TMA landed (count 1 + tx)
-  uint64_t* conv_done = bars + kLinStages;    // [stages] hi/lo split written (count 4: one per converter warp)
-  uint64_t* empty = bars + 2 * kLinStages;    // [stages] MMAs that read the stage retired (tcgen05.commit)
-  uint64_t* acc_full = bars + 3 * kLinStages; // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kLinStages + 1);
+  uint8_t* raw0 = smem;
+  uint8_t* conv0 = smem + kLinRaw * kRawBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(conv0 + kLinConv * kConvBytes);
+  uint64_t* raw_full = bars;                        // [kLinRaw]  TMA landed (1 + tx)
+  uint64_t* raw_empty = bars + kLinRaw;             // [kLinRaw]  converters done reading (4 warps)
+  uint64_t* conv_full = bars + 2 * kLinRaw;         // [kLinConv] hi/lo written (4 warps)
+  uint64_t* conv_empty = conv_full + kLinConv;      // [kLinConv] MMAs that read it retired (tcgen05.commit)
+  uint64_t* acc_full = conv_empty + kLinConv;       // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kLinBM;
@@ -46,10 +59,13 @@ __global__ void __launch_bounds__(kLinThreads, 2)
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_x);
     tc::tma_prefetch_desc(&tm_w);
-    for (int s = 0; s < kLinStages; ++s) {
+    for (int s = 0; s < kLinRaw; ++s) {
       tc::mbar_init(raw_full + s, 1);
-      tc::mbar_init(conv_done + s, 4);
-      tc::mbar_init(empty + s, 1);
+      tc::mbar_init(raw_empty + s, 4);
+    }
+    for (int s = 0; s < kLinConv; ++s) {
+      tc::mbar_init(conv_full + s, 4);
+      tc::mbar_init(conv_empty + s, 1);
     }
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
@@ -68,12 +84,12 @@ __global__ void __launch_bounds__(kLinThreads, 2)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb, (++s == kLinStages) ? (s = 0, ph ^= 1) : 0) {
-        tc::mbar_wait_backoff(empty + s, ph ^ 1);
-        uint8_t* st = smem + s * kStageBytes;
-        tc::mbar_arrive_expect_tx(raw_full + s, kXBytes + kWBytes);
-        tc::tma_load_2d(st, &tm_x, raw_full + s, kb * 32, row0);                 // raw x -> "hi" slot
-        tc::tma_load_2d(st + 2 * kXBytes, &tm_w, raw_full + s, kb * 32, 0);      // raw W -> "hi" slot
+      for (int kb = 0; kb < num_kb; ++kb, (++s == kLinRaw) ? (s = 0, ph ^= 1) : 0) {
+        tc::mbar_wait(raw_empty + s, ph ^ 1);
+        uint8_t* st = raw0 + s * kRawBytes;
+        tc::mbar_arrive_expect_tx(raw_full + s, kRawBytes);
+        tc::tma_load_2d(st, &tm_x, raw_full + s, kb * 32, row0);
+        tc::tma_load_2d(st + kXBytes, &tm_w, raw_full + s, kb * 32, 0);
       }
     }
   } else if (warp == 1) {
@@ -82,10 +98,10 @@ __global__ void __launch_bounds__(kLinThreads, 2)
       int s = 0;
       uint32_t ph = 0;
       uint32_t acc = 0;
-      for (int kb = 0; kb < num_kb; ++kb, (++s == kLinStages) ? (s = 0, ph ^= 1) : 0) {
-        tc::mbar_wait_backoff(conv_done + s, ph);
+      for (int kb = 0; kb < num_kb; ++kb, (++s == kLinConv) ? (s = 0, ph ^= 1) : 0) {
+        tc::mbar_wait(conv_full + s, ph);
         tc::fence_after_sync();
-        const uint32_t xh = tc::smem_u32(smem + s * kStageBytes), xl = xh + kXBytes;
+        const uint32_t xh = tc::smem_u32(conv0 + s * kConvBytes), xl = xh + kXBytes;
         const uint32_t wh = xh + 2 * kXBytes, wl = wh + kWBytes;
 #pragma unroll
         for (int sp = 0; sp < 3; ++sp) {
@@ -97,29 +113,30 @@ __global__ void __launch_bounds__(kLinThreads, 2)
             acc = 1;
           }
         }
-        tc::mma_commit(empty + s);
+        tc::mma_commit(conv_empty + s);
       }
       tc::mma_commit(acc_full);
     }
   } else {
-    // ---------------- converters: split every landed stage into TF32 hi (in place) + lo ----------------
+    // ---------------- converters: raw stage -> TF32 hi + lo (same positions => swizzle preserved) ----------
     const int ct = threadIdx.x - 64;   // 0..127
-    int s = 0;
-    uint32_t ph = 0;
-    for (int kb = 0; kb < num_kb; ++kb, (++s == kLinStages) ? (s = 0, ph ^= 1) : 0) {
-      tc::mbar_wait(raw_full + s, ph);
-      uint8_t* st = smem + s * kStageBytes;
-      float4* xh = reinterpret_cast<float4*>(st);
-      float4* xl = reinterpret_cast<float4*>(st + kXBytes);
-      float4* wh = reinterpret_cast<float4*>(st + 2 * kXBytes);
-      float4* wl = reinterpret_cast<float4*>(st + 2 * kXBytes + kWBytes);
+    int rs = 0, cs = 0;
+    uint32_t rph = 0, cph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      tc::mbar_wait(raw_full + rs, rph);
+      tc::mbar_wait(conv_empty + cs, cph ^ 1);
+      const float4* xr = reinterpret_cast<const float4*>(raw0 + rs * kRawBytes);
+      const float4* wr = reinterpret_cast<const float4*>(raw0 + rs * kRawBytes + kXBytes);
+      uint8_t* cv = conv0 + cs * kConvBytes;
+      float4* xh = reinterpret_cast<float4*>(cv);
+      float4* xl = reinterpret_cast<float4*>(cv + kXBytes);
+      float4* wh = reinterpret_cast<float4*>(cv + 2 * kXBytes);
+      float4* wl = reinterpret_cast<float4*>(cv + 2 * kXBytes + kWBytes);
 #pragma unroll
       for (int i = 0; i < (int)(kXBytes / 16) / 128; ++i) {
         const int v = ct + i * 128;
-        const float4 r = xh[v];
         float4 h, l;
-        h.x = tf32_rna(r.x); h.y = tf32_rna(r.y); h.z = tf32_rna(r.z); h.w = tf32_rna(r.w);
-        l.x = tf32_rna(r.x - h.x); l.y = tf32_rna(r.y - h.y); l.z = tf32_rna(r.z - h.z); l.w = tf32_rna(r.w - h.w);
+        split4(xr[v], h, l);
         xh[v] = h;
         xl[v] = l;
       }
@@ -127,17 +144,20 @@ __global__ void __launch_bounds__(kLinThreads, 2)
       for (int i = 0; i < ((int)(kWBytes / 16) + 127) / 128; ++i) {
         const int v = ct + i * 128;
         if (v < (int)(kWBytes / 16)) {
-          const float4 r = wh[v];
           float4 h, l;
-          h.x = tf32_rna(r.x); h.y = tf32_rna(r.y); h.z = tf32_rna(r.z); h.w = tf32_rna(r.w);
-          l.x = tf32_rna(r.x - h.x); l.y = tf32_rna(r.y - h.y); l.z = tf32_rna(r.z - h.z); l.w = tf32_rna(r.w - h.w);
+          split4(wr[v], h, l);
           wh[v] = h;
           wl[v] = l;
         }
       }
       tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(conv_done + s);
+      if (lane == 0) {
+        tc::mbar_arrive(conv_full + cs);
+        tc::mbar_arrive(raw_empty + rs);
+      }
+      if (++rs == kLinRaw) { rs = 0; rph ^= 1; }
+      if (++cs == kLinConv) { cs = 0; cph ^= 1; }
     }
     // ---------------- epilogue: thread == output row ----------------
     const int q = warp & 3;
@@ -184,7 +204,7 @@ static int launch_linear(const float* x, const float* w, const float* b, float s
   if (rc != DGGB_OK) return rc;
   rc = make_tmap_2d_f32(&tm_w, w, (uint64_t)H, (uint64_t)f, H, 32);
   if (rc != DGGB_OK) return rc;
-  const size_t smem = kLinStages * (2 * kLinBM * 128 + 2 * H * 128) + 128 + 1024;
+  const size_t smem = LinRaw<H>::value * (kLinBM * 128 + H * 128) + kLinConv * (2 * kLinBM * 128 + 2 * H * 128) + 256 + 1024;
   cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
   linear_tf32x3_kernel<H><<<(n + kLinBM - 1) / kLinBM, kLinThreads, smem, st>>>(tm_x, tm_w, b, slope, n, f, out);
