@@ -148,12 +148,15 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)
  * -- nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126 and the
  * y = x_enc We^T product.  tcgen05 tensor cores with an in-kernel 3xTF32 split (fp32-level
- * accuracy, fp32 accumulate in TMEM), operands by TMA; x is read from HBM once.
+ * accuracy, fp32 accumulate in TMEM): x tiles by TMA -> registers -> TMEM ("TS" MMA), W
+ * pre-split into the workspace; x is read from HBM once.
  * Requires F % 4 == 0 and H in {16, 32, 64, 128} (else DGGB_ERR_BAD_SHAPE: use a library GEMM).
  * b may be NULL.
  * ---------------------------------------------------------------------------------- */
+int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h);   /* hi/lo split of W */
 int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
-                        int32_t f, int32_t h, float* out, void* stream);
+                        int32_t f, int32_t h, float* out, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Weight gradients of the tall node encoders (nn.Linear of dgm.py:1741-1744 / 1097-1100 /

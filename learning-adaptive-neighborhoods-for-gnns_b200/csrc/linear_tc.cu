@@ -1,23 +1,19 @@
 // Node-encoder GEMM on the 5th-gen tensor cores:  out[N,H] = act(x[N,F] W[H,F]^T + b),  act = LeakyReLU(slope)
 // (nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126, and y = x_enc We^T).
 //
-// fp32 in / fp32 out with ~fp32 accuracy: every operand tile is split IN SHARED MEMORY into TF32 hi + lo
-// parts by four converter warps (position-preserving, so the TMA 128-B swizzle is untouched) and the product
-// is accumulated as hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (3xTF32).  x is read from HBM exactly
-// once (no pre-split copy): HBM-bound, N*F*4 + N*H*4 bytes.
+// fp32 in / fp32 out with ~fp32 accuracy: the x tile is split into TF32 hi + lo parts by four converter warps
+// (thread == row: swizzled LDS -> registers -> tcgen05.st into TENSOR MEMORY) and the product is accumulated as
+// hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (3xTF32) by "TS" MMAs (A from TMEM, B = pre-split W from
+// shared memory).  x is read from HBM exactly once (no pre-split copy): N*F*4 + N*H*4 bytes.
 //
-// CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32, W box Hx32 per k-block, 4-deep raw ring so ~100 KB
-// are in flight per SM), warps 2-5: converters (raw -> hi/lo double buffer), then epilogue (tcgen05.ld -> bias
-// -> LeakyReLU -> global), warp 1: MMA issuer + TMEM owner.
+// CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32 + W hi/lo boxes Hx32 per k-block, 6-deep ring),
+// warps 2-5: converters, then epilogue (tcgen05.ld -> bias -> LeakyReLU -> global), warp 1: MMA issuer + TMEM.
 #include "common.cuh"
 #include "tc05.cuh"
 
 namespace dggb {
 
 constexpr int kLinBM = 128;
-constexpr int kLinConv = 2;         // converted (hi/lo) double buffer feeding the tensor core
-// raw TMA ring depth (x 16 KB + W H*128 B per stage): deep enough to keep ~100 KB in flight per SM
-template <int H> struct LinRaw { static constexpr int value = (H <= 64) ? 4 : 2; };
 constexpr int kLinThreads = 192;
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -26,30 +22,61 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-__device__ __forceinline__ void split4(const float4 r, float4& h, float4& l) {
-  h.x = tf32_rna(r.x); h.y = tf32_rna(r.y); h.z = tf32_rna(r.z); h.w = tf32_rna(r.w);
-  l.x = tf32_rna(r.x - h.x); l.y = tf32_rna(r.y - h.y); l.z = tf32_rna(r.z - h.z); l.w = tf32_rna(r.w - h.w);
+// W -> (hi, lo) TF32 split, once per call (W is tiny: H x F)
+__global__ void split_w_kernel(const float* __restrict__ w, int count, float* __restrict__ hi, float* __restrict__ lo) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const float v = __ldg(w + i);
+    const float h = tf32_rna(v);
+    hi[i] = h;
+    lo[i] = tf32_rna(v - h);
+  }
 }
 
-template <int H>   // output width (UMMA N), multiple of 16, <= 128
+// D[tmem] (+)= A[tmem] * B[smem]^T  (A: 128 lanes x 8 consecutive 32-bit columns per MMA)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Shared-memory traffic is what bounded the first version of this kernel (raw tile in, hi + lo tiles out,
+// three tensor-core reads): here the converters keep the split x operand in REGISTERS and hand it to the
+// tensor core through TMEM (tcgen05.st -> "TS" MMA, A from tensor memory); only W (pre-split) is read from
+// shared memory by the MMA.  Per k-block of 32 features: 16 KB x in, 16 KB LDS, 24 KB of W operand reads.
+template <int H, int STAGES>
 __global__ void __launch_bounds__(kLinThreads, 1)
-    linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                         const float* __restrict__ bias, float slope, int n, int f, float* __restrict__ out) {
-  constexpr int kLinRaw = LinRaw<H>::value;
-  constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats]
-  constexpr uint32_t kWBytes = H * 128;            // one k-block of W: [H rows][32 floats]
-  constexpr uint32_t kRawBytes = kXBytes + kWBytes;             // x | w   (as landed by TMA)
-  constexpr uint32_t kConvBytes = 2 * kXBytes + 2 * kWBytes;    // x hi | x lo | w hi | w lo
+    linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
+                         const __grid_constant__ CUtensorMap tm_wlo, const float* __restrict__ bias, float slope,
+                         int n, int f, float* __restrict__ out) {
+  constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
+  constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
+  constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;
+  constexpr uint32_t kAccCols = H <= 64 ? 64 : 128;
+  constexpr uint32_t kTmemCols = 256;              // accumulator + 2 x (A hi 32 cols | A lo 32 cols)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* raw0 = smem;
-  uint8_t* conv0 = smem + kLinRaw * kRawBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(conv0 + kLinConv * kConvBytes);
-  uint64_t* raw_full = bars;                        // [kLinRaw]  TMA landed (1 + tx)
-  uint64_t* raw_empty = bars + kLinRaw;             // [kLinRaw]  converters done reading (4 warps)
-  uint64_t* conv_full = bars + 2 * kLinRaw;         // [kLinConv] hi/lo written (4 warps)
-  uint64_t* conv_empty = conv_full + kLinConv;      // [kLinConv] MMAs that read it retired (tcgen05.commit)
-  uint64_t* acc_full = conv_empty + kLinConv;       // accumulator complete
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* full = bars;                      // [STAGES] TMA landed (1 + tx)
+  uint64_t* empty = bars + STAGES;            // [STAGES] 4 converter warps read x + MMAs read W (commit) = 5
+  uint64_t* a_full = bars + 2 * STAGES;       // [2] A (hi/lo) written to TMEM by the 4 converter warps
+  uint64_t* a_empty = a_full + 2;             // [2] MMAs that read it retired
+  uint64_t* acc_full = a_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,19 +85,19 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&tm_x);
-    tc::tma_prefetch_desc(&tm_w);
-    for (int s = 0; s < kLinRaw; ++s) {
-      tc::mbar_init(raw_full + s, 1);
-      tc::mbar_init(raw_empty + s, 4);
+    tc::tma_prefetch_desc(&tm_whi);
+    tc::tma_prefetch_desc(&tm_wlo);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 5);
     }
-    for (int s = 0; s < kLinConv; ++s) {
-      tc::mbar_init(conv_full + s, 4);
-      tc::mbar_init(conv_empty + s, 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(a_full + s, 4);
+      tc::mbar_init(a_empty + s, 1);
     }
     tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
   }
-  constexpr uint32_t kTmemCols = H <= 32 ? 32 : (H <= 64 ? 64 : 128);
   if (warp == 1) {
     tc::tmem_alloc(tmem_slot, kTmemCols);
     tc::tmem_relinquish();
@@ -79,95 +106,91 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a0 = tmem_base + kAccCols;   // A buffers start after the accumulator columns
 
   if (warp == 0) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb, (++s == kLinRaw) ? (s = 0, ph ^= 1) : 0) {
-        tc::mbar_wait(raw_empty + s, ph ^ 1);
-        uint8_t* st = raw0 + s * kRawBytes;
-        tc::mbar_arrive_expect_tx(raw_full + s, kRawBytes);
-        tc::tma_load_2d(st, &tm_x, raw_full + s, kb * 32, row0);
-        tc::tma_load_2d(st + kXBytes, &tm_w, raw_full + s, kb * 32, 0);
+      for (int kb = 0; kb < num_kb; ++kb, (++s == STAGES) ? (s = 0, ph ^= 1) : 0) {
+        tc::mbar_wait(empty + s, ph ^ 1);
+        uint8_t* st = smem + s * kStageBytes;
+        tc::mbar_arrive_expect_tx(full + s, kStageBytes);
+        tc::tma_load_2d(st, &tm_x, full + s, kb * 32, row0);
+        tc::tma_load_2d(st + kXBytes, &tm_whi, full + s, kb * 32, 0);
+        tc::tma_load_2d(st + kXBytes + kWBytes, &tm_wlo, full + s, kb * 32, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(kLinBM, H);
       int s = 0;
-      uint32_t ph = 0;
-      uint32_t acc = 0;
-      for (int kb = 0; kb < num_kb; ++kb, (++s == kLinConv) ? (s = 0, ph ^= 1) : 0) {
-        tc::mbar_wait(conv_full + s, ph);
+      uint32_t ph = 0, acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb, (++s == STAGES) ? (s = 0, ph ^= 1) : 0) {
+        const int ab = kb & 1;
+        const uint32_t aph = (kb >> 1) & 1;
+        tc::mbar_wait(full + s, ph);       // W hi/lo of this k-block are in shared memory
+        tc::mbar_wait(a_full + ab, aph);   // x hi/lo of this k-block are in tensor memory
         tc::fence_after_sync();
-        const uint32_t xh = tc::smem_u32(conv0 + s * kConvBytes), xl = xh + kXBytes;
-        const uint32_t wh = xh + 2 * kXBytes, wl = wh + kWBytes;
+        const uint32_t wh = tc::smem_u32(smem + s * kStageBytes + kXBytes), wl = wh + kWBytes;
+        const uint32_t ah = tmem_a0 + ab * 64, al = ah + 32;
 #pragma unroll
         for (int sp = 0; sp < 3; ++sp) {
-          const uint32_t a = (sp == 2) ? xl : xh;   // hi*hi, hi*lo, lo*hi
+          const uint32_t a = (sp == 2) ? al : ah;   // hi*hi, hi*lo, lo*hi
           const uint32_t b = (sp == 1) ? wl : wh;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            tc::mma_tf32(tmem_base, tc::smem_desc_k128(a + ks * 32), tc::smem_desc_k128(b + ks * 32), idesc, acc);
+            mma_tf32_ts(tmem_base, a + ks * 8, tc::smem_desc_k128(b + ks * 32), idesc, acc);
             acc = 1;
           }
         }
-        tc::mma_commit(conv_empty + s);
+        tc::mma_commit(empty + s);
+        tc::mma_commit(a_empty + ab);
       }
       tc::mma_commit(acc_full);
     }
   } else {
-    // ---------------- converters: raw stage -> TF32 hi + lo (same positions => swizzle preserved) ----------
-    const int ct = threadIdx.x - 64;   // 0..127
-    int rs = 0, cs = 0;
-    uint32_t rph = 0, cph = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      tc::mbar_wait(raw_full + rs, rph);
-      tc::mbar_wait(conv_empty + cs, cph ^ 1);
-      const float4* xr = reinterpret_cast<const float4*>(raw0 + rs * kRawBytes);
-      const float4* wr = reinterpret_cast<const float4*>(raw0 + rs * kRawBytes + kXBytes);
-      uint8_t* cv = conv0 + cs * kConvBytes;
-      float4* xh = reinterpret_cast<float4*>(cv);
-      float4* xl = reinterpret_cast<float4*>(cv + kXBytes);
-      float4* wh = reinterpret_cast<float4*>(cv + 2 * kXBytes);
-      float4* wl = reinterpret_cast<float4*>(cv + 2 * kXBytes + kWBytes);
+    // ---------------- converters: thread == row.  smem (swizzled) -> registers -> hi/lo -> TMEM ------------
+    const int q = warp & 3;
+    const int r_in_tile = q * 32 + lane;          // == TMEM lane this thread may access
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb, (++s == STAGES) ? (s = 0, ph ^= 1) : 0) {
+      const int ab = kb & 1;
+      const uint32_t aph = (kb >> 1) & 1;
+      tc::mbar_wait(full + s, ph);
+      // row r of the box: 128 B at r*128, its 16-B chunk c stored at chunk position c ^ (r & 7)
+      const uint8_t* rowp = smem + s * kStageBytes + r_in_tile * 128;
+      uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int i = 0; i < (int)(kXBytes / 16) / 128; ++i) {
-        const int v = ct + i * 128;
-        float4 h, l;
-        split4(xr[v], h, l);
-        xh[v] = h;
-        xl[v] = l;
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r_in_tile & 7)) << 4));
+        const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+        hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+        hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+        lo[4 * c + 0] = __float_as_uint(tf32_rna(v.x - h0)); lo[4 * c + 1] = __float_as_uint(tf32_rna(v.y - h1));
+        lo[4 * c + 2] = __float_as_uint(tf32_rna(v.z - h2)); lo[4 * c + 3] = __float_as_uint(tf32_rna(v.w - h3));
       }
-#pragma unroll
-      for (int i = 0; i < ((int)(kWBytes / 16) + 127) / 128; ++i) {
-        const int v = ct + i * 128;
-        if (v < (int)(kWBytes / 16)) {
-          float4 h, l;
-          split4(wr[v], h, l);
-          wh[v] = h;
-          wl[v] = l;
-        }
-      }
-      tc::fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(conv_full + cs);
-        tc::mbar_arrive(raw_empty + rs);
-      }
-      if (++rs == kLinRaw) { rs = 0; rph ^= 1; }
-      if (++cs == kLinConv) { cs = 0; cph ^= 1; }
+      if (lane == 0) tc::mbar_arrive(empty + s);          // x part of the stage consumed (W part: MMA commit)
+      tc::mbar_wait(a_empty + ab, aph ^ 1);                // previous MMAs on this A buffer retired
+      tc::fence_after_sync();
+      tmem_st_32x32(tmem_a0 + lane_addr + ab * 64, hi);
+      tmem_st_32x32(tmem_a0 + lane_addr + ab * 64 + 32, lo);
+      tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(a_full + ab);
     }
     // ---------------- epilogue: thread == output row ----------------
-    const int q = warp & 3;
-    const int row = row0 + q * 32 + lane;
+    const int row = row0 + r_in_tile;
     tc::mbar_wait(acc_full, 0);
     tc::fence_after_sync();
 #pragma unroll
     for (int c0 = 0; c0 < H; c0 += 16) {
       uint32_t r[16];
-      tc::tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, r);
+      tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r);
       tc::tmem_ld_wait();
       if (row < n) {
         float* dst = out + (size_t)row * H + c0;
@@ -198,34 +221,52 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 
 template <int H>
 static int launch_linear(const float* x, const float* w, const float* b, float slope, int n, int f, float* out,
-                         cudaStream_t st) {
-  CUtensorMap tm_x, tm_w;
-  int rc = make_tmap_2d_f32(&tm_x, x, (uint64_t)n, (uint64_t)f, kLinBM, 32);
+                         float* ws, cudaStream_t st) {
+  constexpr int STAGES = (H <= 64) ? 3 : 4;   // H <= 64: 3 x 32 KB = 96 KB so that two CTAs share an SM (one wave for 2 x 148 tiles)
+  float* w_hi = ws;
+  float* w_lo = ws + (size_t)H * f;
+  split_w_kernel<<<(H * f + 255) / 256, 256, 0, st>>>(w, H * f, w_hi, w_lo);
+  int rc = launch_status();
   if (rc != DGGB_OK) return rc;
-  rc = make_tmap_2d_f32(&tm_w, w, (uint64_t)H, (uint64_t)f, H, 32);
+  CUtensorMap tm_x, tm_whi, tm_wlo;
+  rc = make_tmap_2d_f32(&tm_x, x, (uint64_t)n, (uint64_t)f, kLinBM, 32);
   if (rc != DGGB_OK) return rc;
-  const size_t smem = LinRaw<H>::value * (kLinBM * 128 + H * 128) + kLinConv * (2 * kLinBM * 128 + 2 * H * 128) + 256 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  rc = make_tmap_2d_f32(&tm_whi, w_hi, (uint64_t)H, (uint64_t)f, H, 32);
+  if (rc != DGGB_OK) return rc;
+  rc = make_tmap_2d_f32(&tm_wlo, w_lo, (uint64_t)H, (uint64_t)f, H, 32);
+  if (rc != DGGB_OK) return rc;
+  const size_t smem = STAGES * (kLinBM * 128 + 2 * H * 128) + 256 + 1024;
+  cudaError_t e =
+      cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
-  linear_tf32x3_kernel<H><<<(n + kLinBM - 1) / kLinBM, kLinThreads, smem, st>>>(tm_x, tm_w, b, slope, n, f, out);
+  linear_tf32x3_kernel<H, STAGES><<<(n + kLinBM - 1) / kLinBM, kLinThreads, smem, st>>>(tm_x, tm_whi, tm_wlo, b,
+                                                                                        slope, n, f, out);
   return launch_status();
 }
 
 }  // namespace dggb
 using namespace dggb;
 
+extern "C" int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h) {
+  if (f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
+  return (int64_t)2 * h * f * 4;
+}
+
 extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
-                                   int32_t h, float* out, void* stream) {
-  if (!x || !w || !out || n < 0 || f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
+                                   int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
+  if (workspace_bytes < dggb_linear_act_workspace_bytes(f, h)) return DGGB_ERR_WORKSPACE;
+  if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
+  float* ws = reinterpret_cast<float*>(workspace);
   // TMA needs 16-byte row pitches and base addresses; the supported widths are the hidden sizes of the path
   if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16)) return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
   cudaStream_t st = as_stream(stream);
   switch (h) {
-    case 16: return launch_linear<16>(x, w, b, slope, n, f, out, st);
-    case 32: return launch_linear<32>(x, w, b, slope, n, f, out, st);
-    case 64: return launch_linear<64>(x, w, b, slope, n, f, out, st);
-    case 128: return launch_linear<128>(x, w, b, slope, n, f, out, st);
+    case 16: return launch_linear<16>(x, w, b, slope, n, f, out, ws, st);
+    case 32: return launch_linear<32>(x, w, b, slope, n, f, out, ws, st);
+    case 64: return launch_linear<64>(x, w, b, slope, n, f, out, ws, st);
+    case 128: return launch_linear<128>(x, w, b, slope, n, f, out, ws, st);
     default: return DGGB_ERR_BAD_SHAPE;
   }
 }

@@ -248,8 +248,9 @@ def _linear_act_tc(x, w, b, slope):
     h = w.shape[0]
     out = torch.empty(n, h, dtype=torch.float32, device=x.device)
     bb = None if b is None else b.contiguous()
+    ws = torch.empty(2 * h * f_in, dtype=torch.float32, device=x.device)
     rc = lib().dggb_linear_act_fwd(p(x), p(w), p(bb), ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out),
-                                   stream())
+                                   p(ws), ctypes.c_int64(ws.numel() * 4), stream())
     if rc == -2:
         return None
     check(rc, "linear_act_fwd")
