@@ -167,6 +167,11 @@ int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float sl
 int dggb_gemm_tn_splitk(const float* a /* [N,P] */, const float* b /* [N,Q] */, int32_t n, int32_t p,
                         int32_t q, float* out /* [P,Q] */, float* colsum_a /* [P] or NULL */,
                         void* stream);
+/* Same contract on the tcgen05 tensor cores (3xTF32 split in-kernel, b streamed by TMA once,
+ * a transposed + split into the workspace).  Requires Q % 4 == 0, P in {16,32,64,128}. */
+int64_t dggb_gemm_tn_tc_workspace_bytes(int32_t n, int32_t p);
+int dggb_gemm_tn_tc(const float* a, const float* b, int32_t n, int32_t p, int32_t q, float* out,
+                    float* colsum_a, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * All-pairs scoring + per-row streaming top-K (legacy all-pairs DGG, dgm.py:271-301; a15):

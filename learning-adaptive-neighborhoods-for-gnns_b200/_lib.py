@@ -33,7 +33,8 @@ def lib():
         _lib.dggb_error_string.restype = ctypes.c_char_p
         for name in declared_symbols():
             fn = getattr(_lib, name)
-            if name in ("dggb_kernel_launches", "dggb_allpairs_workspace_bytes", "dggb_linear_act_workspace_bytes"):
+            if name in ("dggb_kernel_launches", "dggb_allpairs_workspace_bytes", "dggb_linear_act_workspace_bytes",
+                        "dggb_gemm_tn_tc_workspace_bytes"):
                 fn.restype = ctypes.c_longlong
             elif name != "dggb_error_string":
                 fn.restype = ctypes.c_int

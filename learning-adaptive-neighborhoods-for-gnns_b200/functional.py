@@ -257,7 +257,7 @@ def _linear_act_tc(x, w, b, slope):
     return out
 
 
-def gemm_tn(a, b, want_colsum=False):
+def gemm_tn(a, b, want_colsum=False, use_tc=None):
     """(a^T b [P,Q], column sums of a [P] or None) for tall a [N,P], b [N,Q] via dggb_gemm_tn_splitk."""
     a, b = _f32c(a), _f32c(b)
     n, pp = a.shape
@@ -265,7 +265,19 @@ def gemm_tn(a, b, want_colsum=False):
     buf = torch.zeros(pp * q + (pp if want_colsum else 0), dtype=torch.float32, device=a.device)
     out = buf[:pp * q].view(pp, q)
     cs = buf[pp * q:] if want_colsum else None
-    check(lib().dggb_gemm_tn_splitk(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), stream()), "gemm_tn_splitk")
+    if use_tc is None:
+        use_tc = n >= 4096 and q % 4 == 0 and pp in (16, 32, 64, 128)
+    if use_tc:
+        import ctypes
+
+        L = lib()
+        ws_bytes = int(L.dggb_gemm_tn_tc_workspace_bytes(i32(n), i32(pp)))
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
+        check(L.dggb_gemm_tn_tc(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), p(ws), ctypes.c_int64(ws_bytes),
+                                stream()), "gemm_tn_tc")
+    else:
+        check(lib().dggb_gemm_tn_splitk(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), stream()),
+              "gemm_tn_splitk")
     return out, cs
 
 

@@ -207,7 +207,8 @@ def test_model_gcn_dgg_00_matches_reference_golden(golden):
         torch.testing.assert_close(q.grad.cpu(), c["grads"][k], rtol=1e-3, atol=1e-4), k
 
 
-@pytest.mark.parametrize("n,p,q", [(19717, 64, 500), (1000, 64, 64), (333, 16, 30), (5000, 128, 602), (40, 24, 7)])
+@pytest.mark.parametrize("n,p,q", [(19717, 64, 500), (1000, 64, 64), (333, 16, 30), (5000, 128, 602), (40, 24, 7),
+                                   (4500, 32, 128), (6001, 128, 600)])
 def test_gemm_tn_splitk(n, p, q):
     """dW = a^T b and db = colsum(a) vs torch (fp32; split-K sums in a different order: rtol 1e-4)."""
     from dgg_b200 import functional as K
@@ -215,10 +216,11 @@ def test_gemm_tn_splitk(n, p, q):
     gen = torch.Generator().manual_seed(n)
     a = torch.randn(n, p, generator=gen).cuda()
     b = torch.randn(n, q, generator=gen).cuda()
-    out, cs = K.gemm_tn(a, b, True)
     want = (a.double().t() @ b.double()).float()
-    torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-3)
-    torch.testing.assert_close(cs, a.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+    for use_tc in ([False, True] if (q % 4 == 0 and p in (16, 32, 64, 128)) else [False]):
+        out, cs = K.gemm_tn(a, b, True, use_tc=use_tc)    # SIMT split-K and tcgen05 3xTF32 variants
+        torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(cs, a.double().sum(0).float(), rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("n,f,h,slope", [(19717, 500, 64, 0.01), (1000, 64, 64, 1.0), (4097, 128, 16, 0.01),
