@@ -249,10 +249,10 @@ def run_ours(args, rank, local_rank, world):
     flat_grads = None
 
     def eager_step(s, static_grads=False):
-        for p in params:
-            if static_grads:
-                p.grad.zero_()      # graphs share ONE set of static .grad buffers, accumulated in place
-            else:
+        if static_grads:
+            flat_grads.zero_()      # graphs share ONE flat static .grad buffer, accumulated in place
+        else:
+            for p in params:
                 p.grad = None
         out, x_enc = m(s["x"], s["adj"])
         torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"], s["g_xenc"]])
@@ -262,18 +262,21 @@ def run_ours(args, rank, local_rank, world):
     # device replays its step); --no-graph times the eager path instead
     graphed = None
     if not args.no_graph:
-        for p in params:
-            p.grad = torch.zeros_like(p)
+        from dgg_b200.sharding import flatten_grads
+
+        flat_grads = flatten_grads(params)
         graphed = [dgg_b200.GraphedStep(lambda s=s: eager_step(s, True)) for s in dsets]
 
     def step_resident(i):
         if graphed is not None:
             graphed[i % N_SETS]()
+            if world > 1:
+                dist.all_reduce(flat_grads)     # one NCCL kernel over the flat static gradient buffer
         else:
             eager_step(dsets[i % N_SETS])
-        if world > 1:
-            flat = torch.cat([p.grad.flatten() for p in params])
-            dist.all_reduce(flat)
+            if world > 1:
+                flat = torch.cat([p.grad.flatten() for p in params])
+                dist.all_reduce(flat)
 
     # ---- host-buffer inputs (the `e2e` arm): what train_small_graphs.py does every call ----
     pinned = [dict(idx=s["idx"].pin_memory(), val=s["val"].pin_memory(), x=s["x"].pin_memory()) for s in host_sets]
@@ -375,8 +378,11 @@ def kernel_roofline(m, dsets, shape, iters=30):
     E = prepared[0][0].nnz
 
     def timed(fn):
-        for i in range(3):
+        t_end = time.perf_counter() + 0.05      # >= 50 ms of back-to-back launches first: the clocks have
+        i = 0                                   # dropped while the host was busy, let them ramp up again
+        while time.perf_counter() < t_end or i < 20:
             fn(i)
+            i += 1
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -412,18 +418,49 @@ def kernel_roofline(m, dsets, shape, iters=30):
 
     t_fwd = timed(fwd)
     t_bwd = timed(bwd)
-    # algorithmic bytes (SURVEY 8d, int32 CSR): see DESIGN.md "dgg_edge"
+
+    # the two tensor-core GEMM kernels of the node encoder (forward, weight gradient), outputs preallocated
+    import ctypes
+    f_in = shape["f"]
+    enc = m.node_encoder[0]
+    w_enc, b_enc = enc.weight.detach().contiguous(), enc.bias.detach().contiguous()
+    xs = [s["x"] for s in dsets]
+    x_out = torch.empty(n, h, device=dev)
+    ws_lin = torch.empty(2 * h * f_in, device=dev)
+    dpre = torch.randn(n, h, device=dev)
+    dw_out = torch.zeros(h * f_in + h, device=dev)
+    L = lib()
+    ws_tn_bytes = int(L.dggb_gemm_tn_tc_workspace_bytes(i32(n), i32(h)))
+    ws_tn = torch.empty(ws_tn_bytes // 4, device=dev)
+
+    def lin(i):
+        check(L.dggb_linear_act_fwd(p(xs[i % N_SETS]), p(w_enc), p(b_enc), ctypes.c_float(0.01), i32(n), i32(f_in),
+                                    i32(h), p(x_out), p(ws_lin), ctypes.c_int64(ws_lin.numel() * 4), stream()), "lin")
+
+    def tn(i):
+        check(L.dggb_gemm_tn_tc(p(dpre), p(xs[i % N_SETS]), i32(n), i32(h), i32(f_in), p(dw_out[:h * f_in]),
+                                p(dw_out[h * f_in:]), p(ws_tn), ctypes.c_int64(ws_tn_bytes), stream()), "tn")
+
+    t_lin = timed(lin)
+    t_tn = timed(tn)
+    # algorithmic bytes (int32 CSR, fp32)
     b_fwd = E * (4 + 4 * h) + n * (4 * h + 12) + E * 12
     b_bwd = E * (4 + 4 * h + 12) + E * 4 * h + n * (4 * h * 2 + 12)
-    name, t, b = (("dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd) if t_bwd >= t_fwd
-                  else ("dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd))
+    b_lin = n * f_in * 4 + n * h * 4 + h * f_in * 4
+    b_tn = n * f_in * 4 + n * h * 4 + h * f_in * 4
+    cands = [("linear_tf32x3_kernel (+ split_w)", t_lin, b_lin),
+             ("gemm_tn_tf32x3_kernel (+ transpose_split)", t_tn, b_tn),
+             ("dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd),
+             ("dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd)]
+    name, t, b = max(cands, key=lambda c: c[1])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get(name)
     return dict(bound="hbm", kernel=name, achieved=b / t / 1e9, peak=peak, unit="GB/s", frac=b / t / 1e9 / peak,
                 traffic=traffic, peak_source=peak_src, algorithmic_bytes=int(b), kernel_us=t * 1e6,
-                others={"dgg_edge_fwd_pair_us": t_fwd * 1e6, "dgg_edge_bwd_pair_us": t_bwd * 1e6})
+                others={c[0]: dict(us=c[1] * 1e6, algorithmic_bytes=int(c[2]), gbps=c[2] / c[1] / 1e9,
+                                  frac=c[2] / c[1] / 1e9 / peak) for c in cands})
 
 
 # --------------------------------------------------------------------------- Reddit-shape all-pairs arm

@@ -75,6 +75,18 @@ def all_reduce_grads(params, group=None):
         off += g.numel()
 
 
+def flatten_grads(params):
+    """Back every ``p.grad`` by a view into ONE flat buffer, so a single all-reduce of that buffer (no
+    concatenation, capturable in a CUDA graph) sums all replicated-parameter gradients.  Returns the buffer."""
+    params = [p for p in params if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return flat
+
+
 def sharded_allpairs_topk(z_local, t, n, kc, group=None, precision=3, seed=0, noise_scale=0.0, noise_local=None):
     """Row-sharded all-pairs top-K: all-gather the embeddings, score this rank's row block against all
     columns.  Returns (idx [cnt,kc] global column ids, y [cnt,kc]); gradients flow back to ``z_local``
