@@ -171,7 +171,11 @@ class DGG_LearnableK_SDD(nn.Module):
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
                 idx, y = K.allpairs_topk(z, self.t, None, kc, self.precision, seed=seed, noise_scale=1.0)
         else:
-            raise NotImplementedError("evaluation (softmax) branch lands with the fused softmax epilogue")
+            # evaluation branch (dgm.py:298): edge_prob = softmax(log_p / temp) over ALL columns.  The ordering is
+            # that of log_p; the normaliser sum_j exp(log_p_ij / temp) is accumulated by the same streaming pass.
+            # Forward only (inference): the normaliser's gradient would touch all N^2 pairs.
+            idx, logp, zsum = K.allpairs_topk(z, self.t, None, kc, self.precision, inv_temp=1.0 / float(temp))
+            y = (torch.exp(logp / float(temp)) / zsum.unsqueeze(-1)).detach()
         r = torch.arange(kc, device=x.device, dtype=torch.float32).reshape(1, kc)
         first_k = torch.sigmoid(self.hs_start - self.interval * r + (k - 1) * self.interval)   # dgm.py:315-326
         vals = y * first_k

@@ -194,6 +194,8 @@ int dggb_gemm_tn_tc(const float* a, const float* b, int32_t n, int32_t p, int32_
  *          communication (tests/philox_ref.py is the host restatement).
  *   out_idx/out_val: [row_count, kc]; unused slots (n < kc) hold idx -1 / val 0.
  *   workspace: dggb_allpairs_workspace_bytes(n, d) bytes (hi/lo split of z + squared norms).
+ *   out_rowsum (optional): sum_j exp(y_ij * inv_temp) over ALL n columns -- the normaliser of the
+ *          evaluation branch softmax(log_p / temp) (dgm.py:298), accumulated in the same pass.
  * Requires d <= 128, kc <= 64.
  * ---------------------------------------------------------------------------------- */
 int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d);
@@ -201,7 +203,8 @@ int dggb_allpairs_topk_fwd(const float* z /* [n,d] */, int32_t n, int32_t d, int
                            int32_t row_count, const float* t /* [1] device */, const float* noise,
                            int64_t noise_ld, uint64_t seed, float noise_scale, int32_t kc,
                            int32_t precision, void* workspace,
-                           int64_t workspace_bytes, int32_t* out_idx, float* out_val, void* stream);
+                           int64_t workspace_bytes, int32_t* out_idx, float* out_val, float inv_temp,
+                           float* out_rowsum /* [row_count] or NULL */, void* stream);
 /* Backward by recomputation over the selected pairs only (O(rows*kc*d)):
  * dz[n,d] and dt[1] are ACCUMULATED INTO. */
 int dggb_allpairs_pair_bwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,

@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(kAPThreads, 1)
                          const float* __restrict__ nrm, int n, int row_begin, int row_count,
                          const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
                          unsigned long long seed, float noise_scale, int kc, int stages,
-                         int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                         int32_t* __restrict__ out_idx, float* __restrict__ out_val, float inv_temp,
+                         float* __restrict__ out_rowsum) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B align WITHOUT laundering the pointer through an integer (keeps it a shared-space pointer, so
   // every access below compiles to LDS/STS instead of generic LD/ST)
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(kAPThreads, 1)
     int32_t* qi = reinterpret_cast<int32_t*>(smem + L.qi);
     float thr = -INFINITY;   // this row's current K-th best value (stale between merges: only admits extras)
     int qn = 0;              // pending candidates of this row
+    float zsum = 0.f;        // sum_j exp(y_ij * inv_temp): the softmax normaliser of the evaluation branch
     const float* nz = (NOISE == 1 && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const bool wide = kc > 32;
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(kAPThreads, 1)
                 yy += gumbel_from_bits(b, noise_scale);
               }
               y[c] = yy;
+              if (out_rowsum != nullptr && j < n) zsum += __expf(yy * inv_temp);
               pass |= (j < n && yy > thr) ? (1u << c) : 0u;
             }
             // phase 2 (rare once the list is warm): append the survivors to this row's queue
@@ -467,6 +470,7 @@ __global__ void __launch_bounds__(kAPThreads, 1)
       }
     }
     flush(__ballot_sync(0xffffffffu, qn > 0));
+    if (out_rowsum != nullptr && row_ok) out_rowsum[lrow] = zsum;
     // ---- write the sorted lists: lanes sweep the list positions of one row at a time ----
     __syncwarp();
     for (int rr = 0; rr < 32; ++rr) {
@@ -561,7 +565,8 @@ extern "C" int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d) {
 extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
                                       const float* t, const float* noise, int64_t noise_ld, uint64_t seed,
                                       float noise_scale, int32_t kc, int32_t precision, void* workspace,
-                                      int64_t workspace_bytes, int32_t* out_idx, float* out_val, void* stream) {
+                                      int64_t workspace_bytes, int32_t* out_idx, float* out_val, float inv_temp,
+                                      float* out_rowsum, void* stream) {
   if (!z || !t || !workspace || !out_idx || !out_val || n <= 0 || d <= 0 || row_begin < 0 || row_count < 0 || kc <= 0)
     return DGGB_ERR_BAD_ARG;
   if (d > 128 || kc > 64) return DGGB_ERR_BAD_SHAPE;
@@ -601,7 +606,7 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
     if (e != cudaSuccess) return cuda_status(e);                                                                  \
     allpairs_topk_kernel<KB_, SP_, NM_><<<grid, kAPThreads, smem_bytes, st>>>(                                    \
         tm_hi, tm_lo, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld, (unsigned long long)seed,      \
-        noise_scale, kc, stages, out_idx, out_val);                                                               \
+        noise_scale, kc, stages, out_idx, out_val, inv_temp, out_rowsum);                                         \
   } while (0)
 #define DGGB_AP_LAUNCH(KB_, SP_)                                                                                  \
   do {                                                                                                            \

@@ -127,7 +127,7 @@ class _AllPairsTopK(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, t, noise, kc: int, precision: int, row_begin: int, row_count: int, seed: int,
-                noise_scale: float):
+                noise_scale: float, inv_temp: float = 0.0):
         import ctypes
 
         from ._lib import i64
@@ -139,20 +139,25 @@ class _AllPairsTopK(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
         idx = torch.empty(row_count, kc, dtype=torch.int32, device=z.device)
         val = torch.empty(row_count, kc, dtype=torch.float32, device=z.device)
+        rowsum = torch.empty(row_count, dtype=torch.float32, device=z.device) if inv_temp != 0.0 else None
         if noise is not None:
             noise = _f32c(noise)
             assert noise.dim() == 2 and noise.shape[0] == row_count and noise.shape[1] >= n
         check(L.dggb_allpairs_topk_fwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(t), p(noise),
                                        i64(0 if noise is None else noise.stride(0)), ctypes.c_uint64(seed),
                                        ctypes.c_float(noise_scale), i32(kc), i32(precision), p(ws),
-                                       i64(ws_bytes), p(idx), p(val), stream()), "allpairs_topk_fwd")
+                                       i64(ws_bytes), p(idx), p(val), ctypes.c_float(inv_temp), p(rowsum), stream()),
+              "allpairs_topk_fwd")
         ctx.meta = (kc, row_begin, row_count)
         ctx.save_for_backward(z, t, idx)
         ctx.mark_non_differentiable(idx)
+        if rowsum is not None:
+            ctx.mark_non_differentiable(rowsum)
+            return idx, val, rowsum
         return idx, val
 
     @staticmethod
-    def backward(ctx, _gidx, gy):
+    def backward(ctx, _gidx, gy, *_unused):
         z, t, idx = ctx.saved_tensors
         kc, row_begin, row_count = ctx.meta
         n, d = z.shape
@@ -160,16 +165,18 @@ class _AllPairsTopK(torch.autograd.Function):
         dt = torch.zeros(1, dtype=torch.float32, device=z.device)
         check(lib().dggb_allpairs_pair_bwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(idx),
                                            p(_f32c(gy)), i32(kc), p(t), p(dz), p(dt), stream()), "allpairs_pair_bwd")
-        return dz, dt, None, None, None, None, None, None, None
+        return dz, dt, None, None, None, None, None, None, None, None
 
 
-def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=None, seed=0, noise_scale=0.0):
+def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=None, seed=0, noise_scale=0.0,
+                  inv_temp=0.0):
     """-> (idx int32 [rows,kc], y fp32 [rows,kc]) sorted descending per row; differentiable in z and t.
-    noise: injected [rows, n] tensor, or None with noise_scale != 0 for in-kernel Philox Gumbel noise."""
+    noise: injected [rows, n] tensor, or None with noise_scale != 0 for in-kernel Philox Gumbel noise.
+    inv_temp != 0 additionally returns rowsum [rows] = sum_j exp(y_ij * inv_temp) over all columns."""
     if row_count is None:
         row_count = z.shape[0] - row_begin
     return _AllPairsTopK.apply(z, t, noise, int(kc), int(precision), int(row_begin), int(row_count), int(seed),
-                               float(noise_scale))
+                               float(noise_scale), float(inv_temp))
 
 
 class _RowFirstK(torch.autograd.Function):

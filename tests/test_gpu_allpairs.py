@@ -123,6 +123,10 @@ def test_legacy_allpairs_module_matches_reference_golden(golden):
     for name, q in m.named_parameters():
         if name in c["grads"] and c["grads"][name] is not None and q.grad is not None:
             torch.testing.assert_close(q.grad.cpu(), c["grads"][name], rtol=5e-3, atol=5e-4), name
+    # evaluation branch: softmax(log_p / temp) over all columns, then the same first-k weighting
+    with torch.no_grad():
+        adj_e, _ = m(c["x"].cuda().unsqueeze(0), temp=10.0, noise=False)
+    torch.testing.assert_close(adj_e.to_dense().cpu(), c["out_eval_t10"], rtol=2e-4, atol=1e-6)
 
 
 def test_philox_noise_matches_host_restatement():
