@@ -47,12 +47,11 @@ class _EdgeRankerBase(nn.Module):
         assert x.ndim == 2
         assert len(adj.shape) == 2
         graph, _ = CSRGraph.from_coo(adj)
-        enc = self.node_encoder[0]
-        x_enc = K.tall_linear(x, enc.weight, enc.bias, self.node_encoder[1].negative_slope)   # dgm.py:1778
-        lin = self.edge_encoder[0]
+        enc, lin = self.node_encoder[0], self.edge_encoder[0]
         # Linear is linear: We (x_u - x_v) + be == y_u - y_v + be with y = x_enc We^T, so the per-edge
         # E x h x h GEMM of dgm.py:1783-1784 becomes one N x h x h GEMM plus a gather.
-        y = K.tall_linear(x_enc, lin.weight)
+        x_enc, y = K.encode_project(x, enc.weight, enc.bias, lin.weight,
+                                    self.node_encoder[1].negative_slope)                       # dgm.py:1778, 1784
         dd = self.degree_decoder[0]
         out_vals, k, R, rank = K.dgg_edge(y, lin.bias, dd.weight, dd.bias, graph, noise, hard_k)
         self.last_k = k

@@ -154,6 +154,15 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
  * b may be NULL.
  * ---------------------------------------------------------------------------------- */
 int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h);   /* hi/lo split of W */
+/* General form used by the fused encoder backward:
+ *   v = x W_eff^T + b + addend;   out = act_src ? v * LeakyReLU'_slope(act_src) : LeakyReLU_slope(v)
+ * W_eff = w ([H,F]) or, with w_transposed, w^T (w given as [F,H]).  With x = dy, w = We (transposed),
+ * addend = dL/dx_enc, act_src = x_enc this is d pre = LeakyReLU'(x_enc) * (dy We + dL/dx_enc) in one pass
+ * (autograd of dgm.py:1778-1784).  b / addend / act_src may be NULL. */
+int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
+                      const float* addend /* [N,H] */, const float* act_src /* [N,H] */, float slope,
+                      int32_t n, int32_t f, int32_t h, float* out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
 int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
                         int32_t f, int32_t h, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);

@@ -47,7 +47,6 @@ __global__ void __launch_bounds__(256)
     }
   }
   if (colsum != nullptr) {
-    // reduce the 8 partial sums per column through shared memory, one atomic per column per block
     __syncthreads();
     tile[ty][tx] = cs;
     __syncthreads();

@@ -19,9 +19,11 @@ constexpr int kLinThreads = 192;
 using tc::tf32_rna;
 
 // W -> (hi, lo) TF32 split, once per call (W is tiny: H x F)
-__global__ void split_w_kernel(const float* __restrict__ w, int count, float* __restrict__ hi, float* __restrict__ lo) {
+// (transposed: w is given as [F, H] and the kernel needs W_eff[h][f] = w[f][h])
+__global__ void split_w_kernel(const float* __restrict__ w, int count, int h, int f, int transposed,
+                               float* __restrict__ hi, float* __restrict__ lo) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const float v = __ldg(w + i);
+    const float v = transposed ? __ldg(w + (size_t)(i % f) * h + (i / f)) : __ldg(w + i);
     const float h = tf32_rna(v);
     hi[i] = h;
     lo[i] = tf32_rna(v - h);
@@ -39,7 +41,8 @@ using tc::tmem_st_wait;
 template <int H, int STAGES>
 __global__ void __launch_bounds__(kLinThreads, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
-                         const __grid_constant__ CUtensorMap tm_wlo, const float* __restrict__ bias, float slope,
+                         const __grid_constant__ CUtensorMap tm_wlo, const float* __restrict__ bias,
+                         const float* __restrict__ addend, const float* __restrict__ act_src, float slope,
                          int n, int f, float* __restrict__ out) {
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
@@ -160,29 +163,51 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a_full + ab);
     }
-    // ---------------- epilogue: thread == output row ----------------
-    const int row = row0 + r_in_tile;
+    // ---------------- epilogue: TMEM -> registers -> this warp's shared-memory slice -> coalesced rows -------
+    // (every stage buffer has been consumed by now: all TMA loads landed and all MMAs retired before acc_full)
     tc::mbar_wait(acc_full, 0);
     tc::fence_after_sync();
+    constexpr int kPitch = H + 1;                                   // odd pitch: conflict-free column writes
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * kPitch;
 #pragma unroll
     for (int c0 = 0; c0 < H; c0 += 16) {
       uint32_t r[16];
       tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r);
       tc::tmem_ld_wait();
-      if (row < n) {
-        float* dst = out + (size_t)row * H + c0;
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) {
-          float4 v;
-          v.x = __uint_as_float(r[c]) + (bias ? __ldg(bias + c0 + c) : 0.f);
-          v.y = __uint_as_float(r[c + 1]) + (bias ? __ldg(bias + c0 + c + 1) : 0.f);
-          v.z = __uint_as_float(r[c + 2]) + (bias ? __ldg(bias + c0 + c + 2) : 0.f);
-          v.w = __uint_as_float(r[c + 3]) + (bias ? __ldg(bias + c0 + c + 3) : 0.f);
-          v.x = v.x > 0.f ? v.x : slope * v.x;
-          v.y = v.y > 0.f ? v.y : slope * v.y;
-          v.z = v.z > 0.f ? v.z : slope * v.z;
-          v.w = v.w > 0.f ? v.w : slope * v.w;
-          *reinterpret_cast<float4*>(dst + c) = v;
+      for (int c = 0; c < 16; ++c) stg[lane * kPitch + c0 + c] = __uint_as_float(r[c]);
+    }
+    __syncwarp();
+    // rows in batches of 8 with all global loads issued first (independent iterations => latency overlapped)
+    constexpr int kCols = H / 32 > 0 ? H / 32 : 1;       // columns per lane (H = 16: lanes >= 16 idle)
+    float bv[kCols];
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) bv[j] = (bias && lane + 32 * j < H) ? __ldg(bias + lane + 32 * j) : 0.f;
+    for (int rb = 0; rb < 32; rb += 8) {
+      float ad[8][kCols], ac[8][kCols];
+#pragma unroll
+      for (int r8 = 0; r8 < 8; ++r8) {
+        const int row = row0 + q * 32 + rb + r8;
+#pragma unroll
+        for (int j = 0; j < kCols; ++j) {
+          const int c = lane + 32 * j;
+          const bool ok = row < n && c < H;
+          ad[r8][j] = (addend != nullptr && ok) ? __ldg(addend + (size_t)row * H + c) : 0.f;
+          ac[r8][j] = (act_src != nullptr && ok) ? __ldg(act_src + (size_t)row * H + c) : 1.f;
+        }
+      }
+#pragma unroll
+      for (int r8 = 0; r8 < 8; ++r8) {
+        const int row = row0 + q * 32 + rb + r8;
+#pragma unroll
+        for (int j = 0; j < kCols; ++j) {
+          const int c = lane + 32 * j;
+          if (row < n && c < H) {
+            float v = stg[(rb + r8) * kPitch + c] + bv[j] + ad[r8][j];
+            if (act_src != nullptr) v *= ac[r8][j] > 0.f ? 1.f : slope;
+            else v = v > 0.f ? v : slope * v;
+            out[(size_t)row * H + c] = v;
+          }
         }
       }
     }
@@ -197,12 +222,12 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 }
 
 template <int H>
-static int launch_linear(const float* x, const float* w, const float* b, float slope, int n, int f, float* out,
-                         float* ws, cudaStream_t st) {
+static int launch_linear(const float* x, const float* w, int w_transposed, const float* b, const float* addend,
+                         const float* act_src, float slope, int n, int f, float* out, float* ws, cudaStream_t st) {
   constexpr int STAGES = (H <= 64) ? 3 : 4;   // H <= 64: 3 x 32 KB = 96 KB so that two CTAs share an SM (one wave for 2 x 148 tiles)
   float* w_hi = ws;
   float* w_lo = ws + (size_t)H * f;
-  split_w_kernel<<<(H * f + 255) / 256, 256, 0, st>>>(w, H * f, w_hi, w_lo);
+  split_w_kernel<<<(H * f + 255) / 256, 256, 0, st>>>(w, H * f, H, f, w_transposed, w_hi, w_lo);
   int rc = launch_status();
   if (rc != DGGB_OK) return rc;
   CUtensorMap tm_x, tm_whi, tm_wlo;
@@ -216,8 +241,8 @@ static int launch_linear(const float* x, const float* w, const float* b, float s
   cudaError_t e =
       cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
-  linear_tf32x3_kernel<H, STAGES><<<(n + kLinBM - 1) / kLinBM, kLinThreads, smem, st>>>(tm_x, tm_whi, tm_wlo, b,
-                                                                                        slope, n, f, out);
+  linear_tf32x3_kernel<H, STAGES><<<(n + kLinBM - 1) / kLinBM, kLinThreads, smem, st>>>(
+      tm_x, tm_whi, tm_wlo, b, addend, act_src, slope, n, f, out);
   return launch_status();
 }
 
@@ -229,21 +254,29 @@ extern "C" int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h) {
   return (int64_t)2 * h * f * 4;
 }
 
-extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
-                                   int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
+                                 const float* addend, const float* act_src, float slope, int32_t n, int32_t f,
+                                 int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
   if (workspace_bytes < dggb_linear_act_workspace_bytes(f, h)) return DGGB_ERR_WORKSPACE;
   if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
   float* ws = reinterpret_cast<float*>(workspace);
   // TMA needs 16-byte row pitches and base addresses; the supported widths are the hidden sizes of the path
-  if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16)) return DGGB_ERR_BAD_SHAPE;
+  if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16) ||
+      (addend && ((uintptr_t)addend % 16)) || (act_src && ((uintptr_t)act_src % 16)))
+    return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
   cudaStream_t st = as_stream(stream);
   switch (h) {
-    case 16: return launch_linear<16>(x, w, b, slope, n, f, out, ws, st);
-    case 32: return launch_linear<32>(x, w, b, slope, n, f, out, ws, st);
-    case 64: return launch_linear<64>(x, w, b, slope, n, f, out, ws, st);
-    case 128: return launch_linear<128>(x, w, b, slope, n, f, out, ws, st);
+    case 16: return launch_linear<16>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
+    case 32: return launch_linear<32>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
+    case 64: return launch_linear<64>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
+    case 128: return launch_linear<128>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
     default: return DGGB_ERR_BAD_SHAPE;
   }
+}
+
+extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
+                                   int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, workspace, workspace_bytes, stream);
 }

@@ -243,25 +243,67 @@ class _TallLinear(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def _linear_act_tc(x, w, b, slope):
-    """act(x W^T + b) through dggb_linear_act_fwd (tcgen05, 3xTF32); None if the shape is not supported."""
+def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None):
+    """out = epi(x W_eff^T + b + addend) through dggb_linear_fused (tcgen05, 3xTF32); None if the shape is
+    not supported.  epi = LeakyReLU(slope), or * LeakyReLU'(act_src) when act_src is given (backward form)."""
     import ctypes
 
+    h = w.shape[1] if w_transposed else w.shape[0]
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 4 == 0
-            and w.shape[0] in (16, 32, 64, 128) and x.shape[0] >= 512):
+            and h in (16, 32, 64, 128) and x.shape[0] >= 512):
         return None
     x, w = x.contiguous(), w.contiguous()
     n, f_in = x.shape
-    h = w.shape[0]
     out = torch.empty(n, h, dtype=torch.float32, device=x.device)
     bb = None if b is None else b.contiguous()
+    ad = None if addend is None else _f32c(addend)
+    ac = None if act_src is None else _f32c(act_src)
     ws = torch.empty(2 * h * f_in, dtype=torch.float32, device=x.device)
-    rc = lib().dggb_linear_act_fwd(p(x), p(w), p(bb), ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out),
-                                   p(ws), ctypes.c_int64(ws.numel() * 4), stream())
+    rc = lib().dggb_linear_fused(p(x), p(w), i32(1 if w_transposed else 0), p(bb), p(ad), p(ac),
+                                 ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out), p(ws),
+                                 ctypes.c_int64(ws.numel() * 4), stream())
     if rc == -2:
         return None
-    check(rc, "linear_act_fwd")
+    check(rc, "linear_fused")
     return out
+
+
+class _EncodeProject(torch.autograd.Function):
+    """(x_enc, y) = (LeakyReLU(x Wn^T + bn), x_enc We^T): the node encoder and the edge-encoder projection of
+    ``DGG`` (dgm.py:1778, 1784) as ONE autograd node, so the backward is three kernels:
+        dpre = LeakyReLU'(x_enc) * (g_y We + g_xenc)   (dggb_linear_fused)
+        dWe  = g_y^T x_enc ;  (dWn, dbn) = dpre^T x     (dggb_gemm_tn_tc)"""
+
+    @staticmethod
+    def forward(ctx, x, wn, bn, we, slope: float):
+        x_enc = _linear_act_tc(x, wn, bn, slope)
+        y = _linear_act_tc(x_enc, we, None, 1.0) if x_enc is not None else None
+        if y is None:
+            raise RuntimeError("encode_project: shape not supported by the tensor-core kernels")
+        ctx.slope = slope
+        ctx.save_for_backward(x, wn, we, x_enc)
+        return x_enc, y
+
+    @staticmethod
+    def backward(ctx, g_xenc, g_y):
+        x, wn, we, x_enc = ctx.saved_tensors
+        g_y = _f32c(g_y)
+        dpre = _linear_act_tc(g_y, we, None, ctx.slope, w_transposed=True, addend=g_xenc, act_src=x_enc)
+        dwe, _ = gemm_tn(g_y, x_enc, False)
+        dwn, dbn = gemm_tn(dpre, x, True)
+        dx = dpre @ wn if ctx.needs_input_grad[0] else None
+        return dx, dwn, dbn, dwe, None
+
+
+def encode_project(x, wn, bn, we, slope):
+    """-> (x_enc, y); falls back to two tall_linear nodes when the fused tensor-core path does not apply."""
+    n, f_in = x.shape
+    h = wn.shape[0]
+    if (x.is_cuda and x.dtype == torch.float32 and f_in % 4 == 0 and h in (16, 32, 64, 128) and n >= 512
+            and tuple(we.shape) == (h, h) and bn is not None):
+        return _EncodeProject.apply(x, wn, bn, we, float(slope))
+    x_enc = tall_linear(x, wn, bn, slope)
+    return x_enc, tall_linear(x_enc, we)
 
 
 def gemm_tn(a, b, want_colsum=False, use_tc=None):
@@ -273,7 +315,8 @@ def gemm_tn(a, b, want_colsum=False, use_tc=None):
     out = buf[:pp * q].view(pp, q)
     cs = buf[pp * q:] if want_colsum else None
     if use_tc is None:
-        use_tc = n >= 4096 and q % 4 == 0 and pp in (16, 32, 64, 128)
+        # wide outputs amortise the transpose pre-pass; narrow ones (dWe, Q = h) stay on the SIMT split-K kernel
+        use_tc = n >= 4096 and q % 4 == 0 and q >= 256 and pp in (16, 32, 64, 128)
     if use_tc:
         import ctypes
 
