@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include <climits>
+#include <cstdlib>
 
 namespace dggb {
 
@@ -253,7 +254,7 @@ __device__ __forceinline__ float merge_row(float* Lv, int32_t* Li, const float* 
   return kth;
 }
 
-// NOISE: 0 none, 1 injected tensor, 2 Philox Gumbel(0, noise_scale)
+// NOISE: 0 none, 1 injected tensor, 2 Philox Gumbel(0, noise_scale), 3 none + softmax normaliser (out_rowsum)
 template <int KB, int SPLIT, int NOISE>
 __global__ void __launch_bounds__(kAPThreads, 1)
     allpairs_topk_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(kAPThreads, 1)
                 yy += gumbel_from_bits(b, noise_scale);
               }
               y[c] = yy;
-              if (out_rowsum != nullptr && j < n) zsum += __expf(yy * inv_temp);
+              if (NOISE == 3 && j < n) zsum += __expf(yy * inv_temp);   // evaluation branch only
               pass |= (j < n && yy > thr) ? (1u << c) : 0u;
             }
             // phase 2 (rare once the list is warm): append the survivors to this row's queue
@@ -491,6 +492,297 @@ __global__ void __launch_bounds__(kAPThreads, 1)
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, 2 * kBN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 of the kernel above (kc <= 32): the SIMT epilogue is the bound, so it gets TWO warps per scheduler.
+//   * the query tile (A operand, hi/lo) lives in TENSOR MEMORY ("TS" MMA): each epilogue thread copies its own
+//     row global -> registers -> tcgen05.st once; that frees 64 KB of shared memory ...
+//   * ... which pays for a second, independent epilogue group: group g (4 warps) owns TMEM accumulator g and
+//     scores tiles jt = g, g+2, ... into its own per-row list/queue; the two sorted lists of a row are merged
+//     once at the end.  10 warps: w0 TMA producer, w1 MMA issuer, w2-5 group 0, w6-9 group 1.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAP2Threads = 320;
+
+struct AP2Smem {
+  uint32_t b0, b_stage_bytes, nrm, vals[2], idx[2], qv[2], qi[2], zpart, bars, total;
+};
+__host__ __device__ inline AP2Smem ap2_smem_layout(int kb, int split, int stages, int kc) {
+  AP2Smem L;
+  uint32_t off = 0;
+  L.b0 = off;
+  L.b_stage_bytes = kb * kBN * 128 * (split == 3 ? 2 : 1);
+  off += L.b_stage_bytes * stages;
+  L.nrm = off; off += stages * kBN * 4;
+  for (int g = 0; g < 2; ++g) {
+    L.vals[g] = off; off += kc * kBM * 4;
+    L.idx[g] = off; off += kc * kBM * 4;
+    L.qv[g] = off; off += kQCap * kBM * 4;
+    L.qi[g] = off; off += kQCap * kBM * 4;
+  }
+  L.zpart = off; off += kBM * 4;
+  L.bars = off; off += 128;
+  L.total = off;
+  return L;
+}
+
+template <int KB, int SPLIT, int NOISE>
+__global__ void __launch_bounds__(kAP2Threads, 1)
+    allpairs_topk2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                          const float* __restrict__ z_hi, const float* __restrict__ z_lo, int npad, int dpad,
+                          const float* __restrict__ nrm, int n, int row_begin, int row_count,
+                          const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
+                          unsigned long long seed, float noise_scale, int kc, int stages,
+                          int32_t* __restrict__ out_idx, float* __restrict__ out_val, float inv_temp,
+                          float* __restrict__ out_rowsum) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const AP2Smem L = ap2_smem_layout(KB, SPLIT, stages, kc);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* full = bars;            // [stages]  TMA -> MMA / epilogue
+  uint64_t* empty = bars + 4;       // [stages]  MMA commit + the 4 warps of the group that scored the tile
+  uint64_t* tfull = bars + 8;       // [2]       MMA -> epilogue group
+  uint64_t* tempty = bars + 10;     // [2]       epilogue group -> MMA
+  uint64_t* aready = bars + 12;     // query tile written to TMEM (8 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  constexpr uint32_t kTmemCols = (KB <= 2) ? 256 : 512;
+  constexpr uint32_t kAHi = 2 * kBN, kALo = 2 * kBN + KB * 32;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (n + kBN - 1) / kBN;
+  const int row0 = row_begin + blockIdx.x * kBM;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tm_hi);
+    if (SPLIT == 3) tc::tma_prefetch_desc(&tm_lo);
+    for (int s = 0; s < stages; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 5);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(tfull + b, 1);
+      tc::mbar_init(tempty + b, 4);
+    }
+    tc::mbar_init(aready, 8);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, kTmemCols);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: key tiles only =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
+        tc::mbar_wait_backoff(empty + s, ph ^ 1);
+        tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes + kBN * 4);
+        uint8_t* bs = smem + L.b0 + s * L.b_stage_bytes;
+        for (int kb = 0; kb < KB; ++kb) {
+          tc::tma_load_2d(bs + kb * kBN * 128, &tm_hi, full + s, kb * 32, jt * kBN);
+          if (SPLIT == 3) tc::tma_load_2d(bs + (KB + kb) * kBN * 128, &tm_lo, full + s, kb * 32, jt * kBN);
+        }
+        tc::bulk_load_1d(smem + L.nrm + s * kBN * 4, nrm + (size_t)jt * kBN, kBN * 4, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: A from TMEM, B from shared memory =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_tf32(kBM, kBN);
+      tc::mbar_wait_backoff(aready, 0);
+      tc::fence_after_sync();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
+        const int buf = jt & 1;
+        const uint32_t bph = (jt >> 1) & 1;
+        tc::mbar_wait_backoff(tempty + buf, bph ^ 1);
+        tc::mbar_wait_backoff(full + s, ph);
+        tc::fence_after_sync();
+        const uint32_t b_hi = tc::smem_u32(smem + L.b0 + s * L.b_stage_bytes);
+        const uint32_t b_lo = b_hi + KB * kBN * 128;
+        const uint32_t d_tmem = tmem_base + buf * kBN;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int sp = 0; sp < SPLIT; ++sp) {
+          const uint32_t a = tmem_base + ((sp == 2) ? kALo : kAHi);   // hi*hi, hi*lo, lo*hi
+          const uint32_t b = (sp == 1) ? b_lo : b_hi;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc::mma_tf32_ts(d_tmem, a + kb * 32 + ks * 8, tc::smem_desc_k128(b + kb * kBN * 128 + ks * 32), idesc,
+                              acc);
+              acc = 1;
+            }
+        }
+        tc::mma_commit(empty + s);
+        tc::mma_commit(tfull + buf);
+      }
+    }
+  } else {
+    // ================= two epilogue groups; thread == query row =================
+    const int g = (warp - 2) >> 2;                  // 0: even tiles / accumulator 0, 1: odd tiles / accumulator 1
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int row_t = q * 32 + lane;
+    const int lrow = blockIdx.x * kBM + row_t;
+    const bool row_ok = lrow < row_count && (row_begin + lrow) < n;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // ---- stage this thread's query row (group 0: hi part, group 1: lo part) into tensor memory ----
+    {
+      const int grow = row0 + row_t;
+      const float* src = (g == 0 ? z_hi : z_lo) + (size_t)grow * dpad;
+      const bool have = grow < npad && (g == 0 || SPLIT == 3);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        uint32_t r[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 v = have ? __ldg(reinterpret_cast<const float4*>(src + kb * 32 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          r[c] = __float_as_uint(v.x); r[c + 1] = __float_as_uint(v.y);
+          r[c + 2] = __float_as_uint(v.z); r[c + 3] = __float_as_uint(v.w);
+        }
+        if (g == 0 || SPLIT == 3) tc::tmem_st_32x32(tmem_base + lane_addr + (g == 0 ? kAHi : kALo) + kb * 32, r);
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(aready);
+    }
+    const float ni = row_ok ? __ldg(nrm + row_begin + lrow) : 0.f;
+    const float t = __ldg(t_ptr);
+    float* vals = reinterpret_cast<float*>(smem + L.vals[g]);
+    int32_t* idxs = reinterpret_cast<int32_t*>(smem + L.idx[g]);
+    float* qv = reinterpret_cast<float*>(smem + L.qv[g]);
+    int32_t* qi = reinterpret_cast<int32_t*>(smem + L.qi[g]);
+    for (int r = 0; r < kc; ++r) {
+      vals[r * kBM + row_t] = -INFINITY;
+      idxs[r * kBM + row_t] = -1;
+    }
+    float thr = -INFINITY;
+    int qn = 0;
+    float zsum = 0.f;
+    const float* nz = (NOISE == 1 && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    auto flush = [&](unsigned need) {
+      __syncwarp();
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n_q = __shfl_sync(0xffffffffu, qn, src);
+        const float kth = merge_row<1>(vals, idxs, qv, qi, kc, q * 32 + src, n_q, lane);
+        if (lane == src) {
+          thr = kth;
+          qn = 0;
+        }
+      }
+      __syncwarp();
+    };
+    int s = g % stages;
+    uint32_t ph = (g / stages) & 1;
+    uint32_t bph = 0;
+    for (int jt = g; jt < num_tiles; jt += 2) {
+      tc::mbar_wait(full + s, ph);
+      tc::mbar_wait(tfull + g, bph);
+      tc::fence_after_sync();
+      const float* nj = reinterpret_cast<const float*>(smem + L.nrm + s * kBN * 4);
+      const bool diag_tile = (jt * kBN < row0 + kBM) && (jt * kBN + kBN > row0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kBN; c0 += kChunk) {
+        uint32_t r[kChunk];
+        tc::tmem_ld_32x16(tmem_base + lane_addr + g * kBN + c0, r);
+        tc::tmem_ld_wait();
+        if (row_ok) {
+          const int jbase = jt * kBN + c0;
+          auto body = [&](auto diag_c) {
+            float y[kChunk];
+            float njv[kChunk];
+#pragma unroll
+            for (int c = 0; c < kChunk; c += 4) {
+              const float4 v4 = *reinterpret_cast<const float4*>(nj + c0 + c);
+              njv[c] = v4.x; njv[c + 1] = v4.y; njv[c + 2] = v4.z; njv[c + 3] = v4.w;
+            }
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            unsigned pass = 0u;
+#pragma unroll
+            for (int c = 0; c < kChunk; ++c) {
+              const int j = jbase + c;
+              float d2 = fmaf(-2.f, __uint_as_float(r[c]), ni + njv[c]);
+              if (decltype(diag_c)::value && j == row_begin + lrow) d2 = 0.f;
+              float yy = -t * sqrt_fast(fmaxf(d2, 0.f));
+              if (NOISE == 1) {
+                if (j < n) yy += __ldg(nz + j);
+              } else if (NOISE == 2) {
+                if ((c & 3) == 0) bits = philox4x32_7((uint32_t)(row_begin + lrow), (uint32_t)(j >> 2), key0, key1);
+                const uint32_t b = (c & 3) == 0 ? bits.x : ((c & 3) == 1 ? bits.y : ((c & 3) == 2 ? bits.z : bits.w));
+                yy += gumbel_from_bits(b, noise_scale);
+              }
+              y[c] = yy;
+              if (NOISE == 3 && j < n) zsum += __expf(yy * inv_temp);   // evaluation branch only
+              pass |= (j < n && yy > thr) ? (1u << c) : 0u;
+            }
+            if (pass) {
+#pragma unroll
+              for (int c = 0; c < kChunk; ++c) {
+                if (pass & (1u << c)) {
+                  qv[qn * kBM + row_t] = y[c];
+                  qi[qn * kBM + row_t] = jbase + c;
+                  ++qn;
+                }
+              }
+            }
+          };
+          if (diag_tile) body(std::true_type{});
+          else body(std::false_type{});
+        }
+        flush(__ballot_sync(0xffffffffu, qn >= kQFlush));
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(tempty + g);
+        tc::mbar_arrive(empty + s);
+      }
+      s += 2;
+      if (s >= stages) { s -= stages; ph ^= 1; }
+      bph ^= 1;
+    }
+    flush(__ballot_sync(0xffffffffu, qn > 0));
+    // ---- merge the two groups' lists (named barrier over the 8 epilogue warps), group 0 writes out ----
+    float* zpart = reinterpret_cast<float*>(smem + L.zpart);
+    if (g == 1) zpart[row_t] = zsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (g == 0) {
+      float* vals1 = reinterpret_cast<float*>(smem + L.vals[1]);
+      int32_t* idxs1 = reinterpret_cast<int32_t*>(smem + L.idx[1]);
+      for (int rr = 0; rr < 32; ++rr) {
+        const int rt = q * 32 + rr;
+        const int lr = blockIdx.x * kBM + rt;
+        if (!(lr < row_count && (row_begin + lr) < n)) continue;   // warp-uniform
+        merge_row<1>(vals, idxs, vals1, idxs1, kc, rt, kc, lane);
+        __syncwarp();
+        for (int r = lane; r < kc; r += kWarp) {
+          const int32_t id = idxs[r * kBM + rt];
+          out_idx[(size_t)lr * kc + r] = id;
+          out_val[(size_t)lr * kc + r] = id < 0 ? 0.f : vals[r * kBM + rt];
+        }
+      }
+      if (out_rowsum != nullptr && row_ok) out_rowsum[lrow] = zsum + zpart[row_t];
+    }
+  }
+  __syncwarp();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -590,6 +882,43 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   if (rc != DGGB_OK) return rc;
 
   const int kb = dpad / 32;
+  // ---- v2 (two epilogue groups, A in TMEM) whenever the second list/queue set fits: kc <= 32 ----
+  const int nmode2 = noise ? 1 : (noise_scale != 0.f ? 2 : (out_rowsum ? 3 : 0));
+  if (out_rowsum && nmode2 != 3) return DGGB_ERR_UNSUPPORTED;
+  if (kc <= 32 && !(kb == 4 && precision == 3) && !getenv("DGGB_AP_V1")) {
+    int st2 = 4;
+    AP2Smem L2 = ap2_smem_layout(kb, precision, st2, kc);
+    while (st2 > 2 && L2.total + 1024 > 227 * 1024) L2 = ap2_smem_layout(kb, precision, --st2, kc);
+    if (L2.total + 1024 <= 227 * 1024) {
+      const size_t smem2 = L2.total + 1024;
+      const int grid2 = (row_count + kBM - 1) / kBM;
+#define DGGB_AP2_LAUNCH1(KB_, SP_, NM_)                                                                           \
+  do {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(allpairs_topk2_kernel<KB_, SP_, NM_>,                                    \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);                \
+    if (e != cudaSuccess) return cuda_status(e);                                                                  \
+    allpairs_topk2_kernel<KB_, SP_, NM_><<<grid2, kAP2Threads, smem2, st>>>(                                      \
+        tm_hi, tm_lo, hi, lo, npad, dpad, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld,            \
+        (unsigned long long)seed, noise_scale, kc, st2, out_idx, out_val, inv_temp, out_rowsum);                  \
+  } while (0)
+#define DGGB_AP2_LAUNCH(KB_, SP_)                                                                                 \
+  do {                                                                                                            \
+    if (nmode2 == 0) DGGB_AP2_LAUNCH1(KB_, SP_, 0);                                                               \
+    else if (nmode2 == 1) DGGB_AP2_LAUNCH1(KB_, SP_, 1);                                                          \
+    else if (nmode2 == 2) DGGB_AP2_LAUNCH1(KB_, SP_, 2);                                                          \
+    else DGGB_AP2_LAUNCH1(KB_, SP_, 3);                                                                           \
+  } while (0)
+      if (kb == 1 && precision == 3) DGGB_AP2_LAUNCH(1, 3);
+      else if (kb == 1) DGGB_AP2_LAUNCH(1, 1);
+      else if (kb == 2 && precision == 3) DGGB_AP2_LAUNCH(2, 3);
+      else if (kb == 2) DGGB_AP2_LAUNCH(2, 1);
+      else if (kb == 4) DGGB_AP2_LAUNCH(4, 1);
+      else return DGGB_ERR_BAD_SHAPE;
+#undef DGGB_AP2_LAUNCH
+#undef DGGB_AP2_LAUNCH1
+      return launch_status();
+    }
+  }
   int stages = 4;
   APSmem L = ap_smem_layout(kb, precision, stages, kc);
   while (stages > 2 && L.total + 1024 > 227 * 1024) L = ap_smem_layout(kb, precision, --stages, kc);
@@ -598,7 +927,8 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   const int grid = (row_count + kBM - 1) / kBM;
 
   // noise mode: injected tensor if given, else Philox when noise_scale != 0, else none
-  const int nmode = noise ? 1 : (noise_scale != 0.f ? 2 : 0);
+  const int nmode = noise ? 1 : (noise_scale != 0.f ? 2 : (out_rowsum ? 3 : 0));
+  if (out_rowsum && nmode != 3) return DGGB_ERR_UNSUPPORTED;   // the normaliser is an evaluation (no-noise) feature
 #define DGGB_AP_LAUNCH1(KB_, SP_, NM_)                                                                            \
   do {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(allpairs_topk_kernel<KB_, SP_, NM_>,                                     \
@@ -612,7 +942,8 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   do {                                                                                                            \
     if (nmode == 0) DGGB_AP_LAUNCH1(KB_, SP_, 0);                                                                 \
     else if (nmode == 1) DGGB_AP_LAUNCH1(KB_, SP_, 1);                                                            \
-    else DGGB_AP_LAUNCH1(KB_, SP_, 2);                                                                            \
+    else if (nmode == 2) DGGB_AP_LAUNCH1(KB_, SP_, 2);                                                            \
+    else DGGB_AP_LAUNCH1(KB_, SP_, 3);                                                                            \
   } while (0)
 
   if (kb == 1 && precision == 3) DGGB_AP_LAUNCH(1, 3);

@@ -44,7 +44,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // for the single-thread producer / MMA-issuer roles: sleep between polls so the spinning warp does not
 // steal issue slots from the epilogue warp that shares its scheduler
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+#ifdef DGGB_NO_BACKOFF
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#else
   while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+#endif
 }
 
 // ---------------------------------------------------------------- TMA
