@@ -885,7 +885,10 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   // ---- v2 (two epilogue groups, A in TMEM) whenever the second list/queue set fits: kc <= 32 ----
   const int nmode2 = noise ? 1 : (noise_scale != 0.f ? 2 : (out_rowsum ? 3 : 0));
   if (out_rowsum && nmode2 != 3) return DGGB_ERR_UNSUPPORTED;
-  if (kc <= 32 && !(kb == 4 && precision == 3) && !getenv("DGGB_AP_V1")) {
+  // measured (scripts/ap_micro.py): v2 wins when the epilogue carries noise work (+12 % with Philox), v1 (two
+  // accumulators per group, MMA overlapped with its own epilogue) wins for the noise-free modes
+  const bool want_v2 = (nmode2 == 1 || nmode2 == 2) ? !getenv("DGGB_AP_V1") : (getenv("DGGB_AP_V2") != nullptr);
+  if (kc <= 32 && !(kb == 4 && precision == 3) && want_v2) {
     int st2 = 4;
     AP2Smem L2 = ap2_smem_layout(kb, precision, st2, kc);
     while (st2 > 2 && L2.total + 1024 > 227 * 1024) L2 = ap2_smem_layout(kb, precision, --st2, kc);
