@@ -499,9 +499,10 @@ __global__ void __launch_bounds__(kAPThreads, 1)
 // v2 of the kernel above (kc <= 32): the SIMT epilogue is the bound, so it gets TWO warps per scheduler.
 //   * the query tile (A operand, hi/lo) lives in TENSOR MEMORY ("TS" MMA): each epilogue thread copies its own
 //     row global -> registers -> tcgen05.st once; that frees 64 KB of shared memory ...
-//   * ... which pays for a second, independent epilogue group: group g (4 warps) owns TMEM accumulator g and
-//     scores tiles jt = g, g+2, ... into its own per-row list/queue; the two sorted lists of a row are merged
-//     once at the end.  10 warps: w0 TMA producer, w1 MMA issuer, w2-5 group 0, w6-9 group 1.
+//   * ... which pays for a second, independent epilogue group: group g (4 warps) owns TMEM accumulators g and
+//     g+2 (double-buffered, so its MMA overlaps its own epilogue) and scores tiles jt = g, g+2, ... into its own
+//     per-row list/queue; the two sorted lists of a row are merged once at the end.
+//     10 warps: w0 TMA producer, w1 MMA issuer, w2-5 group 0, w6-9 group 1.  TMEM: 4 x 64 + 128 columns.
 // ------------------------------------------------------------------------------------------------
 constexpr int kAP2Threads = 320;
 
@@ -522,7 +523,7 @@ __host__ __device__ inline AP2Smem ap2_smem_layout(int kb, int split, int stages
     L.qi[g] = off; off += kQCap * kBM * 4;
   }
   L.zpart = off; off += kBM * 4;
-  L.bars = off; off += 128;
+  L.bars = off; off += 192;
   L.total = off;
   return L;
 }
@@ -542,12 +543,12 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;            // [stages]  TMA -> MMA / epilogue
   uint64_t* empty = bars + 4;       // [stages]  MMA commit + the 4 warps of the group that scored the tile
-  uint64_t* tfull = bars + 8;       // [2]       MMA -> epilogue group
-  uint64_t* tempty = bars + 10;     // [2]       epilogue group -> MMA
-  uint64_t* aready = bars + 12;     // query tile written to TMEM (8 epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  constexpr uint32_t kTmemCols = (KB <= 2) ? 256 : 512;
-  constexpr uint32_t kAHi = 2 * kBN, kALo = 2 * kBN + KB * 32;
+  uint64_t* tfull = bars + 8;       // [4]       MMA -> epilogue group (accumulators g and g+2 belong to group g)
+  uint64_t* tempty = bars + 12;     // [4]       epilogue group -> MMA
+  uint64_t* aready = bars + 16;     // query tile written to TMEM (8 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  constexpr uint32_t kTmemCols = 512;   // 4 accumulators x 64 columns + the query tile (hi | lo)
+  constexpr uint32_t kAHi = 4 * kBN, kALo = 4 * kBN + KB * 32;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (n + kBN - 1) / kBN;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       tc::mbar_init(full + s, 1);
       tc::mbar_init(empty + s, 5);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       tc::mbar_init(tfull + b, 1);
       tc::mbar_init(tempty + b, 4);
     }
@@ -601,8 +602,8 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       int s = 0;
       uint32_t ph = 0;
       for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
-        const int buf = jt & 1;
-        const uint32_t bph = (jt >> 1) & 1;
+        const int buf = jt & 3;
+        const uint32_t bph = (jt >> 2) & 1;
         tc::mbar_wait_backoff(tempty + buf, bph ^ 1);
         tc::mbar_wait_backoff(full + s, ph);
         tc::fence_after_sync();
@@ -687,17 +688,19 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
     };
     int s = g % stages;
     uint32_t ph = (g / stages) & 1;
-    uint32_t bph = 0;
-    for (int jt = g; jt < num_tiles; jt += 2) {
+    int it = 0;
+    for (int jt = g; jt < num_tiles; jt += 2, ++it) {
+      const int buf = g + 2 * (it & 1);          // == jt & 3
+      const uint32_t bph = (it >> 1) & 1;        // == (jt >> 2) & 1
       tc::mbar_wait(full + s, ph);
-      tc::mbar_wait(tfull + g, bph);
+      tc::mbar_wait(tfull + buf, bph);
       tc::fence_after_sync();
       const float* nj = reinterpret_cast<const float*>(smem + L.nrm + s * kBN * 4);
       const bool diag_tile = (jt * kBN < row0 + kBM) && (jt * kBN + kBN > row0);
 #pragma unroll 1
       for (int c0 = 0; c0 < kBN; c0 += kChunk) {
         uint32_t r[kChunk];
-        tc::tmem_ld_32x16(tmem_base + lane_addr + g * kBN + c0, r);
+        tc::tmem_ld_32x16(tmem_base + lane_addr + buf * kBN + c0, r);
         tc::tmem_ld_wait();
         if (row_ok) {
           const int jbase = jt * kBN + c0;
@@ -747,12 +750,11 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        tc::mbar_arrive(tempty + g);
+        tc::mbar_arrive(tempty + buf);
         tc::mbar_arrive(empty + s);
       }
       s += 2;
       if (s >= stages) { s -= stages; ph ^= 1; }
-      bph ^= 1;
     }
     flush(__ballot_sync(0xffffffffu, qn > 0));
     // ---- merge the two groups' lists (named barrier over the 8 epilogue warps), group 0 writes out ----
@@ -885,9 +887,8 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   // ---- v2 (two epilogue groups, A in TMEM) whenever the second list/queue set fits: kc <= 32 ----
   const int nmode2 = noise ? 1 : (noise_scale != 0.f ? 2 : (out_rowsum ? 3 : 0));
   if (out_rowsum && nmode2 != 3) return DGGB_ERR_UNSUPPORTED;
-  // measured (scripts/ap_micro.py): v2 wins when the epilogue carries noise work (+12 % with Philox), v1 (two
-  // accumulators per group, MMA overlapped with its own epilogue) wins for the noise-free modes
-  const bool want_v2 = (nmode2 == 1 || nmode2 == 2) ? !getenv("DGGB_AP_V1") : (getenv("DGGB_AP_V2") != nullptr);
+  // measured (scripts/ap_micro.py, N = 37 888, Gpairs/s, v1 -> v2): no noise 352 -> 377, Philox 215 -> 284
+  const bool want_v2 = !getenv("DGGB_AP_V1");
   if (kc <= 32 && !(kb == 4 && precision == 3) && want_v2) {
     int st2 = 4;
     AP2Smem L2 = ap2_smem_layout(kb, precision, st2, kc);
