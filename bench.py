@@ -285,13 +285,32 @@ def run_ours(args, rank, local_rank, world):
     h2d = sum(t.numel() * t.element_size() for t in pinned[0].values())
     d2h = pinned[0]["idx"].shape[1] * 4 + 4
 
+    # Every step copies ITS inputs host -> device (pinned memory) and reads its result back; the copy of step
+    # i+1 is issued on a side stream while step i computes (what a prefetching training loop does), so the
+    # timed region still contains every H2D/D2H byte but PCIe and the SMs overlap.
+    copy_stream = torch.cuda.Stream()
+    staged = {}
+
+    def prefetch(i):
+        hs = pinned[i % N_SETS]
+        with torch.cuda.stream(copy_stream):
+            bufs = (hs["idx"].to(dev, non_blocking=True), hs["val"].to(dev, non_blocking=True),
+                    hs["x"].to(dev, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[i] = (bufs, ev)
+
     def step_e2e(i):
-        s, hs = dsets[i % N_SETS], pinned[i % N_SETS]
+        s = dsets[i % N_SETS]
+        if i not in staged:
+            prefetch(i)
+        (idx, val, x), ev = staged.pop(i)
+        prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ev)
+        for t_ in (idx, val, x):
+            t_.record_stream(torch.cuda.current_stream())
         for p in params:
             p.grad = None
-        idx = hs["idx"].to(dev, non_blocking=True)
-        val = hs["val"].to(dev, non_blocking=True)
-        x = hs["x"].to(dev, non_blocking=True)
         adj = torch.sparse_coo_tensor(idx, val, (shape["n"], shape["n"]), is_coalesced=True)
         out, x_enc = m(x, adj)
         torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"], s["g_xenc"]])
@@ -315,6 +334,8 @@ def run_ours(args, rank, local_rank, world):
         launches = sum(graphed[i % N_SETS].dggb_launches_per_replay for i in range(args.steps))
     for i in range(max(3, args.warmup)):
         step_e2e(i)
+    staged.clear()          # the timed region starts with nothing prefetched
+    torch.cuda.synchronize()
     ms_e2e = time_region(step_e2e, args.steps, world)
     clocks = sampler.stop() if rank == 0 else None
 

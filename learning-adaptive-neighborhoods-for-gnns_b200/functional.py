@@ -47,8 +47,10 @@ class _DGGEdge(torch.autograd.Function):
         y, be, deg_w, deg_b, noise, R, rank, s, k = ctx.saved_tensors
         g = ctx.graph
         n, h = y.shape
-        dy = torch.zeros_like(y)
-        small = torch.zeros(h + 4 + n, dtype=torch.float32, device=y.device)   # dbe | ddeg (+pad) | ds scratch
+        # one zero-filled buffer (one fill launch): dy | dbe | ddeg (+pad) | ds scratch
+        zbuf = torch.zeros(n * h + h + 4 + n, dtype=torch.float32, device=y.device)
+        dy = zbuf[:n * h].view(n, h)
+        small = zbuf[n * h:]
         dbe, ddeg, ds_ws = small[:h], small[h:h + 2], small[h + 4:]
         check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
                                       p(deg_w), p(deg_b), p(noise), i32(ctx.hard_k), p(R), p(rank), p(s), p(k),
@@ -289,8 +291,10 @@ class _EncodeProject(torch.autograd.Function):
         x, wn, we, x_enc = ctx.saved_tensors
         g_y = _f32c(g_y)
         dpre = _linear_act_tc(g_y, we, None, ctx.slope, w_transposed=True, addend=g_xenc, act_src=x_enc)
-        dwe, _ = gemm_tn(g_y, x_enc, False)
-        dwn, dbn = gemm_tn(dpre, x, True)
+        h, f_in = wn.shape
+        zbuf = torch.zeros(h * h + h * f_in + h, dtype=torch.float32, device=x.device)   # one fill for both GEMMs
+        dwe, _ = gemm_tn(g_y, x_enc, False, zeroed=zbuf[:h * h])
+        dwn, dbn = gemm_tn(dpre, x, True, zeroed=zbuf[h * h:])
         dx = dpre @ wn if ctx.needs_input_grad[0] else None
         return dx, dwn, dbn, dwe, None
 
@@ -306,12 +310,15 @@ def encode_project(x, wn, bn, we, slope):
     return x_enc, tall_linear(x_enc, we)
 
 
-def gemm_tn(a, b, want_colsum=False, use_tc=None):
-    """(a^T b [P,Q], column sums of a [P] or None) for tall a [N,P], b [N,Q] via dggb_gemm_tn_splitk."""
+def gemm_tn(a, b, want_colsum=False, use_tc=None, zeroed=None):
+    """(a^T b [P,Q], column sums of a [P] or None) for tall a [N,P], b [N,Q] via dggb_gemm_tn_splitk / _tc.
+    ``zeroed``: optional pre-zeroed flat fp32 buffer of pp*q (+pp) elements to accumulate into."""
     a, b = _f32c(a), _f32c(b)
     n, pp = a.shape
     q = b.shape[1]
-    buf = torch.zeros(pp * q + (pp if want_colsum else 0), dtype=torch.float32, device=a.device)
+    need = pp * q + (pp if want_colsum else 0)
+    buf = zeroed if zeroed is not None else torch.zeros(need, dtype=torch.float32, device=a.device)
+    assert buf.numel() == need
     out = buf[:pp * q].view(pp, q)
     cs = buf[pp * q:] if want_colsum else None
     if use_tc is None:
