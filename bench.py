@@ -447,7 +447,7 @@ def kernel_roofline(m, dsets, shape, iters=30):
     w_enc, b_enc = enc.weight.detach().contiguous(), enc.bias.detach().contiguous()
     xs = [s["x"] for s in dsets]
     x_out = torch.empty(n, h, device=dev)
-    ws_lin = torch.empty(2 * h * f_in, device=dev)
+    ws_lin = torch.empty(2 * h * f_in + 2 * h * h, device=dev)
     dpre = torch.randn(n, h, device=dev)
     dw_out = torch.zeros(h * f_in + h, device=dev)
     L = lib()

@@ -158,11 +158,14 @@ int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h);   /* hi/lo split 
  *   v = x W_eff^T + b + addend;   out = act_src ? v * LeakyReLU'_slope(act_src) : LeakyReLU_slope(v)
  * W_eff = w ([H,F]) or, with w_transposed, w^T (w given as [F,H]).  With x = dy, w = We (transposed),
  * addend = dL/dx_enc, act_src = x_enc this is d pre = LeakyReLU'(x_enc) * (dy We + dL/dx_enc) in one pass
- * (autograd of dgm.py:1778-1784).  b / addend / act_src may be NULL. */
+ * (autograd of dgm.py:1778-1784).  b / addend / act_src may be NULL.
+ * w2/out2 (H in {32, 64}): additionally out2 = out w2^T, chained inside the same kernel (the activated tile
+ * goes registers -> TMEM as the next A operand): x_enc and y = x_enc We^T of dgm.py:1778+1784 in one launch. */
 int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
                       const float* addend /* [N,H] */, const float* act_src /* [N,H] */, float slope,
-                      int32_t n, int32_t f, int32_t h, float* out, void* workspace,
-                      int64_t workspace_bytes, void* stream);
+                      int32_t n, int32_t f, int32_t h, float* out,
+                      const float* w2 /* [H,H] or NULL */, float* out2 /* [N,H] or NULL */,
+                      void* workspace, int64_t workspace_bytes, void* stream);
 int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
                         int32_t f, int32_t h, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);

@@ -38,12 +38,17 @@ using tc::tmem_st_wait;
 // three tensor-core reads): here the converters keep the split x operand in REGISTERS and hand it to the
 // tensor core through TMEM (tcgen05.st -> "TS" MMA, A from tensor memory); only W (pre-split) is read from
 // shared memory by the MMA.  Per k-block of 32 features: 16 KB x in, 16 KB LDS, 24 KB of W operand reads.
-template <int H, int STAGES>
+// FUSE2 (H <= 64): a second GEMM out2 = out W2^T (the edge-encoder projection y = x_enc We^T of dgm.py:1784) is
+// chained in the epilogue: the activated tile goes registers -> TMEM as the A operand, W2 hi/lo arrive by TMA
+// into a retired stage buffer, the accumulator columns are reused.
+template <int H, int STAGES, bool FUSE2>
 __global__ void __launch_bounds__(kLinThreads, 1)
     linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
-                         const __grid_constant__ CUtensorMap tm_wlo, const float* __restrict__ bias,
+                         const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_w2hi,
+                         const __grid_constant__ CUtensorMap tm_w2lo, const float* __restrict__ bias,
                          const float* __restrict__ addend, const float* __restrict__ act_src, float slope,
-                         int n, int f, float* __restrict__ out) {
+                         int n, int f, float* __restrict__ out, float* __restrict__ out2) {
+  static_assert(!FUSE2 || (H <= 64 && STAGES >= 3), "fused second GEMM needs H <= 64 and a third stage buffer");
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
   constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;
@@ -57,7 +62,10 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   uint64_t* a_full = bars + 2 * STAGES;       // [2] A (hi/lo) written to TMEM by the 4 converter warps
   uint64_t* a_empty = a_full + 2;             // [2] MMAs that read it retired
   uint64_t* acc_full = a_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* w2_full = acc_full + 1;           // W2 hi/lo landed (second GEMM)
+  uint64_t* a2_full = acc_full + 2;           // activated tile written to TMEM by the 4 epilogue warps
+  uint64_t* acc2_full = acc_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kLinBM;
@@ -76,6 +84,9 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       tc::mbar_init(a_empty + s, 1);
     }
     tc::mbar_init(acc_full, 1);
+    tc::mbar_init(w2_full, 1);
+    tc::mbar_init(a2_full, 4);
+    tc::mbar_init(acc2_full, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -99,6 +110,16 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         tc::tma_load_2d(st, &tm_x, full + s, kb * 32, row0);
         tc::tma_load_2d(st + kXBytes, &tm_whi, full + s, kb * 32, 0);
         tc::tma_load_2d(st + kXBytes + kWBytes, &tm_wlo, full + s, kb * 32, 0);
+      }
+      if (FUSE2) {
+        tc::mbar_wait(acc_full, 0);                    // GEMM 1 retired: every stage buffer is free again
+        uint8_t* w2 = smem + 2 * kStageBytes;          // [hi kb0 | hi kb1 | lo kb0 | lo kb1], H x 128 B each
+        tc::mbar_arrive_expect_tx(w2_full, 4 * kWBytes);
+#pragma unroll
+        for (int kb2 = 0; kb2 < 2; ++kb2) {
+          tc::tma_load_2d(w2 + kb2 * kWBytes, &tm_w2hi, w2_full, kb2 * 32, 0);
+          tc::tma_load_2d(w2 + (2 + kb2) * kWBytes, &tm_w2lo, w2_full, kb2 * 32, 0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -128,6 +149,27 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         tc::mma_commit(a_empty + ab);
       }
       tc::mma_commit(acc_full);
+      if (FUSE2) {
+        tc::mbar_wait(w2_full, 0);
+        tc::mbar_wait(a2_full, 0);
+        tc::fence_after_sync();
+        const uint32_t w2h = tc::smem_u32(smem + 2 * kStageBytes), w2l = w2h + 2 * kWBytes;
+        uint32_t acc2 = 0;
+#pragma unroll
+        for (int sp = 0; sp < 3; ++sp) {
+          const uint32_t a = tmem_a0 + ((sp == 2) ? 64 : 0);
+          const uint32_t b = (sp == 1) ? w2l : w2h;
+#pragma unroll
+          for (int kb2 = 0; kb2 < H / 32; ++kb2)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_tf32_ts(tmem_base, a + kb2 * 32 + ks * 8, tc::smem_desc_k128(b + kb2 * kWBytes + ks * 32), idesc,
+                          acc2);
+              acc2 = 1;
+            }
+        }
+        tc::mma_commit(acc2_full);
+      }
     }
   } else {
     // ---------------- converters: thread == row.  smem (swizzled) -> registers -> hi/lo -> TMEM ------------
@@ -207,7 +249,50 @@ __global__ void __launch_bounds__(kLinThreads, 1)
             if (act_src != nullptr) v *= ac[r8][j] > 0.f ? 1.f : slope;
             else v = v > 0.f ? v : slope * v;
             out[(size_t)row * H + c] = v;
+            if (FUSE2) stg[(rb + r8) * kPitch + c] = v;     // keep the activated tile for the chained GEMM
+          } else if (FUSE2 && c < H) {
+            stg[(rb + r8) * kPitch + c] = 0.f;
           }
+        }
+      }
+    }
+    if (FUSE2) {
+      // ---- chained GEMM: this thread's activated row -> TF32 hi/lo -> TMEM (A operand, K = H) ----
+      __syncwarp();
+#pragma unroll
+      for (int kb2 = 0; kb2 < H / 32; ++kb2) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float v = stg[lane * kPitch + kb2 * 32 + c];
+          const float hh = tf32_rna(v);
+          hi[c] = __float_as_uint(hh);
+          lo[c] = __float_as_uint(tf32_rna(v - hh));
+        }
+        tmem_st_32x32(tmem_a0 + lane_addr + kb2 * 32, hi);
+        tmem_st_32x32(tmem_a0 + lane_addr + 64 + kb2 * 32, lo);
+      }
+      tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(a2_full);
+      tc::mbar_wait(acc2_full, 0);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c0 = 0; c0 < H; c0 += 16) {
+        uint32_t r[16];
+        tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) stg[lane * kPitch + c0 + c] = __uint_as_float(r[c]);
+      }
+      __syncwarp();
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = row0 + q * 32 + rr;
+#pragma unroll
+        for (int j = 0; j < kCols; ++j) {
+          const int c = lane + 32 * j;
+          if (row < n && c < H) out2[(size_t)row * H + c] = stg[rr * kPitch + c];
         }
       }
     }
@@ -223,14 +308,15 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 
 template <int H>
 static int launch_linear(const float* x, const float* w, int w_transposed, const float* b, const float* addend,
-                         const float* act_src, float slope, int n, int f, float* out, float* ws, cudaStream_t st) {
-  constexpr int STAGES = (H <= 64) ? 3 : 4;   // H <= 64: 3 x 32 KB = 96 KB so that two CTAs share an SM (one wave for 2 x 148 tiles)
+                         const float* act_src, float slope, int n, int f, float* out, float* ws, const float* w2,
+                         float* out2, cudaStream_t st) {
+  constexpr int STAGES = (H <= 64) ? 3 : 4;   // H <= 64: 3 x 32 KB = 96 KB so that two CTAs share an SM
   float* w_hi = ws;
   float* w_lo = ws + (size_t)H * f;
   split_w_kernel<<<(H * f + 255) / 256, 256, 0, st>>>(w, H * f, H, f, w_transposed, w_hi, w_lo);
   int rc = launch_status();
   if (rc != DGGB_OK) return rc;
-  CUtensorMap tm_x, tm_whi, tm_wlo;
+  CUtensorMap tm_x, tm_whi, tm_wlo, tm_w2hi, tm_w2lo;
   rc = make_tmap_2d_f32(&tm_x, x, (uint64_t)n, (uint64_t)f, kLinBM, 32);
   if (rc != DGGB_OK) return rc;
   rc = make_tmap_2d_f32(&tm_whi, w_hi, (uint64_t)H, (uint64_t)f, H, 32);
@@ -238,11 +324,32 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   rc = make_tmap_2d_f32(&tm_wlo, w_lo, (uint64_t)H, (uint64_t)f, H, 32);
   if (rc != DGGB_OK) return rc;
   const size_t smem = STAGES * (kLinBM * 128 + 2 * H * 128) + 256 + 1024;
-  cudaError_t e =
-      cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = (n + kLinBM - 1) / kLinBM;
+  if constexpr (H <= 64) {
+    if (w2 != nullptr) {
+      float* w2_hi = ws + (size_t)2 * H * f;
+      float* w2_lo = w2_hi + (size_t)H * H;
+      split_w_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(w2, H * H, H, H, 0, w2_hi, w2_lo);
+      rc = launch_status();
+      if (rc != DGGB_OK) return rc;
+      rc = make_tmap_2d_f32(&tm_w2hi, w2_hi, (uint64_t)H, (uint64_t)H, H, 32);
+      if (rc != DGGB_OK) return rc;
+      rc = make_tmap_2d_f32(&tm_w2lo, w2_lo, (uint64_t)H, (uint64_t)H, H, 32);
+      if (rc != DGGB_OK) return rc;
+      cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_status(e);
+      linear_tf32x3_kernel<H, STAGES, true><<<grid, kLinThreads, smem, st>>>(
+          tm_x, tm_whi, tm_wlo, tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2);
+      return launch_status();
+    }
+  }
+  if (w2 != nullptr) return DGGB_ERR_BAD_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
-  linear_tf32x3_kernel<H, STAGES><<<(n + kLinBM - 1) / kLinBM, kLinThreads, smem, st>>>(
-      tm_x, tm_whi, tm_wlo, b, addend, act_src, slope, n, f, out);
+  linear_tf32x3_kernel<H, STAGES, false><<<grid, kLinThreads, smem, st>>>(
+      tm_x, tm_whi, tm_wlo, tm_whi, tm_wlo, b, addend, act_src, slope, n, f, out, nullptr);
   return launch_status();
 }
 
@@ -251,32 +358,35 @@ using namespace dggb;
 
 extern "C" int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h) {
   if (f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
-  return (int64_t)2 * h * f * 4;
+  return ((int64_t)2 * h * f + (int64_t)2 * h * h) * 4;   // W hi/lo (+ W2 hi/lo of the chained GEMM)
 }
 
 extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
                                  const float* addend, const float* act_src, float slope, int32_t n, int32_t f,
-                                 int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
-  if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
+                                 int32_t h, float* out, const float* w2, float* out2, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0 || ((w2 == nullptr) != (out2 == nullptr)))
+    return DGGB_ERR_BAD_ARG;
   if (workspace_bytes < dggb_linear_act_workspace_bytes(f, h)) return DGGB_ERR_WORKSPACE;
   if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
   float* ws = reinterpret_cast<float*>(workspace);
   // TMA needs 16-byte row pitches and base addresses; the supported widths are the hidden sizes of the path
-  if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16) ||
+  if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16) || (w2 && (h > 64 || h % 32)) ||
       (addend && ((uintptr_t)addend % 16)) || (act_src && ((uintptr_t)act_src % 16)))
     return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
   cudaStream_t st = as_stream(stream);
   switch (h) {
-    case 16: return launch_linear<16>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
-    case 32: return launch_linear<32>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
-    case 64: return launch_linear<64>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
-    case 128: return launch_linear<128>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, st);
+    case 16: return launch_linear<16>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
+    case 32: return launch_linear<32>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
+    case 64: return launch_linear<64>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
+    case 128: return launch_linear<128>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
     default: return DGGB_ERR_BAD_SHAPE;
   }
 }
 
 extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
                                    int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
-  return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, workspace, workspace_bytes, stream);
+  return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, nullptr, nullptr, workspace,
+                           workspace_bytes, stream);
 }

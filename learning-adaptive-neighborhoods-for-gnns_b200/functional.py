@@ -245,7 +245,7 @@ class _TallLinear(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None):
+def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None, w2=None):
     """out = epi(x W_eff^T + b + addend) through dggb_linear_fused (tcgen05, 3xTF32); None if the shape is
     not supported.  epi = LeakyReLU(slope), or * LeakyReLU'(act_src) when act_src is given (backward form)."""
     import ctypes
@@ -260,14 +260,16 @@ def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None
     bb = None if b is None else b.contiguous()
     ad = None if addend is None else _f32c(addend)
     ac = None if act_src is None else _f32c(act_src)
-    ws = torch.empty(2 * h * f_in, dtype=torch.float32, device=x.device)
+    ws = torch.empty(2 * h * f_in + 2 * h * h, dtype=torch.float32, device=x.device)
+    out2 = torch.empty(n, h, dtype=torch.float32, device=x.device) if w2 is not None else None
+    w2c = None if w2 is None else w2.contiguous()
     rc = lib().dggb_linear_fused(p(x), p(w), i32(1 if w_transposed else 0), p(bb), p(ad), p(ac),
-                                 ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out), p(ws),
+                                 ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out), p(w2c), p(out2), p(ws),
                                  ctypes.c_int64(ws.numel() * 4), stream())
     if rc == -2:
         return None
     check(rc, "linear_fused")
-    return out
+    return out if w2 is None else (out, out2)
 
 
 class _EncodeProject(torch.autograd.Function):
@@ -278,8 +280,12 @@ class _EncodeProject(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, wn, bn, we, slope: float):
-        x_enc = _linear_act_tc(x, wn, bn, slope)
-        y = _linear_act_tc(x_enc, we, None, 1.0) if x_enc is not None else None
+        if wn.shape[0] in (32, 64):     # one launch: y chained in the encoder kernel's epilogue
+            res = _linear_act_tc(x, wn, bn, slope, w2=we)
+            x_enc, y = res if res is not None else (None, None)
+        else:
+            x_enc = _linear_act_tc(x, wn, bn, slope)
+            y = _linear_act_tc(x_enc, we, None, 1.0) if x_enc is not None else None
         if y is None:
             raise RuntimeError("encode_project: shape not supported by the tensor-core kernels")
         ctx.slope = slope

@@ -302,3 +302,20 @@ def test_bad_shapes_raise():
         K.dgg_edge(y, torch.zeros(6, device="cuda"), torch.ones(1, 1, device="cuda"), torch.zeros(1, device="cuda"), g)
     with pytest.raises(RuntimeError):
         K.spmm(torch.ones(g.nnz), torch.ones(50, 4), g)                 # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("n,f,h", [(19717, 500, 64), (3000, 128, 32)])
+def test_encode_project_chained_gemm(n, f, h):
+    """x_enc = LeakyReLU(x Wn^T + bn) and y = x_enc We^T from ONE kernel launch vs fp64."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(n, f, generator=gen).cuda()
+    wn = (torch.randn(h, f, generator=gen) / f ** 0.5).cuda()
+    bn = torch.randn(h, generator=gen).cuda()
+    we = (torch.randn(h, h, generator=gen) / h ** 0.5).cuda()
+    x_enc, y = K._linear_act_tc(x, wn, bn, 0.01, w2=we)
+    pre = x.double() @ wn.double().t() + bn.double()
+    xe = torch.where(pre > 0, pre, pre * 0.01)
+    torch.testing.assert_close(x_enc, xe.float(), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(y, (xe @ we.double().t()).float(), rtol=2e-5, atol=3e-5)
