@@ -349,6 +349,7 @@ def run_ours(args, rank, local_rank, world):
         return
 
     roofline = kernel_roofline(m, dsets, shape)
+    epoch = full_model_epoch(dsets, shape, dev) if world == 1 else None
     cpu = None
     if world == 1:
         torch.set_num_threads(os.cpu_count())
@@ -369,10 +370,89 @@ def run_ours(args, rank, local_rank, world):
                                          if world > 1 else "single GPU")),
                 e2e=dict(value=e2e_value, unit="nodes/s", ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks, epoch=epoch)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def full_model_epoch(dsets, shape, dev, iters=20):
+    """BASELINE.json's second number, "epoch ms": one GCN_DGG_00 training step (forward, nll loss, backward,
+    Adam with the script's two parameter groups) at Pubmed shape, and the script epoch = 1 train step + 2
+    evaluation forwards (train_small_graphs.py:429-440).  Eager launches, device-resident inputs."""
+    import torch.nn.functional as F
+
+    import model as models
+
+    args = argparse.Namespace(extra_edge_dim=0, dgg_adj_input="input_adj")
+    torch.manual_seed(0)
+    net = models.GCN_DGG_00(nfeat=shape["f"], nlayers=2, nhidden=shape["h"], nclass=3, dropout=0.5, lamda=0.5,
+                            alpha=0.1, variant=False, args=args).to(dev)
+    with torch.no_grad():
+        net.conv1.W.mul_(0.1)
+        net.conv2.W.mul_(0.1)
+    opt = torch.optim.Adam([dict(params=net.params1, weight_decay=5e-4), dict(params=net.params2, weight_decay=0.0)],
+                           lr=0.01)
+    n = shape["n"]
+    labels = torch.randint(0, 3, (n,), device=dev)
+    mask = torch.zeros(n, dtype=torch.bool, device=dev)
+    mask[:60] = True
+
+    def train_step(i):
+        s = dsets[i % N_SETS]
+        net.train()
+        opt.zero_grad()
+        out, _, _ = net(s["x"], s["adj"])
+        F.nll_loss(out[mask], labels[mask]).backward()
+        opt.step()
+
+    def script_epoch(i):
+        train_step(i)
+        net.eval()
+        with torch.no_grad():
+            for _ in range(2):
+                net(dsets[i % N_SETS]["x"], dsets[i % N_SETS]["adj"])
+
+    def timed(fn):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    t_step, t_epoch = timed(train_step), timed(script_epoch)
+    res = dict(model="GCN_DGG_00", shape="pubmed", train_step_ms=t_step, script_epoch_ms=t_epoch,
+               nodes_per_s_train_step=n / (t_step * 1e-3),
+               reference_cpu="BASELINE.md: 125 s per train step on 8 CPU cores (dense D A D normalisation, N^3)")
+    # the same train step replayed as a CUDA graph (capturable Adam, one graph per resident batch)
+    try:
+        import dgg_b200
+
+        opt_g = torch.optim.Adam([dict(params=net.params1, weight_decay=5e-4),
+                                  dict(params=net.params2, weight_decay=0.0)], lr=0.01, capturable=True)
+        idx_train = mask.nonzero().flatten()
+        y_train = labels[idx_train]
+
+        def graph_body(s):
+            net.train()
+            opt_g.zero_grad(set_to_none=True)
+            out, _, _ = net(s["x"], s["adj"])
+            loss = F.nll_loss(out[idx_train], y_train)
+            loss.backward()
+            opt_g.step()
+            return loss
+
+        graphs = [dgg_b200.GraphedStep(lambda s=s: graph_body(s)) for s in dsets]
+        res["train_step_graph_ms"] = timed(lambda i: graphs[i % N_SETS]())
+    except Exception as e:   # capture is an optimisation, never a reason to lose the bench line
+        res["train_step_graph_ms"] = None
+        res["train_step_graph_error"] = repr(e)[:200]
+    return res
 
 
 def kernel_roofline(m, dsets, shape, iters=30):
