@@ -391,8 +391,9 @@ def full_model_epoch(dsets, shape, dev, iters=20):
     with torch.no_grad():
         net.conv1.W.mul_(0.1)
         net.conv2.W.mul_(0.1)
+    # the script's two parameter groups (train_small_graphs.py:407-414); fused=True: one Adam kernel per group
     opt = torch.optim.Adam([dict(params=net.params1, weight_decay=5e-4), dict(params=net.params2, weight_decay=0.0)],
-                           lr=0.01)
+                           lr=0.01, fused=True)
     n = shape["n"]
     labels = torch.randint(0, 3, (n,), device=dev)
     mask = torch.zeros(n, dtype=torch.bool, device=dev)
@@ -434,7 +435,8 @@ def full_model_epoch(dsets, shape, dev, iters=20):
         import dgg_b200
 
         opt_g = torch.optim.Adam([dict(params=net.params1, weight_decay=5e-4),
-                                  dict(params=net.params2, weight_decay=0.0)], lr=0.01, capturable=True)
+                                  dict(params=net.params2, weight_decay=0.0)], lr=0.01, capturable=True,
+                                 fused=True)
         idx_train = mask.nonzero().flatten()
         y_train = labels[idx_train]
 

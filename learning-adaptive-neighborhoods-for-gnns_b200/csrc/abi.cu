@@ -1,9 +1,14 @@
 // ABI bookkeeping: version, error strings, last CUDA error.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace dggb {
 int g_last_cuda_error = 0;
 long long g_kernel_launches = 0;
+bool pdl_enabled() {
+  static const bool on = std::getenv("DGGB_NO_PDL") == nullptr;
+  return on;
+}
 }
 
 extern "C" int dggb_version(void) { return 1; }

@@ -28,6 +28,30 @@ inline int launch_status(int kernels = 1) {
 }
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: every kernel of the path opens with pdl_trigger(); pdl_wait(); and is launched
+// with programmatic stream serialisation, so that its CTAs are scheduled (and run their prologue: barrier init,
+// TMEM allocation, descriptor prefetch) while the preceding kernel drains.  pdl_wait() returns once the preceding
+// grid has completed and its writes are visible, so nothing before it may touch global memory.  The step of this
+// path is a chain of ~10-30 us kernels: without this ~2 us of launch latency is exposed at every boundary.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();   // false when DGGB_NO_PDL is set in the environment (A/B measurements)
+
+template <typename... Params, typename... Args>
+inline void launch_pdl(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at = {};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);   // errors surface through cudaGetLastError()
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

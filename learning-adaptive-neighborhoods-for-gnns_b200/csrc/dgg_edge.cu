@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     dgg_edge_score_kernel(const int32_t* __restrict__ erow, const int32_t* __restrict__ col, int nnz, int h, int L,
                           const float* __restrict__ y, const float* __restrict__ be,
                           const float* __restrict__ abl_noise, float* __restrict__ R) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int G = kWarp / L, PER = kWarp / G;  // PER == L
   const int lg = lane % L, grp = lane / L;
@@ -138,6 +140,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
                         const float* __restrict__ deg_w, const float* __restrict__ deg_b, int hard_k,
                         int32_t* __restrict__ rank, float* __restrict__ s_out, float* __restrict__ k_out,
                         float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float srow_all[kEdgeWarps * kRankCap];
   float* srow = srow_all + (threadIdx.x >> 5) * kRankCap;
   const int lane = threadIdx.x & 31;
@@ -175,6 +179,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
                       const float* __restrict__ k_in, const float* __restrict__ g_out,
                       const float* __restrict__ deg_w, const float* __restrict__ deg_b, float* __restrict__ ds,
                       float* __restrict__ ddeg) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const float w = __ldg(deg_w), b = __ldg(deg_b);
   float dw_acc = 0.f, db_acc = 0.f;
@@ -220,6 +226,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
                          const int32_t* __restrict__ rank, const float* __restrict__ k_in,
                          const float* __restrict__ ds, const float* __restrict__ g_out, float* __restrict__ dy,
                          float* __restrict__ dbe) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int G = kWarp / L, PER = kWarp / G;
   const int lg = lane % L, grp = lane / L;
@@ -332,6 +340,8 @@ __device__ __forceinline__ float first_k_tanh(float r, float k) { return 1.f - 0
 __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     row_firstk_fwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
                           const float* __restrict__ k_in, int32_t* __restrict__ rank, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float srow_all[kEdgeWarps * kRankCap];
   float* srow = srow_all + (threadIdx.x >> 5) * kRankCap;
   const int lane = threadIdx.x & 31;
@@ -354,6 +364,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     row_firstk_bwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
                           const float* __restrict__ k_in, const int32_t* __restrict__ rank,
                           const float* __restrict__ g_out, float* __restrict__ dscore, float* __restrict__ dk) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kEdgeWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
@@ -404,13 +416,13 @@ extern "C" int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow, con
   if (nnz > 0) {
     st = dispatch_T(h, L, [&](auto tc) {
       constexpr int T = decltype(tc)::value;
-      dgg_edge_score_kernel<T><<<edges_grid(nnz), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(
+      launch_pdl(dgg_edge_score_kernel<T>, dim3(edges_grid(nnz)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
           erow, col, nnz, h, L, y, be, ablation_noise, R);
       return launch_status();
     });
     if (st != DGGB_OK) return st;
   }
-  dgg_row_rank_kernel<<<rows_grid(n, kEdgeWarps, 8), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(
+  launch_pdl(dgg_row_rank_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
       rowptr, n, R, deg_w, deg_b, hard_k, rank, s, k, out);
   return launch_status();
 }
@@ -427,14 +439,14 @@ extern "C" int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, con
   if (n == 0 || nnz == 0) return DGGB_OK;
   const int L = pow2_floor32(h / 4);
   if (hard_k < 0) {
-    dgg_row_dk_kernel<<<rows_grid(n, kEdgeWarps, 8), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(
+    launch_pdl(dgg_row_dk_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
         rowptr, n, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, ddeg);
     const int st = launch_status();
     if (st != DGGB_OK) return st;
   }
   return dispatch_T(h, L, [&](auto tc) {
     constexpr int T = decltype(tc)::value;
-    dgg_edge_grad_kernel<T><<<edges_grid(nnz), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(
+    launch_pdl(dgg_edge_grad_kernel<T>, dim3(edges_grid(nnz)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
         erow, col, nnz, h, L, y, be, ablation_noise, hard_k, R, rank, k, ds_ws, g_out, dy, dbe);
     return launch_status();
   });
@@ -444,7 +456,7 @@ extern "C" int dggb_row_firstk_fwd(const int32_t* rowptr, int32_t n, const float
                                    int32_t* rank, float* out, void* stream) {
   if (!rowptr || !score || !k || !rank || !out || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
-  row_firstk_fwd_kernel<<<rows_grid(n, kEdgeWarps, 8), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(rowptr, n, score,
+  launch_pdl(row_firstk_fwd_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), rowptr, n, score,
                                                                                                  k, rank, out);
   return launch_status();
 }
@@ -454,7 +466,7 @@ extern "C" int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float
                                    void* stream) {
   if (!rowptr || !score || !k || !rank || !g_out || !dscore || !dk || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
-  row_firstk_bwd_kernel<<<rows_grid(n, kEdgeWarps, 8), kEdgeWarps * kWarp, 0, as_stream(stream)>>>(
+  launch_pdl(row_firstk_bwd_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
       rowptr, n, score, k, rank, g_out, dscore, dk);
   return launch_status();
 }

@@ -28,6 +28,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(kTnThreads)
     gemm_tn_splitk_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int p, int q,
                           int rows_per_split, float* __restrict__ out, float* __restrict__ colsum) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float as[2][kTnNodes][kTnP];
   __shared__ __align__(16) float bs[2][kTnNodes][kTnQ];
   const int tid = threadIdx.x;
@@ -147,10 +149,10 @@ extern "C" int dggb_gemm_tn_splitk(const float* a, const float* b, int32_t n, in
   const bool vec4 = (p % 4 == 0) && (q % 4 == 0) && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) &&
                     ((uintptr_t)out % 16 == 0);
   if (vec4)
-    gemm_tn_splitk_kernel<true><<<grid, kTnThreads, 0, as_stream(stream)>>>(a, b, n, p, q, rows_per_split, out,
+    launch_pdl(gemm_tn_splitk_kernel<true>, dim3(grid), dim3(kTnThreads), 0, as_stream(stream), a, b, n, p, q, rows_per_split, out,
                                                                            colsum_a);
   else
-    gemm_tn_splitk_kernel<false><<<grid, kTnThreads, 0, as_stream(stream)>>>(a, b, n, p, q, rows_per_split, out,
+    launch_pdl(gemm_tn_splitk_kernel<false>, dim3(grid), dim3(kTnThreads), 0, as_stream(stream), a, b, n, p, q, rows_per_split, out,
                                                                             colsum_a);
   return launch_status();
 }

@@ -26,6 +26,8 @@ constexpr int kTcThreads = 192;
 __global__ void __launch_bounds__(256)
     transpose_split_kernel(const float* __restrict__ a, int n, int npad, int p, float* __restrict__ hi,
                            float* __restrict__ lo, float* __restrict__ colsum) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   constexpr uint32_t kAccCols = P <= 64 ? 64 : 128;
   constexpr uint32_t kTmemCols = 256;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kStageBytes);
   uint64_t* full = bars;
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      pdl_wait();   // a^T hi/lo come from transpose_split_kernel, b possibly from the kernel before it
       for (int i = 0; i < num_kb; ++i, (++s == kTcStages) ? (s = 0, ph ^= 1) : 0) {
         const int node0 = (kb_begin + i) * 32;
         tc::mbar_wait(empty + s, ph ^ 1);
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     if (num_kb > 0) {
       tc::mbar_wait(acc_full, 0);
       tc::fence_after_sync();
+      pdl_wait();   // `out` was zeroed by an earlier kernel; returns immediately here
       const int feat = m0 + m;
 #pragma unroll
       for (int c0 = 0; c0 < P; c0 += 16) {
@@ -217,7 +222,7 @@ static int launch_tn(const float* a, const float* b, int n, int q, float* out, f
   const int npad = (n + 31) / 32 * 32;
   float* a_hi = ws;
   float* a_lo = ws + (size_t)P * npad;
-  transpose_split_kernel<<<dim3(npad / 32, (P + 31) / 32), 256, 0, st>>>(a, n, npad, P, a_hi, a_lo, colsum);
+  launch_pdl(transpose_split_kernel, dim3(dim3(npad / 32, (P + 31) / 32)), dim3(256), 0, st, a, n, npad, P, a_hi, a_lo, colsum);
   int rc = launch_status();
   if (rc != DGGB_OK) return rc;
   CUtensorMap tm_b, tm_ahi, tm_alo;
@@ -236,8 +241,8 @@ static int launch_tn(const float* a, const float* b, int n, int q, float* out, f
   const size_t smem = kTcStages * (4 * 4096 + 2 * P * 128) + 256 + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
-  gemm_tn_tf32x3_kernel<P><<<dim3(m_tiles, splits), kTcThreads, smem, st>>>(tm_b, tm_ahi, tm_alo, n, q, kb_per_split,
-                                                                            out);
+  launch_pdl(gemm_tn_tf32x3_kernel<P>, dim3(m_tiles, splits), dim3(kTcThreads), smem, st, tm_b, tm_ahi, tm_alo, n, q,
+             kb_per_split, out);
   return launch_status();
 }
 

@@ -22,6 +22,8 @@ __global__ void cast_i64_i32(const int64_t* __restrict__ src, int32_t* __restric
 
 // erow[e] = i for every e in [rowptr[i], rowptr[i+1])
 __global__ void csr_expand_rows(const int32_t* __restrict__ rowptr, int n, int32_t* __restrict__ erow) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
@@ -51,6 +53,8 @@ __global__ void self_loop_count(const int32_t* __restrict__ rowptr, const int32_
 __global__ void self_loop_fill(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                const float* __restrict__ val, int n, const int32_t* __restrict__ out_rowptr,
                                int32_t* __restrict__ out_col, float* __restrict__ out_val) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
@@ -133,7 +137,7 @@ extern "C" int dggb_cast_i64_i32(const int64_t* src, int32_t* dst, int64_t n, vo
 extern "C" int dggb_csr_expand_rows(const int32_t* rowptr, int32_t n, int32_t* erow, void* stream) {
   if (!rowptr || !erow || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
-  csr_expand_rows<<<rows_grid(n, 8, 8), 256, 0, as_stream(stream)>>>(rowptr, n, erow);
+  launch_pdl(csr_expand_rows, dim3(rows_grid(n, 8, 8)), dim3(256), 0, as_stream(stream), rowptr, n, erow);
   return launch_status();
 }
 
@@ -151,6 +155,6 @@ extern "C" int dggb_add_self_loops_fill(const int32_t* rowptr, const int32_t* co
   if (!rowptr || !out_rowptr || !out_col || !out_val || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
   const int grid = rows_grid(n, 8, 8);
-  self_loop_fill<<<grid, 256, 0, as_stream(stream)>>>(rowptr, col, val, n, out_rowptr, out_col, out_val);
+  launch_pdl(self_loop_fill, dim3(grid), dim3(256), 0, as_stream(stream), rowptr, col, val, n, out_rowptr, out_col, out_val);
   return launch_status();
 }

@@ -6,7 +6,7 @@
 // hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (3xTF32) by "TS" MMAs (A from TMEM, B = pre-split W from
 // shared memory).  x is read from HBM exactly once (no pre-split copy): N*F*4 + N*H*4 bytes.
 //
-// CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32 + W hi/lo boxes Hx32 per k-block, 6-deep ring),
+// CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32 ring + [W_hi ; W_lo] box 2Hx32 ring per k-block),
 // warps 2-5: converters, then epilogue (tcgen05.ld -> bias -> LeakyReLU -> global), warp 1: MMA issuer + TMEM.
 #include "common.cuh"
 #include "tc05.cuh"
@@ -22,6 +22,8 @@ using tc::tf32_rna;
 // (transposed: w is given as [F, H] and the kernel needs W_eff[h][f] = w[f][h])
 __global__ void split_w_kernel(const float* __restrict__ w, int count, int h, int f, int transposed,
                                float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_trigger();
+  pdl_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     const float v = transposed ? __ldg(w + (size_t)(i % f) * h + (i / f)) : __ldg(w + i);
     const float h = tf32_rna(v);
@@ -37,29 +39,53 @@ using tc::tmem_st_wait;
 // Shared-memory traffic is what bounded the first version of this kernel (raw tile in, hi + lo tiles out,
 // three tensor-core reads): here the converters keep the split x operand in REGISTERS and hand it to the
 // tensor core through TMEM (tcgen05.st -> "TS" MMA, A from tensor memory); only W (pre-split) is read from
-// shared memory by the MMA.  Per k-block of 32 features: 16 KB x in, 16 KB LDS, 24 KB of W operand reads.
+// shared memory by the MMA.
+//
+// Pipeline (clock64 trace of the previous single-ring version: the k-loop ran at ~1200 cycles per k-block because
+// a stage was only recycled after TMA latency + conversion + MMA, 3 stages deep):
+//   * x ring (XS x 16 KB, HBM stream) is released by the converters as soon as the tile is in registers;
+//   * W ring (WS x [W_hi ; W_lo] stacked along N, L2-resident) is released by the MMA commit;
+//   * one producer thread polls both rings; the first XS + WS loads are issued before the TMEM allocation.
+//   * 3xTF32 as TWO MMAs per k-step instead of three: A_hi x [W_hi ; W_lo]^T (N = 2H: hi*hi | hi*lo side by side
+//     in the accumulator) and A_lo x W_hi^T (N = H, accumulated onto the hi*hi columns); the epilogue adds the two
+//     column halves.  Measured tcgen05.mma kind::tf32 M=128 K=8 cost: N=64 47 cycles, N=128 64, N=256 127
+//     (scripts/micro/mma_rate.cu), so 111 instead of 141 cycles per k-step at H = 64.
 // FUSE2 (H <= 64): a second GEMM out2 = out W2^T (the edge-encoder projection y = x_enc We^T of dgm.py:1784) is
 // chained in the epilogue: the activated tile goes registers -> TMEM as the A operand, W2 hi/lo arrive by TMA
-// into a retired stage buffer, the accumulator columns are reused.
-template <int H, int STAGES, bool FUSE2>
+// into the retired rings, the accumulator columns are reused.
+#ifdef DGGB_LIN_TRACE
+__device__ long long g_lin_trace[2][160];
+__device__ int g_lin_smid[1024];
+#define LTRACE(slot) do { if (blockIdx.x == 0 || blockIdx.x == 77) g_lin_trace[blockIdx.x ? 1 : 0][slot] = clock64(); } while (0)
+#else
+#define LTRACE(slot) do {} while (0)
+#endif
+template <int H, int XS, int WS, bool FUSE2>
 __global__ void __launch_bounds__(kLinThreads, 1)
-    linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_whi,
-                         const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_w2hi,
-                         const __grid_constant__ CUtensorMap tm_w2lo, const float* __restrict__ bias,
-                         const float* __restrict__ addend, const float* __restrict__ act_src, float slope,
-                         int n, int f, float* __restrict__ out, float* __restrict__ out2) {
-  static_assert(!FUSE2 || (H <= 64 && STAGES >= 3), "fused second GEMM needs H <= 64 and a third stage buffer");
+    linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                         const __grid_constant__ CUtensorMap tm_w2hi, const __grid_constant__ CUtensorMap tm_w2lo,
+                         const float* __restrict__ bias, const float* __restrict__ addend,
+                         const float* __restrict__ act_src, float slope, int n, int f, float* __restrict__ out,
+                         float* __restrict__ out2) {
+  static_assert(!FUSE2 || H == 32 || H == 64, "fused second GEMM: K = H must be one or two 32-float k-blocks");
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
-  constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;
-  constexpr uint32_t kAccCols = H <= 64 ? 64 : 128;
-  constexpr uint32_t kTmemCols = 256;              // accumulator + 2 x (A hi 32 cols | A lo 32 cols)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
-  uint64_t* full = bars;                      // [STAGES] TMA landed (1 + tx)
-  uint64_t* empty = bars + STAGES;            // [STAGES] 4 converter warps read x + MMAs read W (commit) = 5
-  uint64_t* a_full = bars + 2 * STAGES;       // [2] A (hi/lo) written to TMEM by the 4 converter warps
+  constexpr uint32_t kWStage = 2 * kWBytes;        // [W_hi ; W_lo]: 2H rows
+  constexpr uint32_t kRing = XS * kXBytes + WS * kWStage;
+  constexpr uint32_t kAccCols = 2 * H;             // hi*hi (+ lo*hi) | hi*lo
+  constexpr uint32_t kTmemCols = (kAccCols + 128 <= 256) ? 256 : 512;   // + 2 x (A hi 32 cols | A lo 32 cols)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing);
+  pdl_trigger();
+  if (threadIdx.x == 0) LTRACE(0);
+#ifdef DGGB_LIN_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 1024) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_lin_smid[blockIdx.x] = (int)sm; }
+#endif
+  uint64_t* x_full = bars;                    // [XS] TMA landed
+  uint64_t* x_empty = x_full + XS;            // [XS] 4 converter warps have the tile in registers
+  uint64_t* w_full = x_empty + XS;            // [WS]
+  uint64_t* w_empty = w_full + WS;            // [WS] MMAs that read it retired (commit)
+  uint64_t* a_full = w_empty + WS;            // [2] A (hi/lo) written to TMEM by the 4 converter warps
   uint64_t* a_empty = a_full + 2;             // [2] MMAs that read it retired
   uint64_t* acc_full = a_empty + 2;
   uint64_t* w2_full = acc_full + 1;           // W2 hi/lo landed (second GEMM)
@@ -71,13 +97,28 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   const int row0 = blockIdx.x * kLinBM;
   const int num_kb = (f + 31) / 32;
 
+  auto load_x = [&](int kb) {
+    const int s = kb % XS;
+    tc::mbar_arrive_expect_tx(x_full + s, kXBytes);
+    tc::tma_load_2d(smem + s * kXBytes, &tm_x, x_full + s, kb * 32, row0);
+  };
+  auto load_w = [&](int kb) {
+    const int s = kb % WS;
+    tc::mbar_arrive_expect_tx(w_full + s, kWStage);
+    tc::tma_load_2d(smem + XS * kXBytes + s * kWStage, &tm_w, w_full + s, kb * 32, 0);
+  };
+
   if (warp == 0 && lane == 0) {
+    if (tc::smem_u32(smem) & 1023u) __trap();      // 128-B swizzle atoms need a 1024-B aligned window
     tc::tma_prefetch_desc(&tm_x);
-    tc::tma_prefetch_desc(&tm_whi);
-    tc::tma_prefetch_desc(&tm_wlo);
-    for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(full + s, 1);
-      tc::mbar_init(empty + s, 5);
+    tc::tma_prefetch_desc(&tm_w);
+    for (int s = 0; s < XS; ++s) {
+      tc::mbar_init(x_full + s, 1);
+      tc::mbar_init(x_empty + s, 4);
+    }
+    for (int s = 0; s < WS; ++s) {
+      tc::mbar_init(w_full + s, 1);
+      tc::mbar_init(w_empty + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(a_full + s, 4);
@@ -88,6 +129,10 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tc::mbar_init(a2_full, 4);
     tc::mbar_init(acc2_full, 1);
     tc::fence_barrier_init();
+    pdl_wait();   // x / W may come from the preceding kernel; everything above overlapped its tail
+    // the first round of both rings needs no "empty" wait: put it in flight before the TMEM allocation / CTA sync
+    for (int kb = 0; kb < XS && kb < num_kb; ++kb) load_x(kb);
+    for (int kb = 0; kb < WS && kb < num_kb; ++kb) load_w(kb);
   }
   if (warp == 1) {
     tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -98,76 +143,76 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_a0 = tmem_base + kAccCols;   // A buffers start after the accumulator columns
+  if (threadIdx.x == 0) LTRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb, (++s == STAGES) ? (s = 0, ph ^= 1) : 0) {
-        tc::mbar_wait(empty + s, ph ^ 1);
-        uint8_t* st = smem + s * kStageBytes;
-        tc::mbar_arrive_expect_tx(full + s, kStageBytes);
-        tc::tma_load_2d(st, &tm_x, full + s, kb * 32, row0);
-        tc::tma_load_2d(st + kXBytes, &tm_whi, full + s, kb * 32, 0);
-        tc::tma_load_2d(st + kXBytes + kWBytes, &tm_wlo, full + s, kb * 32, 0);
+      int xk = num_kb < XS ? num_kb : XS, wk = num_kb < WS ? num_kb : WS;   // next k-block of each ring
+      while (xk < num_kb || wk < num_kb) {
+        bool moved = false;
+        if (xk < num_kb && tc::mbar_try_wait(x_empty + xk % XS, ((xk / XS) - 1) & 1)) {
+          LTRACE(8 + xk);
+          load_x(xk++);
+          moved = true;
+        }
+        if (wk < num_kb && tc::mbar_try_wait(w_empty + wk % WS, ((wk / WS) - 1) & 1)) {
+          load_w(wk++);
+          moved = true;
+        }
+        if (!moved) __nanosleep(32);
       }
       if (FUSE2) {
-        tc::mbar_wait(acc_full, 0);                    // GEMM 1 retired: every stage buffer is free again
-        uint8_t* w2 = smem + 2 * kStageBytes;          // [hi kb0 | hi kb1 | lo kb0 | lo kb1], H x 128 B each
-        tc::mbar_arrive_expect_tx(w2_full, 4 * kWBytes);
+        tc::mbar_wait_backoff(acc_full, 0);            // GEMM 1 retired: both rings are free again
+        uint8_t* w2 = smem + 36864;                    // behind the epilogue staging tile; [hi ; lo] per k-block
+        tc::mbar_arrive_expect_tx(w2_full, (H / 32) * kWStage);
 #pragma unroll
-        for (int kb2 = 0; kb2 < 2; ++kb2) {
-          tc::tma_load_2d(w2 + kb2 * kWBytes, &tm_w2hi, w2_full, kb2 * 32, 0);
-          tc::tma_load_2d(w2 + (2 + kb2) * kWBytes, &tm_w2lo, w2_full, kb2 * 32, 0);
+        for (int kb2 = 0; kb2 < H / 32; ++kb2) {
+          tc::tma_load_2d(w2 + kb2 * kWStage, &tm_w2hi, w2_full, kb2 * 32, 0);
+          tc::tma_load_2d(w2 + kb2 * kWStage + kWBytes, &tm_w2lo, w2_full, kb2 * 32, 0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_tf32(kLinBM, H);
-      int s = 0;
-      uint32_t ph = 0, acc = 0;
-      for (int kb = 0; kb < num_kb; ++kb, (++s == STAGES) ? (s = 0, ph ^= 1) : 0) {
-        const int ab = kb & 1;
-        const uint32_t aph = (kb >> 1) & 1;
-        tc::mbar_wait(full + s, ph);       // W hi/lo of this k-block are in shared memory
-        tc::mbar_wait(a_full + ab, aph);   // x hi/lo of this k-block are in tensor memory
+      constexpr uint32_t idesc2 = tc::idesc_tf32(kLinBM, 2 * H);
+      constexpr uint32_t idesc1 = tc::idesc_tf32(kLinBM, H);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int ab = kb & 1, ws = kb % WS;
+        tc::mbar_wait_backoff(a_full + ab, (kb >> 1) & 1);    // x hi/lo of this k-block in tensor memory
+        LTRACE(136 + kb);
+        tc::mbar_wait_backoff(w_full + ws, (kb / WS) & 1);    // [W_hi ; W_lo] of this k-block in shared memory
+        LTRACE(24 + kb);
         tc::fence_after_sync();
-        const uint32_t wh = tc::smem_u32(smem + s * kStageBytes + kXBytes), wl = wh + kWBytes;
+        const uint32_t wst = tc::smem_u32(smem + XS * kXBytes + ws * kWStage);
         const uint32_t ah = tmem_a0 + ab * 64, al = ah + 32;
 #pragma unroll
-        for (int sp = 0; sp < 3; ++sp) {
-          const uint32_t a = (sp == 2) ? al : ah;   // hi*hi, hi*lo, lo*hi
-          const uint32_t b = (sp == 1) ? wl : wh;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mma_tf32_ts(tmem_base, a + ks * 8, tc::smem_desc_k128(b + ks * 32), idesc, acc);
-            acc = 1;
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bdesc = tc::smem_desc_k128(wst + ks * 32);
+          mma_tf32_ts(tmem_base, ah + ks * 8, bdesc, idesc2, acc);   // [hi*hi | hi*lo]
+          mma_tf32_ts(tmem_base, al + ks * 8, bdesc, idesc1, 1u);    // hi*hi columns += lo*hi
+          acc = 1;
         }
-        tc::mma_commit(empty + s);
+        tc::mma_commit(w_empty + ws);
         tc::mma_commit(a_empty + ab);
+        LTRACE(40 + kb);
       }
       tc::mma_commit(acc_full);
       if (FUSE2) {
-        tc::mbar_wait(w2_full, 0);
-        tc::mbar_wait(a2_full, 0);
+        tc::mbar_wait_backoff(w2_full, 0);
+        tc::mbar_wait_backoff(a2_full, 0);
         tc::fence_after_sync();
-        const uint32_t w2h = tc::smem_u32(smem + 2 * kStageBytes), w2l = w2h + 2 * kWBytes;
+        const uint32_t w2s = tc::smem_u32(smem + 36864);
         uint32_t acc2 = 0;
 #pragma unroll
-        for (int sp = 0; sp < 3; ++sp) {
-          const uint32_t a = tmem_a0 + ((sp == 2) ? 64 : 0);
-          const uint32_t b = (sp == 1) ? w2l : w2h;
+        for (int kb2 = 0; kb2 < H / 32; ++kb2)
 #pragma unroll
-          for (int kb2 = 0; kb2 < H / 32; ++kb2)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              mma_tf32_ts(tmem_base, a + kb2 * 32 + ks * 8, tc::smem_desc_k128(b + kb2 * kWBytes + ks * 32), idesc,
-                          acc2);
-              acc2 = 1;
-            }
-        }
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bdesc = tc::smem_desc_k128(w2s + kb2 * kWStage + ks * 32);
+            mma_tf32_ts(tmem_base, tmem_a0 + kb2 * 32 + ks * 8, bdesc, idesc2, acc2);
+            mma_tf32_ts(tmem_base, tmem_a0 + 64 + kb2 * 32 + ks * 8, bdesc, idesc1, 1u);
+            acc2 = 1;
+          }
         tc::mma_commit(acc2_full);
       }
     }
@@ -176,14 +221,12 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     const int q = warp & 3;
     const int r_in_tile = q * 32 + lane;          // == TMEM lane this thread may access
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int kb = 0; kb < num_kb; ++kb, (++s == STAGES) ? (s = 0, ph ^= 1) : 0) {
-      const int ab = kb & 1;
-      const uint32_t aph = (kb >> 1) & 1;
-      tc::mbar_wait(full + s, ph);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int ab = kb & 1, xs = kb % XS;
+      tc::mbar_wait(x_full + xs, (kb / XS) & 1);
+      if (threadIdx.x == 64) LTRACE(72 + kb);
       // row r of the box: 128 B at r*128, its 16-B chunk c stored at chunk position c ^ (r & 7)
-      const uint8_t* rowp = smem + s * kStageBytes + r_in_tile * 128;
+      const uint8_t* rowp = smem + xs * kXBytes + r_in_tile * 128;
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -195,8 +238,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         lo[4 * c + 2] = __float_as_uint(tf32_rna(v.z - h2)); lo[4 * c + 3] = __float_as_uint(tf32_rna(v.w - h3));
       }
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(empty + s);          // x part of the stage consumed (W part: MMA commit)
-      tc::mbar_wait(a_empty + ab, aph ^ 1);                // previous MMAs on this A buffer retired
+      if (lane == 0) tc::mbar_arrive(x_empty + xs);        // tile is in registers: the stage can be refilled
+      tc::mbar_wait(a_empty + ab, ((kb >> 1) & 1) ^ 1);    // previous MMAs on this A buffer retired
       tc::fence_after_sync();
       tmem_st_32x32(tmem_a0 + lane_addr + ab * 64, hi);
       tmem_st_32x32(tmem_a0 + lane_addr + ab * 64 + 32, lo);
@@ -204,58 +247,73 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a_full + ab);
+      if (threadIdx.x == 64) LTRACE(104 + kb);
     }
     // ---------------- epilogue: TMEM -> registers -> this warp's shared-memory slice -> coalesced rows -------
-    // (every stage buffer has been consumed by now: all TMA loads landed and all MMAs retired before acc_full)
+    // (both rings are idle by now: all TMA loads landed and all MMAs retired before acc_full)
     tc::mbar_wait(acc_full, 0);
+    if (threadIdx.x == 64) LTRACE(2);
     tc::fence_after_sync();
-    constexpr int kPitch = H + 1;                                   // odd pitch: conflict-free column writes
+    pdl_wait();   // returns immediately here (the producer passed it long ago); orders this thread's global accesses
+    // staging pitch H + 4 floats: 16-B aligned rows; STS.128 by thread == row and LDS.128 by (row, 16-B chunk)
+    // are both conflict-free per quarter warp (row stride 4 banks mod 32)
+    constexpr int kPitch = H + 4;
     float* stg = reinterpret_cast<float*>(smem) + (size_t)(q * 32) * kPitch;
+    auto drain_acc = [&]() {                                        // stg[row][c] = D[c] + D[H + c]
 #pragma unroll
-    for (int c0 = 0; c0 < H; c0 += 16) {
-      uint32_t r[16];
-      tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r);
-      tc::tmem_ld_wait();
+      for (int c0 = 0; c0 < H; c0 += 16) {
+        uint32_t r1[16], r2[16];
+        tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r1);
+        tc::tmem_ld_32x16(tmem_base + lane_addr + H + c0, r2);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 16; ++c) stg[lane * kPitch + c0 + c] = __uint_as_float(r[c]);
-    }
-    __syncwarp();
-    // rows in batches of 8 with all global loads issued first (independent iterations => latency overlapped)
-    constexpr int kCols = H / 32 > 0 ? H / 32 : 1;       // columns per lane (H = 16: lanes >= 16 idle)
-    float bv[kCols];
+        for (int c = 0; c < 16; c += 4)
+          *reinterpret_cast<float4*>(stg + lane * kPitch + c0 + c) =
+              make_float4(__uint_as_float(r1[c]) + __uint_as_float(r2[c]),
+                          __uint_as_float(r1[c + 1]) + __uint_as_float(r2[c + 1]),
+                          __uint_as_float(r1[c + 2]) + __uint_as_float(r2[c + 2]),
+                          __uint_as_float(r1[c + 3]) + __uint_as_float(r2[c + 3]));
+      }
+      __syncwarp();
+    };
+    drain_acc();
+    if (threadIdx.x == 64) LTRACE(6);
+    // coalesced 128-bit rows: lane -> (row = it * kRowsPerIt + lane / kLanesPerRow, 16-B chunk = lane % kLanesPerRow)
+    constexpr int kLanesPerRow = H / 4, kRowsPerIt = 32 / kLanesPerRow, kIters = 32 / kRowsPerIt;
+    const int er = lane / kLanesPerRow, ec = (lane % kLanesPerRow) * 4;
+    const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + ec)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int kBatch = kIters < 4 ? kIters : 4;   // global loads of a batch are issued before they are used
+    for (int it0 = 0; it0 < kIters; it0 += kBatch) {
+      float4 ad[kBatch], ac[kBatch];
 #pragma unroll
-    for (int j = 0; j < kCols; ++j) bv[j] = (bias && lane + 32 * j < H) ? __ldg(bias + lane + 32 * j) : 0.f;
-    for (int rb = 0; rb < 32; rb += 8) {
-      float ad[8][kCols], ac[8][kCols];
-#pragma unroll
-      for (int r8 = 0; r8 < 8; ++r8) {
-        const int row = row0 + q * 32 + rb + r8;
-#pragma unroll
-        for (int j = 0; j < kCols; ++j) {
-          const int c = lane + 32 * j;
-          const bool ok = row < n && c < H;
-          ad[r8][j] = (addend != nullptr && ok) ? __ldg(addend + (size_t)row * H + c) : 0.f;
-          ac[r8][j] = (act_src != nullptr && ok) ? __ldg(act_src + (size_t)row * H + c) : 1.f;
-        }
+      for (int u = 0; u < kBatch; ++u) {
+        const int row = row0 + q * 32 + (it0 + u) * kRowsPerIt + er;
+        const bool ok = row < n;
+        ad[u] = (addend != nullptr && ok) ? __ldg(reinterpret_cast<const float4*>(addend + (size_t)row * H + ec))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        ac[u] = (act_src != nullptr && ok) ? __ldg(reinterpret_cast<const float4*>(act_src + (size_t)row * H + ec))
+                                           : make_float4(1.f, 1.f, 1.f, 1.f);
       }
 #pragma unroll
-      for (int r8 = 0; r8 < 8; ++r8) {
-        const int row = row0 + q * 32 + rb + r8;
-#pragma unroll
-        for (int j = 0; j < kCols; ++j) {
-          const int c = lane + 32 * j;
-          if (row < n && c < H) {
-            float v = stg[(rb + r8) * kPitch + c] + bv[j] + ad[r8][j];
-            if (act_src != nullptr) v *= ac[r8][j] > 0.f ? 1.f : slope;
-            else v = v > 0.f ? v : slope * v;
-            out[(size_t)row * H + c] = v;
-            if (FUSE2) stg[(rb + r8) * kPitch + c] = v;     // keep the activated tile for the chained GEMM
-          } else if (FUSE2 && c < H) {
-            stg[(rb + r8) * kPitch + c] = 0.f;
-          }
+      for (int u = 0; u < kBatch; ++u) {
+        const int lr = (it0 + u) * kRowsPerIt + er;
+        const int row = row0 + q * 32 + lr;
+        float4 v = *reinterpret_cast<const float4*>(stg + lr * kPitch + ec);
+        v.x += bv.x + ad[u].x; v.y += bv.y + ad[u].y; v.z += bv.z + ad[u].z; v.w += bv.w + ad[u].w;
+        if (act_src != nullptr) {
+          v.x *= ac[u].x > 0.f ? 1.f : slope; v.y *= ac[u].y > 0.f ? 1.f : slope;
+          v.z *= ac[u].z > 0.f ? 1.f : slope; v.w *= ac[u].w > 0.f ? 1.f : slope;
+        } else {
+          v.x = v.x > 0.f ? v.x : slope * v.x; v.y = v.y > 0.f ? v.y : slope * v.y;
+          v.z = v.z > 0.f ? v.z : slope * v.z; v.w = v.w > 0.f ? v.w : slope * v.w;
         }
+        if (row < n) *reinterpret_cast<float4*>(out + (size_t)row * H + ec) = v;
+        else v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FUSE2) *reinterpret_cast<float4*>(stg + lr * kPitch + ec) = v;   // activated tile for the chained GEMM
       }
+      if (it0 == 0 && threadIdx.x == 64) LTRACE(7);
     }
+    if (threadIdx.x == 64) LTRACE(3);
     if (FUSE2) {
       // ---- chained GEMM: this thread's activated row -> TF32 hi/lo -> TMEM (A operand, K = H) ----
       __syncwarp();
@@ -263,11 +321,13 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       for (int kb2 = 0; kb2 < H / 32; ++kb2) {
         uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float v = stg[lane * kPitch + kb2 * 32 + c];
-          const float hh = tf32_rna(v);
-          hi[c] = __float_as_uint(hh);
-          lo[c] = __float_as_uint(tf32_rna(v - hh));
+        for (int c = 0; c < 32; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(stg + lane * kPitch + kb2 * 32 + c);
+          const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+          hi[c] = __float_as_uint(h0); hi[c + 1] = __float_as_uint(h1);
+          hi[c + 2] = __float_as_uint(h2); hi[c + 3] = __float_as_uint(h3);
+          lo[c] = __float_as_uint(tf32_rna(v.x - h0)); lo[c + 1] = __float_as_uint(tf32_rna(v.y - h1));
+          lo[c + 2] = __float_as_uint(tf32_rna(v.z - h2)); lo[c + 3] = __float_as_uint(tf32_rna(v.w - h3));
         }
         tmem_st_32x32(tmem_a0 + lane_addr + kb2 * 32, hi);
         tmem_st_32x32(tmem_a0 + lane_addr + 64 + kb2 * 32, lo);
@@ -277,29 +337,22 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a2_full);
       tc::mbar_wait(acc2_full, 0);
+      if (threadIdx.x == 64) LTRACE(4);
       tc::fence_after_sync();
-#pragma unroll
-      for (int c0 = 0; c0 < H; c0 += 16) {
-        uint32_t r[16];
-        tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) stg[lane * kPitch + c0 + c] = __uint_as_float(r[c]);
-      }
-      __syncwarp();
-      for (int rr = 0; rr < 32; ++rr) {
-        const int row = row0 + q * 32 + rr;
-#pragma unroll
-        for (int j = 0; j < kCols; ++j) {
-          const int c = lane + 32 * j;
-          if (row < n && c < H) out2[(size_t)row * H + c] = stg[rr * kPitch + c];
-        }
+      drain_acc();
+#pragma unroll 4
+      for (int it = 0; it < kIters; ++it) {
+        const int lr = it * kRowsPerIt + er;
+        const int row = row0 + q * 32 + lr;
+        if (row < n)
+          *reinterpret_cast<float4*>(out2 + (size_t)row * H + ec) = *reinterpret_cast<const float4*>(stg + lr * kPitch + ec);
       }
     }
   }
   __syncwarp();
   tc::fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) LTRACE(5);
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, kTmemCols);
@@ -310,46 +363,48 @@ template <int H>
 static int launch_linear(const float* x, const float* w, int w_transposed, const float* b, const float* addend,
                          const float* act_src, float slope, int n, int f, float* out, float* ws, const float* w2,
                          float* out2, cudaStream_t st) {
-  constexpr int STAGES = (H <= 64) ? 3 : 4;   // H <= 64: 3 x 32 KB = 96 KB so that two CTAs share an SM
-  float* w_hi = ws;
+#ifndef DGGB_LIN_XS
+#define DGGB_LIN_XS 4
+#define DGGB_LIN_WS 3
+#endif
+  constexpr int XS = DGGB_LIN_XS, WS = DGGB_LIN_WS;   // H <= 64: 64 KB + 3 x 2H x 128 B <= 112 KB so that two CTAs share an SM
+  float* w_hi = ws;               // [W_hi ; W_lo] stacked: one [2H, F] matrix, one tensor map
   float* w_lo = ws + (size_t)H * f;
-  split_w_kernel<<<(H * f + 255) / 256, 256, 0, st>>>(w, H * f, H, f, w_transposed, w_hi, w_lo);
+  launch_pdl(split_w_kernel, dim3((H * f + 255) / 256), dim3(256), 0, st, w, H * f, H, f, w_transposed, w_hi, w_lo);
   int rc = launch_status();
   if (rc != DGGB_OK) return rc;
-  CUtensorMap tm_x, tm_whi, tm_wlo, tm_w2hi, tm_w2lo;
+  CUtensorMap tm_x, tm_w, tm_w2hi, tm_w2lo;
   rc = make_tmap_2d_f32(&tm_x, x, (uint64_t)n, (uint64_t)f, kLinBM, 32);
   if (rc != DGGB_OK) return rc;
-  rc = make_tmap_2d_f32(&tm_whi, w_hi, (uint64_t)H, (uint64_t)f, H, 32);
+  rc = make_tmap_2d_f32(&tm_w, w_hi, (uint64_t)2 * H, (uint64_t)f, 2 * H, 32);
   if (rc != DGGB_OK) return rc;
-  rc = make_tmap_2d_f32(&tm_wlo, w_lo, (uint64_t)H, (uint64_t)f, H, 32);
-  if (rc != DGGB_OK) return rc;
-  const size_t smem = STAGES * (kLinBM * 128 + 2 * H * 128) + 256 + 1024;
+  const size_t smem = XS * (kLinBM * 128) + WS * (2 * H * 128) + 256;
   const int grid = (n + kLinBM - 1) / kLinBM;
-  if constexpr (H <= 64) {
+  if constexpr (H == 32 || H == 64) {
     if (w2 != nullptr) {
       float* w2_hi = ws + (size_t)2 * H * f;
       float* w2_lo = w2_hi + (size_t)H * H;
-      split_w_kernel<<<(H * H + 255) / 256, 256, 0, st>>>(w2, H * H, H, H, 0, w2_hi, w2_lo);
+      launch_pdl(split_w_kernel, dim3((H * H + 255) / 256), dim3(256), 0, st, w2, H * H, H, H, 0, w2_hi, w2_lo);
       rc = launch_status();
       if (rc != DGGB_OK) return rc;
       rc = make_tmap_2d_f32(&tm_w2hi, w2_hi, (uint64_t)H, (uint64_t)H, H, 32);
       if (rc != DGGB_OK) return rc;
       rc = make_tmap_2d_f32(&tm_w2lo, w2_lo, (uint64_t)H, (uint64_t)H, H, 32);
       if (rc != DGGB_OK) return rc;
-      cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES, true>,
+      cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, XS, WS, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_status(e);
-      linear_tf32x3_kernel<H, STAGES, true><<<grid, kLinThreads, smem, st>>>(
-          tm_x, tm_whi, tm_wlo, tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2);
+      launch_pdl((linear_tf32x3_kernel<H, XS, WS, true>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w,
+                 tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2);
       return launch_status();
     }
   }
   if (w2 != nullptr) return DGGB_ERR_BAD_SHAPE;
-  cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, STAGES, false>,
+  cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, XS, WS, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
-  linear_tf32x3_kernel<H, STAGES, false><<<grid, kLinThreads, smem, st>>>(
-      tm_x, tm_whi, tm_wlo, tm_whi, tm_wlo, b, addend, act_src, slope, n, f, out, nullptr);
+  launch_pdl((linear_tf32x3_kernel<H, XS, WS, false>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w, tm_w, tm_w,
+             b, addend, act_src, slope, n, f, out, static_cast<float*>(nullptr));
   return launch_status();
 }
 
@@ -372,7 +427,8 @@ extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_trans
   float* ws = reinterpret_cast<float*>(workspace);
   // TMA needs 16-byte row pitches and base addresses; the supported widths are the hidden sizes of the path
   if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16) || (w2 && (h > 64 || h % 32)) ||
-      (addend && ((uintptr_t)addend % 16)) || (act_src && ((uintptr_t)act_src % 16)))
+      (addend && ((uintptr_t)addend % 16)) || (act_src && ((uintptr_t)act_src % 16)) ||
+      (b && ((uintptr_t)b % 16)) || (out2 && ((uintptr_t)out2 % 16)))
     return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
   cudaStream_t st = as_stream(stream);
@@ -390,3 +446,12 @@ extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* 
   return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, nullptr, nullptr, workspace,
                            workspace_bytes, stream);
 }
+
+#ifdef DGGB_LIN_TRACE
+extern "C" int dggb_debug_lin_smid(int* host_out) {
+  return cudaMemcpyFromSymbol(host_out, dggb::g_lin_smid, sizeof(int) * 1024) == cudaSuccess ? 0 : -1;
+}
+extern "C" int dggb_debug_lin_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, dggb::g_lin_trace, sizeof(long long) * 2 * 160) == cudaSuccess ? 0 : -1;
+}
+#endif

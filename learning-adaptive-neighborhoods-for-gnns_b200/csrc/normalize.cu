@@ -10,6 +10,8 @@ constexpr int kNormWarps = 8;
 __global__ void __launch_bounds__(kNormWarps* kWarp)
     rowsum_rsqrt_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ val, int n,
                         float* __restrict__ dinv) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kNormWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kNormWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
@@ -23,6 +25,8 @@ __global__ void __launch_bounds__(kNormWarps* kWarp)
 __global__ void __launch_bounds__(kNormWarps* kWarp)
     sym_scale_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, int n, const float* __restrict__ dinv, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kNormWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kNormWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
@@ -36,6 +40,8 @@ __global__ void __launch_bounds__(kNormWarps* kWarp)
     sym_bwd_t_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const float* __restrict__ val, int n, const float* __restrict__ dinv,
                      const float* __restrict__ g, float* __restrict__ t_ws) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kNormWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kNormWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
@@ -56,6 +62,8 @@ __global__ void __launch_bounds__(kNormWarps* kWarp)
     sym_bwd_apply_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n,
                          const float* __restrict__ dinv, const float* __restrict__ g,
                          const float* __restrict__ t_ws, float* __restrict__ dval) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kNormWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kNormWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
@@ -73,8 +81,8 @@ extern "C" int dggb_sym_normalize_fwd(const int32_t* rowptr, const int32_t* col,
   if (!rowptr || !col || !val || !dinv || !out || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
   const int grid = rows_grid(n, kNormWarps, 8);
-  rowsum_rsqrt_kernel<<<grid, kNormWarps * kWarp, 0, as_stream(stream)>>>(rowptr, val, n, dinv);
-  sym_scale_kernel<<<grid, kNormWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, val, n, dinv, out);
+  launch_pdl(rowsum_rsqrt_kernel, dim3(grid), dim3(kNormWarps * kWarp), 0, as_stream(stream), rowptr, val, n, dinv);
+  launch_pdl(sym_scale_kernel, dim3(grid), dim3(kNormWarps * kWarp), 0, as_stream(stream), rowptr, col, val, n, dinv, out);
   return launch_status(2);
 }
 
@@ -83,7 +91,7 @@ extern "C" int dggb_sym_normalize_bwd(const int32_t* rowptr, const int32_t* col,
   if (!rowptr || !col || !val || !dinv || !g || !t_ws || !dval || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
   const int grid = rows_grid(n, kNormWarps, 8);
-  sym_bwd_t_kernel<<<grid, kNormWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, val, n, dinv, g, t_ws);
-  sym_bwd_apply_kernel<<<grid, kNormWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, n, dinv, g, t_ws, dval);
+  launch_pdl(sym_bwd_t_kernel, dim3(grid), dim3(kNormWarps * kWarp), 0, as_stream(stream), rowptr, col, val, n, dinv, g, t_ws);
+  launch_pdl(sym_bwd_apply_kernel, dim3(grid), dim3(kNormWarps * kWarp), 0, as_stream(stream), rowptr, col, n, dinv, g, t_ws, dval);
   return launch_status(2);
 }

@@ -51,11 +51,16 @@ template <> struct Vec<1> {
   __device__ __forceinline__ void red(float* p, float a) const { atomicAdd(p, a * v); }
 };
 
+// Both kernels first pull a 32-entry window of the row's (col, val) pairs into registers with one coalesced
+// load per lane and then broadcast them with shuffles: the neighbour-row gathers no longer wait on a dependent
+// index load, and several of them are in flight per group (unroll 4).
 template <int VEC, int T>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                     const float* __restrict__ val, int n, const float* __restrict__ x, int f, int L,
                     const float* __restrict__ row_scale, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int G = kWarp / L, lg = lane % L, grp = lane / L;
   const int W = VEC * L * T;  // columns covered per pass
@@ -66,19 +71,25 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       Vec<VEC> acc[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) acc[t].zero();
-      for (int e0 = beg; e0 < end; e0 += G) {
-        const int e = e0 + grp;
-        const bool valid = e < end;
-        const int v = valid ? __ldg(col + e) : 0;
-        const float a = valid ? __ldg(val + e) : 0.f;
-        const float* xr = x + (size_t)v * f;
+      for (int w0 = beg; w0 < end; w0 += kWarp) {
+        const int e_l = w0 + lane;
+        const int c_l = (e_l < end) ? __ldg(col + e_l) : 0;
+        const float a_l = (e_l < end) ? __ldg(val + e_l) : 0.f;
+        const int cnt = min(kWarp, end - w0);
+#pragma unroll 4
+        for (int j0 = 0; j0 < cnt; j0 += G) {
+          const int j = j0 + grp;                       // j >= cnt: a_l of that lane is 0 => contributes nothing
+          const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
+          const float a = (j < cnt) ? __shfl_sync(0xffffffffu, a_l, j & 31) : 0.f * __shfl_sync(0xffffffffu, a_l, j & 31);
+          const float* xr = x + (size_t)v * f;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int c = f0 + VEC * (lg + L * t);
-          if (c < f) {
-            Vec<VEC> xv;
-            xv.load(xr + c);
-            acc[t].fma(a, xv);
+          for (int t = 0; t < T; ++t) {
+            const int c = f0 + VEC * (lg + L * t);
+            if (c < f) {
+              Vec<VEC> xv;
+              xv.load(xr + c);
+              acc[t].fma(a, xv);
+            }
           }
         }
       }
@@ -101,6 +112,8 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
                     const float* __restrict__ val, int n, const float* __restrict__ x, int f, int L,
                     const float* __restrict__ row_scale, const float* __restrict__ dy, float* __restrict__ dval,
                     float* __restrict__ dx) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int G = kWarp / L, lg = lane % L, grp = lane / L;
   const int W = VEC * L * T;
@@ -119,28 +132,42 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
           g[t].zero();
         }
       }
-      for (int e0 = beg; e0 < end; e0 += G) {
-        const int e = e0 + grp;
-        const bool valid = e < end;
-        const int v = valid ? __ldg(col + e) : 0;
-        const float a = valid ? __ldg(val + e) : 0.f;
-        float dot = 0.f;
+      for (int w0 = beg; w0 < end; w0 += kWarp) {
+        const int e_l = w0 + lane;
+        const int c_l = (e_l < end) ? __ldg(col + e_l) : 0;
+        const float a_l = (e_l < end) ? __ldg(val + e_l) : 0.f;
+        const int cnt = min(kWarp, end - w0);
+        float dot_l = 0.f;                              // lane j keeps the SDDMM value of entry w0 + j
+#pragma unroll 2
+        for (int j0 = 0; j0 < cnt; j0 += G) {
+          const int j = j0 + grp;
+          const bool valid = j < cnt;
+          const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
+          const float a = __shfl_sync(0xffffffffu, a_l, j & 31);
+          float dot = 0.f;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int c = f0 + VEC * (lg + L * t);
-          if (c < f && valid) {
-            if (dval) {
-              Vec<VEC> xv;
-              xv.load(x + (size_t)v * f + c);
-              dot += g[t].dot(xv);
+          for (int t = 0; t < T; ++t) {
+            const int c = f0 + VEC * (lg + L * t);
+            if (c < f && valid) {
+              if (dval) {
+                Vec<VEC> xv;
+                xv.load(x + (size_t)v * f + c);
+                dot += g[t].dot(xv);
+              }
+              if (dx) g[t].red(dx + (size_t)v * f + c, a);
             }
-            if (dx) g[t].red(dx + (size_t)v * f + c, a);
+          }
+          if (dval) {
+            dot = group_sum(dot, L);
+            // hand the group's result to lane j (each group leader holds one entry of this step)
+#pragma unroll 1
+            for (int gg = 0; gg < G; ++gg) {
+              const float dv = __shfl_sync(0xffffffffu, dot, gg * L);
+              if (lane == j0 + gg) dot_l = dv;
+            }
           }
         }
-        if (dval) {
-          dot = group_sum(dot, L);
-          if (valid && lg == 0) dval[e] = (f0 == 0) ? dot : dval[e] + dot;  // same lane owns e in every pass
-        }
+        if (dval && e_l < end) dval[e_l] = (f0 == 0) ? dot_l : dval[e_l] + dot_l;   // coalesced
       }
     }
   }
@@ -178,8 +205,8 @@ extern "C" int dggb_spmm_csr_fwd(const int32_t* rowptr, const int32_t* col, cons
   if (n == 0) return DGGB_OK;
   const int grid = rows_grid(n, kSpmmWarps, 8);
   return dispatch_vec(f, [&](auto vc, auto tc, int L) {
-    spmm_fwd_kernel<decltype(vc)::value, decltype(tc)::value>
-        <<<grid, kSpmmWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, val, n, x, f, L, row_scale, y);
+    launch_pdl((spmm_fwd_kernel<decltype(vc)::value, decltype(tc)::value>), dim3(grid), dim3(kSpmmWarps * kWarp), 0,
+               as_stream(stream), rowptr, col, val, n, x, f, L, row_scale, y);
     return launch_status();
   });
 }
@@ -191,8 +218,8 @@ extern "C" int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, cons
   if (n == 0 || (!dval && !dx)) return DGGB_OK;
   const int grid = rows_grid(n, kSpmmWarps, 8);
   return dispatch_vec(f, [&](auto vc, auto tc, int L) {
-    spmm_bwd_kernel<decltype(vc)::value, decltype(tc)::value>
-        <<<grid, kSpmmWarps * kWarp, 0, as_stream(stream)>>>(rowptr, col, val, n, x, f, L, row_scale, dy, dval, dx);
+    launch_pdl((spmm_bwd_kernel<decltype(vc)::value, decltype(tc)::value>), dim3(grid), dim3(kSpmmWarps * kWarp), 0,
+               as_stream(stream), rowptr, col, val, n, x, f, L, row_scale, dy, dval, dx);
     return launch_status();
   });
 }

@@ -360,3 +360,27 @@ def splitk_tn(a, b, chunk=1024):
 
 def tall_linear(x, w, b=None, slope=1.0):
     return _TallLinear.apply(x, w, b, float(slope))
+
+
+class _TallMatmul(torch.autograd.Function):
+    """x [N, P] @ w [P, Q] for tall x (the (A x) W products of the conv layers, model.py:596, 74): the weight
+    gradient x^T g reduces over the N nodes into a tiny [P, Q] output, which cuBLAS leaves on a handful of
+    CTAs (81 us at Pubmed shape); it goes through the split-K kernels instead."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return torch.mm(x, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        dx = torch.mm(g, w.t()) if ctx.needs_input_grad[0] else None
+        dw = gemm_tn(x, g, False)[0] if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def tall_matmul(x, w):
+    if x.is_cuda and x.dtype == torch.float32 and x.shape[0] >= 2048 and x.shape[1] <= 512:
+        return _TallMatmul.apply(x, w)
+    return torch.mm(x, w)

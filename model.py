@@ -63,8 +63,8 @@ class GCNConv(nn.Module):
     def forward(self, x, adj):
         if x.shape[1] > self.W.shape[1]:
             # (A x) W == A (x W): aggregate in the narrower space (model.py:594-596 order otherwise)
-            return torch.relu(_aggregate(adj, torch.mm(x, self.W)))
-        return torch.relu(torch.mm(_aggregate(adj, x), self.W))
+            return torch.relu(_aggregate(adj, K.tall_matmul(x, self.W)))
+        return torch.relu(K.tall_matmul(_aggregate(adj, x), self.W))
 
 
 # --------------------------------------------------------------------------- GCN + DGG
@@ -199,7 +199,7 @@ class GraphConvolution(nn.Module):
         else:
             support = (1 - alpha) * hi + alpha * h0
             r = support
-        output = theta * torch.mm(support, self.weight) + (1 - theta) * r
+        output = theta * K.tall_matmul(support, self.weight) + (1 - theta) * r
         if self.residual:
             output = output + input
         return output
