@@ -507,14 +507,27 @@ def kernel_roofline(m, dsets, shape, iters=30):
     dw, db = dd.weight.detach().reshape(-1), dd.bias.detach().reshape(-1)
     be = lin.bias.detach()
 
-    def fwd(i):   # the two forward launches (edge_score + row_rank) through the C-ABI, outputs preallocated
+    fused = all(0 < g.max_row_nnz <= K._FUSED_MAX_ROW for g, _, _ in prepared)   # what the modules dispatch to
+
+    def fwd(i):   # the forward launch(es) of the edge ranker through the C-ABI, outputs preallocated
         g, y, _ = prepared[i % N_SETS]
+        if fused:
+            check(lib().dggb_dgg_edge_fwd_fused(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz),
+                                                i32(g.max_row_nnz), i32(h), p(y), p(be), p(dw), p(db), p(None),
+                                                i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out), stream()), "fwd")
+            return
         check(lib().dggb_dgg_edge_fwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
                                       p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out),
                                       stream()), "fwd")
 
-    def bwd(i):   # the two backward launches (row_dk + edge_grad); R/rank/s/k of the last forward stand in
+    def bwd(i):   # the backward launch(es); R/rank/s/k of the last forward stand in
         g, y, gv = prepared[i % N_SETS]
+        if fused:
+            check(lib().dggb_dgg_edge_bwd_fused(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz),
+                                                i32(g.max_row_nnz), i32(h), p(y), p(be), p(dw), p(db), p(None),
+                                                i32(-1), p(R), p(rank), p(s_row), p(k_row), p(gv), p(small[h + 4:]),
+                                                p(dy), p(small[:h]), p(small[h:h + 2]), stream()), "bwd")
+            return
         check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
                                       p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(s_row), p(k_row), p(gv),
                                       p(small[h + 4:]), p(dy), p(small[:h]), p(small[h:h + 2]), stream()), "bwd")
@@ -553,8 +566,8 @@ def kernel_roofline(m, dsets, shape, iters=30):
     b_tn = n * f_in * 4 + n * h * 4 + h * f_in * 4
     cands = [("linear_tf32x3_kernel (+ split_w)", t_lin, b_lin),
              ("gemm_tn_tf32x3_kernel (+ transpose_split)", t_tn, b_tn),
-             ("dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd),
-             ("dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd)]
+             ("dgg_fwd_fused_kernel" if fused else "dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd),
+             ("dgg_bwd_fused_kernel" if fused else "dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd)]
     name, t, b = max(cands, key=lambda c: c[1])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

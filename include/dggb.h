@@ -103,6 +103,23 @@ int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, const int32_t*
                       const float* g_out /* [E] */, float* ds_ws /* [N] scratch */,
                       float* dy, float* dbe, float* ddeg, void* stream);
 
+/* Single-launch variants of the two calls above for graphs whose longest row has at most 512 entries
+ * (max_row_nnz: the caller's cached max over rows of rowptr[i+1]-rowptr[i]; Cora / Citeseer / Pubmed qualify).
+ * A block owns the rows that start inside its slice of the entry range, keeps their scores (fwd) / ds (bwd) in
+ * shared memory and runs both phases back to back.  Same arguments, same results bit for bit.
+ * Return DGGB_ERR_UNSUPPORTED when max_row_nnz > 512 or nnz == 0: call the two-launch entry point instead. */
+int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
+                            int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
+                            const float* deg_w, const float* deg_b, const float* ablation_noise,
+                            int32_t hard_k, float* R, int32_t* rank, float* s, float* k, float* out,
+                            void* stream);
+int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
+                            int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
+                            const float* deg_w, const float* deg_b, const float* ablation_noise,
+                            int32_t hard_k, const float* R, const int32_t* rank, const float* s,
+                            const float* k, const float* g_out, float* ds_ws, float* dy, float* dbe,
+                            float* ddeg, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * select_top_k of DGG_LearnableK_debug, mode "k_times_edge_prob" (dgm.py:1402-1421; a10, A.2)
  * on CSR rows with an externally estimated k [N]:

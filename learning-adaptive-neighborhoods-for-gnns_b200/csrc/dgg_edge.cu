@@ -382,6 +382,319 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused variants for graphs without hub rows (max row length <= kFusedMaxDeg): ONE launch per direction.
+// Block b owns the CSR rows that START inside the edge interval [b*epb, (b+1)*epb) -- found from erow in two
+// dependent loads, no search -- and therefore the contiguous edge range [rowptr[r0], rowptr[r1]) of at most
+// epb + max_deg entries.  fwd: edge-parallel scores into shared memory -> __syncthreads -> warp-per-row rank from
+// shared memory.  bwd: warp-per-row dk/ds into shared memory -> __syncthreads -> edge-parallel gradients.
+// At Pubmed shape the two-launch path is pure latency (2 x ~12 us for 0.4 MB of edge data); this is one wave of
+// blocks with ~4 dependent memory round trips.  Results are bit-identical to the two-launch kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedMaxDeg = 512;
+constexpr int kFusedThreads = 256;
+constexpr int kFusedRowsCap = 1024;   // rows of ds kept in shared memory (bwd); further rows go through ds_ws
+
+__device__ __forceinline__ void fused_row_range(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
+                                                int n, int nnz, int epb, int* rng) {
+  if (threadIdx.x < 2) {
+    const long long e = (long long)(blockIdx.x + threadIdx.x) * epb;
+    int r;
+    if (e >= nnz || (threadIdx.x == 1 && blockIdx.x == gridDim.x - 1)) {
+      r = n;                                           // trailing (empty) rows belong to the last block
+    } else {
+      r = __ldg(erow + e);                             // row holding entry e
+      if (__ldg(rowptr + r) < (int)e) ++r;             // it started earlier: the next row is the first one >= e
+      else while (r > 0 && __ldg(rowptr + r - 1) == (int)e) --r;   // empty rows that also start at e
+    }
+    rng[threadIdx.x] = r;
+    rng[2 + threadIdx.x] = (r >= n) ? nnz : __ldg(rowptr + r);
+  }
+  __syncthreads();
+}
+
+template <int T>
+__global__ void __launch_bounds__(kFusedThreads)
+    dgg_fwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
+                         const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb, int cap,
+                         const float* __restrict__ y, const float* __restrict__ be,
+                         const float* __restrict__ abl_noise, const float* __restrict__ deg_w,
+                         const float* __restrict__ deg_b, int hard_k, float* R, int32_t* __restrict__ rank,
+                         float* __restrict__ s_out, float* __restrict__ k_out, float* __restrict__ out) {
+  pdl_trigger();
+  extern __shared__ float sR[];          // [cap] scores of this block's edge range
+  __shared__ int rng[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  pdl_wait();
+  fused_row_range(rowptr, erow, n, nnz, epb, rng);
+  const int r0 = rng[0], r1 = rng[1], eb0 = rng[2], eb1 = rng[3];
+  const int nE = eb1 - eb0;
+  // ---- phase 1: every group of L lanes walks a contiguous run of edges ----
+  {
+    RowSlice<T> bias;
+    load_slice<T>(bias, be, h, lg, L);
+    const int groups = (kFusedThreads / kWarp) * G;
+    const int per = (nE + groups - 1) / groups;
+    const int g0 = (warp * G + grp) * per;
+#pragma unroll 4
+    for (int it = 0; it < per; ++it) {
+      const int idx = g0 + it;
+      const bool valid = idx < nE;
+      const int e = eb0 + (valid ? idx : 0);
+      const int u = valid ? __ldg(erow + e) : 0, v = valid ? __ldg(col + e) : 0;
+      RowSlice<T> yu, yv;
+      load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
+      load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+      const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
+      if (valid && lg == 0) {
+        float r = sigmoidf_(z);
+        if (abl_noise != nullptr) r = sigmoidf_(r + __ldg(abl_noise + e));  // dgm.py:1933-1935
+        R[e] = r;
+        if (idx < cap) sR[idx] = r;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: 8 lanes per row (the average row has ~6 entries), four rows per warp at a time.  The rank is a
+  // count over the row (deg^2 compares): rows longer than kLongRow would leave one 8-lane group running long after
+  // the rest of the grid has finished (152-entry row: ~25 us), so they only get s and k here and are ranked by the
+  // whole block afterwards. ----
+  constexpr int kLongRow = 32, kLongCap = 32;
+  __shared__ int long_rows[kLongCap];
+  __shared__ float long_k[kLongCap];
+  __shared__ int n_long;
+  if (threadIdx.x == 0) n_long = 0;
+  __syncthreads();
+  const float w = __ldg(deg_w), b = __ldg(deg_b);
+  const int sub = lane >> 3, sl = lane & 7;
+  auto rank_entries = [&](int beg, int deg, float k, bool in_s, int first, int stride) {
+    const float* srow = sR + (beg - eb0);
+    for (int m = first; m < deg; m += stride) {
+      const float mine = in_s ? srow[m] : __ldcg(R + beg + m);
+      int cnt = 0;
+      if (in_s) {
+#pragma unroll 4
+        for (int j = 0; j < deg; ++j) {
+          const float rj = srow[j];
+          cnt += (rj > mine) || (rj == mine && j < m);
+        }
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < deg; ++j) {
+          const float rj = __ldcg(R + beg + j);
+          cnt += (rj > mine) || (rj == mine && j < m);
+        }
+      }
+      rank[beg + m] = cnt;
+      out[beg + m] = (hard_k >= 0) ? (cnt < hard_k ? mine : 0.f) : mine * first_k_plus_one((float)cnt, k);
+    }
+  };
+  for (int i0 = r0 + warp * 4; i0 < r1; i0 += (kFusedThreads / kWarp) * 4) {
+    const int i = i0 + sub;
+    const bool rv = i < r1;
+    const int beg = rv ? __ldg(rowptr + i) : eb0, end = rv ? __ldg(rowptr + i + 1) : eb0, deg = end - beg;
+    const bool in_s = (end - eb0) <= cap;
+    const float* srow = sR + (beg - eb0);
+    float s = 0.f;
+    for (int e = sl; e < deg; e += 8) s += in_s ? srow[e] : __ldcg(R + beg + e);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const float k = leaky(w * s + b);  // dgm.py:1791-1792
+    int slot = -1;
+    if (deg > kLongRow && sl == 0) slot = atomicAdd(&n_long, 1);
+    slot = __shfl_sync(0xffffffffu, slot, lane & ~7);          // outside any divergent branch
+    const bool deferred = deg > kLongRow && slot < kLongCap;    // list full: rank it here (slow but correct)
+    if (deferred && sl == 0) {
+      long_rows[slot] = i;
+      long_k[slot] = k;
+    }
+    if (!deferred) rank_entries(beg, deg, k, in_s, sl, 8);
+    if (rv && sl == 0) {
+      s_out[i] = s;
+      k_out[i] = k;
+    }
+  }
+  __syncthreads();
+  const int nl = min(n_long, kLongCap);
+  for (int q = 0; q < nl; ++q) {
+    const int i = long_rows[q];
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    rank_entries(beg, end - beg, long_k[q], (end - eb0) <= cap, threadIdx.x, kFusedThreads);
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(kFusedThreads)
+    dgg_bwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
+                         const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb,
+                         const float* __restrict__ y, const float* __restrict__ be,
+                         const float* __restrict__ abl_noise, int hard_k, const float* __restrict__ R,
+                         const int32_t* __restrict__ rank, const float* __restrict__ s_in,
+                         const float* __restrict__ k_in, const float* __restrict__ g_out,
+                         const float* __restrict__ deg_w, const float* __restrict__ deg_b, float* ds_ws,
+                         float* __restrict__ dy, float* __restrict__ dbe, float* __restrict__ ddeg) {
+  pdl_trigger();
+  __shared__ float sds[kFusedRowsCap];
+  __shared__ float dbe_s[512];           // block-level bias-gradient accumulator (h <= 512)
+  __shared__ float red[2][kFusedThreads / kWarp];
+  __shared__ int rng[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  for (int c = threadIdx.x; c < h; c += kFusedThreads) dbe_s[c] = 0.f;
+  pdl_wait();
+  fused_row_range(rowptr, erow, n, nnz, epb, rng);
+  const int r0 = rng[0], r1 = rng[1], eb0 = rng[2], eb1 = rng[3];
+  const int nE = eb1 - eb0;
+  // ---- phase A: d out / d k_i chained through the degree decoder (soft mode only) ----
+  if (hard_k < 0) {
+    const float w = __ldg(deg_w), b = __ldg(deg_b);
+    float dw_acc = 0.f, db_acc = 0.f;
+    const int sub = lane >> 3, sl = lane & 7;
+    for (int i0 = r0 + warp * 4; i0 < r1; i0 += (kFusedThreads / kWarp) * 4) {
+      const int i = i0 + sub;
+      const bool rv = i < r1;
+      const int beg = rv ? __ldg(rowptr + i) : 0, end = rv ? __ldg(rowptr + i + 1) : 0;
+      const float s = rv ? __ldg(s_in + i) : 0.f, k = rv ? __ldg(k_in + i) : 0.f;
+      float dk = 0.f;
+      for (int e = beg + sl; e < end; e += 8) {
+        const float th = tanhf((float)__ldg(rank + e) - k);
+        dk += __ldg(g_out + e) * __ldg(R + e) * 0.5f * (1.f - th * th);
+      }
+      dk += __shfl_xor_sync(0xffffffffu, dk, 4);
+      dk += __shfl_xor_sync(0xffffffffu, dk, 2);
+      dk += __shfl_xor_sync(0xffffffffu, dk, 1);
+      const float lr = leaky_grad(w * s + b);
+      if (rv && sl == 0) {
+        const float dsi = dk * lr * w;
+        ds_ws[i] = dsi;
+        if (i - r0 < kFusedRowsCap) sds[i - r0] = dsi;
+        dw_acc += dk * lr * s;
+        db_acc += dk * lr;
+      }
+    }
+    dw_acc = warp_sum(dw_acc);
+    db_acc = warp_sum(db_acc);
+    if (lane == 0) {
+      red[0][warp] = dw_acc;
+      red[1][warp] = db_acc;
+    }
+  }
+  __syncthreads();
+  if (hard_k < 0 && threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kFusedThreads / kWarp; ++wv) t += red[threadIdx.x][wv];
+    if (t != 0.f) atomicAdd(ddeg + threadIdx.x, t);
+  }
+  // ---- phase B: per edge, recompute z and scatter d pre ----
+  RowSlice<T> bias, dbe_acc, acc;
+  load_slice<T>(bias, be, h, lg, L);
+#pragma unroll
+  for (int t = 0; t < T; ++t) dbe_acc.v[t] = acc.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int groups = (kFusedThreads / kWarp) * G;
+  const int per = (nE + groups - 1) / groups;
+  const int g0 = (warp * G + grp) * per;
+  int cur_u = -1;
+#pragma unroll 2
+  for (int it = 0; it < per; ++it) {
+    const int idx = g0 + it;
+    const bool valid = idx < nE;
+    const int e = eb0 + (valid ? idx : 0);
+    const int u = valid ? __ldg(erow + e) : 0, v = valid ? __ldg(col + e) : 0;
+    float dr = 0.f;
+    if (valid) {
+      const float g = __ldg(g_out + e);
+      if (hard_k >= 0) {
+        dr = (__ldg(rank + e) < hard_k) ? g : 0.f;
+      } else {
+        const float dsu = (u - r0 < kFusedRowsCap) ? sds[u - r0] : __ldcg(ds_ws + u);
+        dr = g * first_k_plus_one((float)__ldg(rank + e), __ldg(k_in + u)) + dsu;
+      }
+      if (abl_noise != nullptr) {
+        const float r2 = __ldg(R + e);
+        dr *= r2 * (1.f - r2);  // through the second sigmoid
+      }
+    }
+    RowSlice<T> yu, yv;
+    load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
+    load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+    const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
+    const float r1s = sigmoidf_(z);
+    const float dz = valid ? dr * r1s * (1.f - r1s) : 0.f;
+    if (valid && u != cur_u) {  // group-uniform branch: flush the finished source row
+      if (cur_u >= 0) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < h) red_add4(dy + (size_t)cur_u * h + c, acc.v[t]);
+          acc.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      cur_u = u;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int c = 4 * (lg + L * t);
+      float4 d;
+      d.x = dz * leaky_grad(yu.v[t].x - yv.v[t].x + bias.v[t].x);
+      d.y = dz * leaky_grad(yu.v[t].y - yv.v[t].y + bias.v[t].y);
+      d.z = dz * leaky_grad(yu.v[t].z - yv.v[t].z + bias.v[t].z);
+      d.w = dz * leaky_grad(yu.v[t].w - yv.v[t].w + bias.v[t].w);
+      dbe_acc.v[t].x += d.x; dbe_acc.v[t].y += d.y; dbe_acc.v[t].z += d.z; dbe_acc.v[t].w += d.w;
+      if (valid && u != v) {  // a self loop adds +d and -d to the same row: skip both (it still counts for dbe)
+        acc.v[t].x += d.x; acc.v[t].y += d.y; acc.v[t].z += d.z; acc.v[t].w += d.w;
+        if (c < h) red_add4(dy + (size_t)v * h + c, make_float4(-d.x, -d.y, -d.z, -d.w));
+      }
+    }
+  }
+  if (cur_u >= 0) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int c = 4 * (lg + L * t);
+      if (c < h) red_add4(dy + (size_t)cur_u * h + c, acc.v[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    for (int o = L; o < kWarp; o <<= 1) {
+      dbe_acc.v[t].x += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].x, o);
+      dbe_acc.v[t].y += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].y, o);
+      dbe_acc.v[t].z += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].z, o);
+      dbe_acc.v[t].w += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].w, o);
+    }
+    const int c = 4 * (lg + L * t);
+    if (grp == 0 && c < h) {
+      atomicAdd(&dbe_s[c + 0], dbe_acc.v[t].x);
+      atomicAdd(&dbe_s[c + 1], dbe_acc.v[t].y);
+      atomicAdd(&dbe_s[c + 2], dbe_acc.v[t].z);
+      atomicAdd(&dbe_s[c + 3], dbe_acc.v[t].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < h; c += kFusedThreads) atomicAdd(dbe + c, dbe_s[c]);
+}
+
+// grid of the fused kernels: at most one wave (blocks_per_sm from the occupancy calculator), >= 256 edges per block
+static void fused_grid(int nnz, int blocks_per_sm, int* blocks, int* epb) {
+  long long b = ((long long)nnz + 255) / 256;
+  const long long cap = (long long)kNumSMs * (blocks_per_sm < 1 ? 1 : blocks_per_sm);
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  *epb = (int)((nnz + b - 1) / b);
+  *blocks = (nnz + *epb - 1) / *epb;
+}
+
+// Lanes per edge.  These kernels are issue-bound, not bandwidth-bound (ncu: 4.6 M warp instructions for 108 k edges
+// with 16 lanes x 1 float4 per edge at h = 64): four float4 chunks per lane amortise the index shuffles, address
+// arithmetic, group reduction and sigmoid over 4x more channels per instruction.
+static int lanes_per_edge(int h) {
+  int L = 1;
+  while (L < 32 && 16 * L < h) L *= 2;
+  return L;
+}
+
 template <typename F>
 static int dispatch_T(int h, int L, F&& f) {
   const int T = (h + 4 * L - 1) / (4 * L);
@@ -411,7 +724,7 @@ extern "C" int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow, con
     return DGGB_ERR_BAD_ARG;
   if (h % 4 != 0 || h > 512) return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
-  const int L = pow2_floor32(h / 4);
+  const int L = lanes_per_edge(h);
   int st = DGGB_OK;
   if (nnz > 0) {
     st = dispatch_T(h, L, [&](auto tc) {
@@ -437,7 +750,7 @@ extern "C" int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, con
     return DGGB_ERR_BAD_ARG;
   if (h % 4 != 0 || h > 512) return DGGB_ERR_BAD_SHAPE;
   if (n == 0 || nnz == 0) return DGGB_OK;
-  const int L = pow2_floor32(h / 4);
+  const int L = lanes_per_edge(h);
   if (hard_k < 0) {
     launch_pdl(dgg_row_dk_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
         rowptr, n, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, ddeg);
@@ -469,4 +782,57 @@ extern "C" int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float
   launch_pdl(row_firstk_bwd_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
       rowptr, n, score, k, rank, g_out, dscore, dk);
   return launch_status();
+}
+
+extern "C" int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
+                                       int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
+                                       const float* deg_w, const float* deg_b, const float* ablation_noise,
+                                       int32_t hard_k, float* R, int32_t* rank, float* s, float* k, float* out,
+                                       void* stream) {
+  if (!rowptr || !erow || !col || !y || !be || !deg_w || !deg_b || !R || !rank || !s || !k || !out || n < 0 ||
+      nnz < 0 || h <= 0 || max_row_nnz < 0)
+    return DGGB_ERR_BAD_ARG;
+  if (h % 4 != 0 || h > 512) return DGGB_ERR_BAD_SHAPE;
+  if (nnz == 0 || max_row_nnz > kFusedMaxDeg) return DGGB_ERR_UNSUPPORTED;   // use the two-launch entry point
+  if (n == 0) return DGGB_OK;
+  const int L = lanes_per_edge(h);
+  return dispatch_T(h, L, [&](auto tc) {
+    constexpr int T = decltype(tc)::value;
+    int occ = 0, blocks, epb;
+    // the shared-memory slice depends on epb, which depends on the occupancy: size it for the smallest grid first
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgg_fwd_fused_kernel<T>, kFusedThreads,
+                                                  (size_t)(256 + max_row_nnz) * sizeof(float));
+    fused_grid(nnz, occ, &blocks, &epb);
+    const int cap = epb + max_row_nnz;
+    if ((size_t)cap * sizeof(float) > 48 * 1024) return (int)DGGB_ERR_UNSUPPORTED;
+    launch_pdl(dgg_fwd_fused_kernel<T>, dim3(blocks), dim3(kFusedThreads), (size_t)cap * sizeof(float),
+               as_stream(stream), rowptr, erow, col, n, nnz, h, L, epb, cap, y, be, ablation_noise, deg_w, deg_b,
+               hard_k, R, rank, s, k, out);
+    return launch_status();
+  });
+}
+
+extern "C" int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
+                                       int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
+                                       const float* deg_w, const float* deg_b, const float* ablation_noise,
+                                       int32_t hard_k, const float* R, const int32_t* rank, const float* s,
+                                       const float* k, const float* g_out, float* ds_ws, float* dy, float* dbe,
+                                       float* ddeg, void* stream) {
+  if (!rowptr || !erow || !col || !y || !be || !deg_w || !deg_b || !R || !rank || !s || !k || !g_out || !ds_ws ||
+      !dy || !dbe || !ddeg || n < 0 || nnz < 0 || h <= 0 || max_row_nnz < 0)
+    return DGGB_ERR_BAD_ARG;
+  if (h % 4 != 0 || h > 512) return DGGB_ERR_BAD_SHAPE;
+  if (nnz == 0 || max_row_nnz > kFusedMaxDeg) return DGGB_ERR_UNSUPPORTED;
+  if (n == 0) return DGGB_OK;
+  const int L = lanes_per_edge(h);
+  return dispatch_T(h, L, [&](auto tc) {
+    constexpr int T = decltype(tc)::value;
+    int occ = 0, blocks, epb;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgg_bwd_fused_kernel<T>, kFusedThreads, 0);
+    fused_grid(nnz, occ, &blocks, &epb);
+    launch_pdl(dgg_bwd_fused_kernel<T>, dim3(blocks), dim3(kFusedThreads), 0, as_stream(stream), rowptr, erow, col, n,
+               nnz, h, L, epb, y, be, ablation_noise, hard_k, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, dy, dbe,
+               ddeg);
+    return launch_status();
+  });
 }

@@ -18,6 +18,9 @@ def _require_cuda(*ts):
             raise RuntimeError("dgg_b200 ops need CUDA tensors (no CPU fallback)")
 
 
+_FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu
+
+
 class _DGGEdge(torch.autograd.Function):
     """dgm.py:1781-1810 on CSR: scores, degree estimate, in-row ranks, soft first-k."""
 
@@ -34,10 +37,17 @@ class _DGGEdge(torch.autograd.Function):
         s = torch.empty(n, dtype=torch.float32, device=dev)
         k = torch.empty(n, dtype=torch.float32, device=dev)
         out = torch.empty(E, dtype=torch.float32, device=dev)
-        check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(h), p(y), p(be), p(deg_w),
-                                      p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k), p(out),
-                                      stream()), "dgg_edge_fwd")
-        ctx.graph, ctx.hard_k = graph, hard_k
+        mx = graph.max_row_nnz
+        fused = 0 < mx <= _FUSED_MAX_ROW and E > 0   # no hub rows: one launch per direction
+        if fused:
+            check(lib().dggb_dgg_edge_fwd_fused(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(mx),
+                                                i32(h), p(y), p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R),
+                                                p(rank), p(s), p(k), p(out), stream()), "dgg_edge_fwd_fused")
+        else:
+            check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(h), p(y),
+                                          p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k),
+                                          p(out), stream()), "dgg_edge_fwd")
+        ctx.graph, ctx.hard_k, ctx.fused_mx = graph, hard_k, (mx if fused else -1)
         ctx.save_for_backward(y, be, deg_w, deg_b, noise, R, rank, s, k)
         ctx.mark_non_differentiable(k, R, rank)
         return out, k, R, rank
@@ -52,9 +62,15 @@ class _DGGEdge(torch.autograd.Function):
         dy = zbuf[:n * h].view(n, h)
         small = zbuf[n * h:]
         dbe, ddeg, ds_ws = small[:h], small[h:h + 2], small[h + 4:]
-        check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
-                                      p(deg_w), p(deg_b), p(noise), i32(ctx.hard_k), p(R), p(rank), p(s), p(k),
-                                      p(_f32c(g_out)), p(ds_ws), p(dy), p(dbe), p(ddeg), stream()), "dgg_edge_bwd")
+        if ctx.fused_mx > 0:
+            check(lib().dggb_dgg_edge_bwd_fused(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(ctx.fused_mx),
+                                                i32(h), p(y), p(be), p(deg_w), p(deg_b), p(noise), i32(ctx.hard_k),
+                                                p(R), p(rank), p(s), p(k), p(_f32c(g_out)), p(ds_ws), p(dy), p(dbe),
+                                                p(ddeg), stream()), "dgg_edge_bwd_fused")
+        else:
+            check(lib().dggb_dgg_edge_bwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
+                                          p(deg_w), p(deg_b), p(noise), i32(ctx.hard_k), p(R), p(rank), p(s), p(k),
+                                          p(_f32c(g_out)), p(ds_ws), p(dy), p(dbe), p(ddeg), stream()), "dgg_edge_bwd")
         return dy, dbe, ddeg[0:1].reshape(1, 1), ddeg[1:2], None, None, None
 
 

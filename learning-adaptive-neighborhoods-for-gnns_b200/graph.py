@@ -16,7 +16,7 @@ from ._lib import check, i32, i64, lib, p, stream
 class CSRGraph:
     """rowptr int32 [n+1], col int32 [nnz]; rows sorted by column (coalesced COO order)."""
 
-    __slots__ = ("n", "nnz", "rowptr", "col", "indices", "_loops", "_erow")
+    __slots__ = ("n", "nnz", "rowptr", "col", "indices", "_loops", "_erow", "_max_row_nnz")
 
     def __init__(self, n, rowptr, col, indices=None):
         self.n = int(n)
@@ -26,6 +26,7 @@ class CSRGraph:
         self.indices = indices  # int64 [2, nnz] (built lazily for COO export)
         self._loops = None
         self._erow = None
+        self._max_row_nnz = None
 
     @property
     def erow(self) -> torch.Tensor:
@@ -34,6 +35,19 @@ class CSRGraph:
             self._erow = torch.empty(self.nnz, dtype=torch.int32, device=self.col.device)
             check(lib().dggb_csr_expand_rows(p(self.rowptr), i32(self.n), p(self._erow), stream()), "csr_expand_rows")
         return self._erow
+
+    @property
+    def max_row_nnz(self) -> int:
+        """Longest row (one device->host read per structure; -1 while a CUDA graph is being captured and the
+        value is not cached yet, which selects the two-launch kernels)."""
+        if self._max_row_nnz is None:
+            if self.nnz == 0:
+                self._max_row_nnz = 0
+            elif self.rowptr.is_cuda and torch.cuda.is_current_stream_capturing():
+                return -1
+            else:
+                self._max_row_nnz = int((self.rowptr[1:] - self.rowptr[:-1]).max().item())
+        return self._max_row_nnz
 
     # ------------------------------------------------------------------ construction
     @staticmethod

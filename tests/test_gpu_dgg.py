@@ -319,3 +319,49 @@ def test_encode_project_chained_gemm(n, f, h):
     xe = torch.where(pre > 0, pre, pre * 0.01)
     torch.testing.assert_close(x_enc, xe.float(), rtol=2e-5, atol=2e-5)
     torch.testing.assert_close(y, (xe @ we.double().t()).float(), rtol=2e-5, atol=3e-5)
+
+
+@pytest.mark.parametrize("n,h,avg_deg,noise,hard_k", [(3000, 64, 6, False, -1), (777, 16, 40, True, -1),
+                                                      (5000, 128, 3, False, 4), (64, 32, 2, False, -1)])
+def test_fused_edge_kernels_match_two_launch(n, h, avg_deg, noise, hard_k):
+    """The single-launch kernels (graphs without hub rows) against the two-launch ones on the same inputs:
+    scores and ranks bit for bit; k / outputs / gradients to summation-order tolerance.  The graph has empty
+    rows in the middle and at the end."""
+    from dgg_b200 import CSRGraph, functional as K
+
+    gen = torch.Generator().manual_seed(n + h)
+    m = n * avg_deg
+    src = torch.randint(0, n - 7, (m,), generator=gen)           # last 7 rows empty
+    dst = torch.randint(0, n, (m,), generator=gen)
+    keep = (src % 11) != 3                                        # every 11th row empty
+    a = torch.sparse_coo_tensor(torch.stack([src[keep], dst[keep]]), torch.ones(int(keep.sum())), (n, n)).coalesce()
+    g = CSRGraph.from_indices(a.indices().cuda(), n)
+    assert 0 < g.max_row_nnz <= K._FUSED_MAX_ROW
+    E = g.nnz
+    y = torch.randn(n, h, generator=gen).cuda()
+    be = (0.1 * torch.randn(h, generator=gen)).cuda()
+    dw = torch.tensor([[0.7]]).cuda()
+    db = torch.tensor([0.3]).cuda()
+    nz = (torch.rand(E, generator=gen) * 2 - 1).cuda() if noise else None
+    wl = torch.randn(E, generator=gen).cuda()
+
+    def run(fused):
+        old = K._FUSED_MAX_ROW
+        K._FUSED_MAX_ROW = old if fused else 0
+        try:
+            ps = [t.clone().requires_grad_(True) for t in (y, be, dw, db)]
+            out, k, R, rank = K.dgg_edge(ps[0], ps[1], ps[2], ps[3], g, noise=nz, hard_k=hard_k)
+            (out * wl).sum().backward()
+            return (out.detach(), k, R, rank), [q.grad for q in ps]
+        finally:
+            K._FUSED_MAX_ROW = old
+
+    (fa, ga), (fb, gb) = run(True), run(False)
+    assert torch.equal(fa[2], fb[2]) and torch.equal(fa[3], fb[3])          # scores and ranks: bit for bit
+    torch.testing.assert_close(fa[1], fb[1], rtol=1e-6, atol=1e-6)           # k: the row sum is ordered differently
+    torch.testing.assert_close(fa[0], fb[0], rtol=1e-5, atol=1e-6)
+    for qa, qb in zip(ga, gb):
+        if qb is None:
+            assert qa is None
+        else:
+            torch.testing.assert_close(qa, qb, rtol=1e-4, atol=1e-5)
