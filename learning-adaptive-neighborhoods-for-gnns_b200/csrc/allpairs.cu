@@ -509,7 +509,7 @@ constexpr int kAP2Threads = 320;
 struct AP2Smem {
   uint32_t b0, b_stage_bytes, nrm, vals[2], idx[2], qv[2], qi[2], zpart, bars, total;
 };
-__host__ __device__ inline AP2Smem ap2_smem_layout(int kb, int split, int stages, int kc) {
+__host__ __device__ inline AP2Smem ap2_smem_layout(int kb, int split, int stages, int kc, int qcap = kQCap) {
   AP2Smem L;
   uint32_t off = 0;
   L.b0 = off;
@@ -519,8 +519,8 @@ __host__ __device__ inline AP2Smem ap2_smem_layout(int kb, int split, int stages
   for (int g = 0; g < 2; ++g) {
     L.vals[g] = off; off += kc * kBM * 4;
     L.idx[g] = off; off += kc * kBM * 4;
-    L.qv[g] = off; off += kQCap * kBM * 4;
-    L.qi[g] = off; off += kQCap * kBM * 4;
+    L.qv[g] = off; off += qcap * kBM * 4;
+    L.qi[g] = off; off += qcap * kBM * 4;
   }
   L.zpart = off; off += kBM * 4;
   L.bars = off; off += 192;
@@ -534,12 +534,12 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
                           const float* __restrict__ z_hi, const float* __restrict__ z_lo, int npad, int dpad,
                           const float* __restrict__ nrm, int n, int row_begin, int row_count,
                           const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
-                          unsigned long long seed, float noise_scale, int kc, int stages,
+                          unsigned long long seed, float noise_scale, int kc, int stages, int qcap, int qflush,
                           int32_t* __restrict__ out_idx, float* __restrict__ out_val, float inv_temp,
                           float* __restrict__ out_rowsum) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const AP2Smem L = ap2_smem_layout(KB, SPLIT, stages, kc);
+  const AP2Smem L = ap2_smem_layout(KB, SPLIT, stages, kc, qcap);   // queue: qcap >= qflush - 1 + kChunk slots
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;            // [stages]  TMA -> MMA / epilogue
   uint64_t* empty = bars + 4;       // [stages]  MMA commit + the 4 warps of the group that scored the tile
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
           if (diag_tile) body(std::true_type{});
           else body(std::false_type{});
         }
-        flush(__ballot_sync(0xffffffffu, qn >= kQFlush));
+        flush(__ballot_sync(0xffffffffu, qn >= qflush));
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -852,7 +852,8 @@ using namespace dggb;
 extern "C" int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d) {
   if (n < 0 || d <= 0) return DGGB_ERR_BAD_ARG;
   const int64_t npad = ((int64_t)n + 127) / 128 * 128;
-  const int64_t dpad = ((int64_t)d + 31) / 32 * 32;
+  int64_t dpad = ((int64_t)d + 31) / 32 * 32;
+  if (dpad == 96) dpad = 128;   // k-blocks come in 1, 2 or 4 (zero-padded columns)
   return npad * dpad * 4 * 2 + npad * 4;
 }
 
@@ -868,7 +869,8 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   if (workspace_bytes < dggb_allpairs_workspace_bytes(n, d)) return DGGB_ERR_WORKSPACE;
   if (row_count == 0) return DGGB_OK;
   const int npad = (n + 127) / 128 * 128;
-  const int dpad = (d + 31) / 32 * 32;
+  int dpad = (d + 31) / 32 * 32;
+  if (dpad == 96) dpad = 128;
   float* hi = reinterpret_cast<float*>(workspace);
   float* lo = hi + (size_t)npad * dpad;
   float* nrm = lo + (size_t)npad * dpad;
@@ -889,10 +891,14 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   if (out_rowsum && nmode2 != 3) return DGGB_ERR_UNSUPPORTED;
   // measured (scripts/ap_micro.py, N = 37 888, Gpairs/s, v1 -> v2): no noise 352 -> 377, Philox 215 -> 284
   const bool want_v2 = !getenv("DGGB_AP_V1");
-  if (kc <= 32 && !(kb == 4 && precision == 3) && want_v2) {
+  // d = 128 at 3xTF32 (the reference's default dgm_dim): a key stage is 64 KB, so the per-row queues shrink to 16
+  // slots (flushed whenever anything is pending) to keep two stages + both groups' lists under 227 KB
+  const bool big = (kb == 4 && precision == 3);
+  const int qcap = big ? kChunk : kQCap, qflush = big ? 1 : kQFlush;
+  if (kc <= 32 && (want_v2 || big)) {
     int st2 = 4;
-    AP2Smem L2 = ap2_smem_layout(kb, precision, st2, kc);
-    while (st2 > 2 && L2.total + 1024 > 227 * 1024) L2 = ap2_smem_layout(kb, precision, --st2, kc);
+    AP2Smem L2 = ap2_smem_layout(kb, precision, st2, kc, qcap);
+    while (st2 > 2 && L2.total + 1024 > 227 * 1024) L2 = ap2_smem_layout(kb, precision, --st2, kc, qcap);
     if (L2.total + 1024 <= 227 * 1024) {
       const size_t smem2 = L2.total + 1024;
       const int grid2 = (row_count + kBM - 1) / kBM;
@@ -903,7 +909,7 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
     if (e != cudaSuccess) return cuda_status(e);                                                                  \
     allpairs_topk2_kernel<KB_, SP_, NM_><<<grid2, kAP2Threads, smem2, st>>>(                                      \
         tm_hi, tm_lo, hi, lo, npad, dpad, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld,            \
-        (unsigned long long)seed, noise_scale, kc, st2, out_idx, out_val, inv_temp, out_rowsum);                  \
+        (unsigned long long)seed, noise_scale, kc, st2, qcap, qflush, out_idx, out_val, inv_temp, out_rowsum);    \
   } while (0)
 #define DGGB_AP2_LAUNCH(KB_, SP_)                                                                                 \
   do {                                                                                                            \
@@ -916,6 +922,7 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
       else if (kb == 1) DGGB_AP2_LAUNCH(1, 1);
       else if (kb == 2 && precision == 3) DGGB_AP2_LAUNCH(2, 3);
       else if (kb == 2) DGGB_AP2_LAUNCH(2, 1);
+      else if (kb == 4 && precision == 3) DGGB_AP2_LAUNCH(4, 3);
       else if (kb == 4) DGGB_AP2_LAUNCH(4, 1);
       else return DGGB_ERR_BAD_SHAPE;
 #undef DGGB_AP2_LAUNCH

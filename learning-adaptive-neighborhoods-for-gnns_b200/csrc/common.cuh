@@ -67,7 +67,8 @@ __device__ __forceinline__ float group_sum(float v, int width) {
   for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeaky * v; }
+// max(v, 0.01 v): same value as the select form for every finite v (slope < 1), two instructions instead of three
+__device__ __forceinline__ float leaky(float v) { return fmaxf(v, kLeaky * v); }
 __device__ __forceinline__ float leaky_grad(float v) { return v > 0.f ? 1.f : kLeaky; }
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 

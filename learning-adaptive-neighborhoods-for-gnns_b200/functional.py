@@ -48,12 +48,15 @@ class _DGGEdge(torch.autograd.Function):
                                           p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k),
                                           p(out), stream()), "dgg_edge_fwd")
         ctx.graph, ctx.hard_k, ctx.fused_mx = graph, hard_k, (mx if fused else -1)
+        ctx.set_materialize_grads(False)   # k / R / rank never carry gradients: no zero tensors for them per step
         ctx.save_for_backward(y, be, deg_w, deg_b, noise, R, rank, s, k)
         ctx.mark_non_differentiable(k, R, rank)
         return out, k, R, rank
 
     @staticmethod
     def backward(ctx, g_out, _gk, _gR, _grank):
+        if g_out is None:
+            return (None,) * 7
         y, be, deg_w, deg_b, noise, R, rank, s, k = ctx.saved_tensors
         g = ctx.graph
         n, h = y.shape
@@ -306,12 +309,16 @@ class _EncodeProject(torch.autograd.Function):
             raise RuntimeError("encode_project: shape not supported by the tensor-core kernels")
         ctx.slope = slope
         ctx.save_for_backward(x, wn, we, x_enc)
+        ctx.set_materialize_grads(False)   # an unused output must not cost an [N, h] zero fill
         return x_enc, y
 
     @staticmethod
     def backward(ctx, g_xenc, g_y):
         x, wn, we, x_enc = ctx.saved_tensors
-        g_y = _f32c(g_y)
+        if g_xenc is None and g_y is None:
+            return (None,) * 5
+        g_y = torch.zeros_like(x_enc) if g_y is None else _f32c(g_y)
+        g_xenc = None if g_xenc is None else _f32c(g_xenc)
         dpre = _linear_act_tc(g_y, we, None, ctx.slope, w_transposed=True, addend=g_xenc, act_src=x_enc)
         h, f_in = wn.shape
         zbuf = torch.zeros(h * h + h * f_in + h, dtype=torch.float32, device=x.device)   # one fill for both GEMMs

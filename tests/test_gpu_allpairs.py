@@ -20,7 +20,8 @@ def _dense_scores(z, t, G):
 
 
 @pytest.mark.parametrize("n,d,kc,noise", [(300, 64, 16, True), (1000, 64, 32, True), (777, 32, 8, False),
-                                          (2100, 64, 24, True), (130, 128, 16, True), (500, 16, 12, True)])
+                                          (2100, 64, 24, True), (130, 128, 16, True), (500, 16, 12, True),
+                                          (1500, 128, 32, True), (700, 96, 20, False), (640, 128, 8, False)])
 def test_topk_matches_dense_sort(n, d, kc, noise):
     from dgg_b200 import functional as K
 
@@ -33,7 +34,7 @@ def test_topk_matches_dense_sort(n, d, kc, noise):
         G = 0.3 * -torch.log(-torch.log(u))
     y, dist = _dense_scores(z, t, G)
     srt, order = torch.sort(y, dim=-1, descending=True, stable=True)
-    prec = 1 if d == 128 else 3
+    prec = 1 if (d == 128 and n == 130) else 3      # one single-pass TF32 case, everything else 3xTF32
     idx, val = K.allpairs_topk(z.cuda(), t.cuda(), None if G is None else G.cuda(), kc, prec)
     idx, val = idx.cpu().long(), val.cpu()
     # Value tolerance: y = -t*D + G with D = sqrt(d2) and d2 = |zi|^2+|zj|^2-2<zi,zj> carrying an absolute
