@@ -345,6 +345,11 @@ def gemm_tn(a, b, want_colsum=False, use_tc=None, zeroed=None):
     a, b = _f32c(a), _f32c(b)
     n, pp = a.shape
     q = b.shape[1]
+    if q % 4 != 0 and q < 64 and pp % 4 == 0 and zeroed is None:
+        # narrow right operand (e.g. the 3 class logits): the kernel's 16-byte staging path needs q % 4 == 0;
+        # padding N x q to N x 4 costs one small copy, the scalar staging path costs 3x the whole GEMM
+        out, cs = gemm_tn(a, torch.nn.functional.pad(b, (0, 4 - q % 4)), want_colsum, use_tc)
+        return out[:, :q].contiguous(), cs
     need = pp * q + (pp if want_colsum else 0)
     buf = zeroed if zeroed is not None else torch.zeros(need, dtype=torch.float32, device=a.device)
     assert buf.numel() == need
