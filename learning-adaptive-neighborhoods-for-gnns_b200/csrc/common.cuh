@@ -87,6 +87,16 @@ __host__ __device__ inline int pow2_floor32(int v) {
   return p;
 }
 
+// resident blocks per SM of a kernel (registers / shared memory decide, not the 2048-thread limit alone): the
+// grid-stride kernels size their grid to ONE wave with it.  A grid sized for 8 blocks/SM with a 40-register kernel
+// (6 resident) runs a second, mostly idle wave and doubles a latency-bound launch.
+template <typename K>
+inline int resident_blocks(K kernel, int threads, size_t smem = 0) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
+}
+
 // warp-per-row grids: rows are dealt to warps round-robin from a persistent grid
 inline int rows_grid(int n_rows, int warps_per_block, int blocks_per_sm) {
   long long need = ((long long)n_rows + warps_per_block - 1) / warps_per_block;

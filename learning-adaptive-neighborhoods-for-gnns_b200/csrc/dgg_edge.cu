@@ -704,9 +704,9 @@ static int dispatch_T(int h, int L, F&& f) {
   return DGGB_ERR_BAD_SHAPE;
 }
 
-static int edges_grid(long long nnz) {
+static int edges_grid(long long nnz, int blocks_per_sm = 8) {
   long long need = (nnz + kEdgeWarps * kWarp - 1) / (kEdgeWarps * kWarp);
-  long long cap = (long long)kNumSMs * 8;
+  long long cap = (long long)kNumSMs * blocks_per_sm;
   long long g = need < cap ? need : cap;
   return (int)(g < 1 ? 1 : g);
 }
@@ -729,13 +729,13 @@ extern "C" int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow, con
   if (nnz > 0) {
     st = dispatch_T(h, L, [&](auto tc) {
       constexpr int T = decltype(tc)::value;
-      launch_pdl(dgg_edge_score_kernel<T>, dim3(edges_grid(nnz)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
+      launch_pdl(dgg_edge_score_kernel<T>, dim3(edges_grid(nnz, resident_blocks(dgg_edge_score_kernel<T>, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
           erow, col, nnz, h, L, y, be, ablation_noise, R);
       return launch_status();
     });
     if (st != DGGB_OK) return st;
   }
-  launch_pdl(dgg_row_rank_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
+  launch_pdl(dgg_row_rank_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(dgg_row_rank_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
       rowptr, n, R, deg_w, deg_b, hard_k, rank, s, k, out);
   return launch_status();
 }
@@ -752,14 +752,14 @@ extern "C" int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, con
   if (n == 0 || nnz == 0) return DGGB_OK;
   const int L = lanes_per_edge(h);
   if (hard_k < 0) {
-    launch_pdl(dgg_row_dk_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
+    launch_pdl(dgg_row_dk_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(dgg_row_dk_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
         rowptr, n, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, ddeg);
     const int st = launch_status();
     if (st != DGGB_OK) return st;
   }
   return dispatch_T(h, L, [&](auto tc) {
     constexpr int T = decltype(tc)::value;
-    launch_pdl(dgg_edge_grad_kernel<T>, dim3(edges_grid(nnz)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
+    launch_pdl(dgg_edge_grad_kernel<T>, dim3(edges_grid(nnz, resident_blocks(dgg_edge_grad_kernel<T>, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
         erow, col, nnz, h, L, y, be, ablation_noise, hard_k, R, rank, k, ds_ws, g_out, dy, dbe);
     return launch_status();
   });
@@ -769,7 +769,7 @@ extern "C" int dggb_row_firstk_fwd(const int32_t* rowptr, int32_t n, const float
                                    int32_t* rank, float* out, void* stream) {
   if (!rowptr || !score || !k || !rank || !out || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
-  launch_pdl(row_firstk_fwd_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), rowptr, n, score,
+  launch_pdl(row_firstk_fwd_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(row_firstk_fwd_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), rowptr, n, score,
                                                                                                  k, rank, out);
   return launch_status();
 }
@@ -779,7 +779,7 @@ extern "C" int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float
                                    void* stream) {
   if (!rowptr || !score || !k || !rank || !g_out || !dscore || !dk || n < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
-  launch_pdl(row_firstk_bwd_kernel, dim3(rows_grid(n, kEdgeWarps, 8)), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
+  launch_pdl(row_firstk_bwd_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(row_firstk_bwd_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
       rowptr, n, score, k, rank, g_out, dscore, dk);
   return launch_status();
 }

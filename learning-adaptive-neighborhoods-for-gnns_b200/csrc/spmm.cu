@@ -54,6 +54,8 @@ template <> struct Vec<1> {
 // Both kernels first pull a 32-entry window of the row's (col, val) pairs into registers with one coalesced
 // load per lane and then broadcast them with shuffles: the neighbour-row gathers no longer wait on a dependent
 // index load, and several of them are in flight per group (unroll 4).
+// (Tried and measured slower at Pubmed shape, model-step graph replay 0.371 -> 0.396 / 0.470 ms: one row per L-lane
+// group with the entries read sequentially, with and without a per-warp shared-memory entry window.)
 template <int VEC, int T>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -80,7 +82,8 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         for (int j0 = 0; j0 < cnt; j0 += G) {
           const int j = j0 + grp;                       // j >= cnt: a_l of that lane is 0 => contributes nothing
           const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
-          const float a = (j < cnt) ? __shfl_sync(0xffffffffu, a_l, j & 31) : 0.f * __shfl_sync(0xffffffffu, a_l, j & 31);
+          float a = __shfl_sync(0xffffffffu, a_l, j & 31);   // shuffles stay outside any lane-dependent condition
+          if (j >= cnt) a = 0.f;
           const float* xr = x + (size_t)v * f;
 #pragma unroll
           for (int t = 0; t < T; ++t) {
@@ -137,7 +140,6 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         const int c_l = (e_l < end) ? __ldg(col + e_l) : 0;
         const float a_l = (e_l < end) ? __ldg(val + e_l) : 0.f;
         const int cnt = min(kWarp, end - w0);
-        float dot_l = 0.f;                              // lane j keeps the SDDMM value of entry w0 + j
 #pragma unroll 2
         for (int j0 = 0; j0 < cnt; j0 += G) {
           const int j = j0 + grp;
@@ -159,15 +161,10 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
           }
           if (dval) {
             dot = group_sum(dot, L);
-            // hand the group's result to lane j (each group leader holds one entry of this step)
-#pragma unroll 1
-            for (int gg = 0; gg < G; ++gg) {
-              const float dv = __shfl_sync(0xffffffffu, dot, gg * L);
-              if (lane == j0 + gg) dot_l = dv;
-            }
+            // the G group leaders hold G consecutive entries of the row: one coalesced store
+            if (lg == 0 && valid) dval[w0 + j] = (f0 == 0) ? dot : dval[w0 + j] + dot;
           }
         }
-        if (dval && e_l < end) dval[e_l] = (f0 == 0) ? dot_l : dval[e_l] + dot_l;   // coalesced
       }
     }
   }
@@ -178,9 +175,12 @@ static int dispatch_vec(int f, Fn&& fn) {
   // pick the widest vector the row stride allows, then lanes-per-row L and chunks-per-lane T
   const int vec = (f % 4 == 0) ? 4 : (f % 2 == 0 ? 2 : 1);
   const int chunks = (f + vec - 1) / vec;
-  const int L = pow2_floor32(chunks);
+  // up to 4 chunks per lane: F = 64 -> 4 lanes per neighbour row, 8 neighbour rows in flight per warp instruction
+  // (a 150-entry hub row is 19 iterations instead of 76; the average 6-entry row is one)
+  int L = 1;
+  while (L < 32 && 4 * L < chunks) L *= 2;
   int T = (chunks + L - 1) / L;
-  T = T >= 4 ? 4 : (T >= 2 ? 2 : 1);
+  T = T > 2 ? 4 : (T >= 2 ? 2 : 1);
   if (vec == 4) {
     if (T == 1) return fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{}, L);
     if (T == 2) return fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{}, L);
@@ -203,9 +203,10 @@ extern "C" int dggb_spmm_csr_fwd(const int32_t* rowptr, const int32_t* col, cons
                                  const float* x, int32_t f, const float* row_scale, float* y, void* stream) {
   if (!rowptr || !col || !val || !x || !y || n < 0 || f <= 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
-  const int grid = rows_grid(n, kSpmmWarps, 8);
   return dispatch_vec(f, [&](auto vc, auto tc, int L) {
-    launch_pdl((spmm_fwd_kernel<decltype(vc)::value, decltype(tc)::value>), dim3(grid), dim3(kSpmmWarps * kWarp), 0,
+    auto kern = spmm_fwd_kernel<decltype(vc)::value, decltype(tc)::value>;
+    const int grid = rows_grid(n, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp));
+    launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), 0,
                as_stream(stream), rowptr, col, val, n, x, f, L, row_scale, y);
     return launch_status();
   });
@@ -216,9 +217,10 @@ extern "C" int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, cons
                                  float* dx, void* stream) {
   if (!rowptr || !col || !val || !x || !dy || n < 0 || f <= 0) return DGGB_ERR_BAD_ARG;
   if (n == 0 || (!dval && !dx)) return DGGB_OK;
-  const int grid = rows_grid(n, kSpmmWarps, 8);
   return dispatch_vec(f, [&](auto vc, auto tc, int L) {
-    launch_pdl((spmm_bwd_kernel<decltype(vc)::value, decltype(tc)::value>), dim3(grid), dim3(kSpmmWarps * kWarp), 0,
+    auto kern = spmm_bwd_kernel<decltype(vc)::value, decltype(tc)::value>;
+    const int grid = rows_grid(n, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp));
+    launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), 0,
                as_stream(stream), rowptr, col, val, n, x, f, L, row_scale, dy, dval, dx);
     return launch_status();
   });

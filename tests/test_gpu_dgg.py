@@ -208,7 +208,8 @@ def test_model_gcn_dgg_00_matches_reference_golden(golden):
 
 
 @pytest.mark.parametrize("n,p,q", [(19717, 64, 500), (1000, 64, 64), (333, 16, 30), (5000, 128, 602), (40, 24, 7),
-                                   (4500, 32, 128), (6001, 128, 600)])
+                                   (4500, 32, 128), (6001, 128, 600), (19717, 64, 3), (5000, 64, 4), (3000, 100, 16),
+                                   (2500, 64, 40), (900, 7, 13)])
 def test_gemm_tn_splitk(n, p, q):
     """dW = a^T b and db = colsum(a) vs torch (fp32; split-K sums in a different order: rtol 1e-4)."""
     from dgg_b200 import functional as K
