@@ -413,7 +413,10 @@ __device__ __forceinline__ void fused_row_range(const int32_t* __restrict__ rowp
   __syncthreads();
 }
 
-template <int T>
+// LC > 0: lanes per edge and the hidden width (h == 16 * LC, T == 4) are compile-time constants, which folds every
+// `chunk < h` guard, the zero fills of out-of-range chunks and the per-chunk address arithmetic (static SASS of the
+// runtime-L version: ~270 instructions per edge slot, a third of them guards / CS2R / IMAD).
+template <int T, int LC>
 __global__ void __launch_bounds__(kFusedThreads)
     dgg_fwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
                          const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb, int cap,
@@ -422,6 +425,10 @@ __global__ void __launch_bounds__(kFusedThreads)
                          const float* __restrict__ deg_b, int hard_k, float* R, int32_t* __restrict__ rank,
                          float* __restrict__ s_out, float* __restrict__ k_out, float* __restrict__ out) {
   pdl_trigger();
+  if constexpr (LC > 0) {
+    L = LC;
+    h = 16 * LC;
+  }
   extern __shared__ float sR[];          // [cap] scores of this block's edge range
   __shared__ int rng[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -525,7 +532,7 @@ __global__ void __launch_bounds__(kFusedThreads)
   }
 }
 
-template <int T>
+template <int T, int LC>
 __global__ void __launch_bounds__(kFusedThreads)
     dgg_bwd_fused_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
                          const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb,
@@ -536,6 +543,10 @@ __global__ void __launch_bounds__(kFusedThreads)
                          const float* __restrict__ deg_w, const float* __restrict__ deg_b, float* ds_ws,
                          float* __restrict__ dy, float* __restrict__ dbe, float* __restrict__ ddeg) {
   pdl_trigger();
+  if constexpr (LC > 0) {
+    L = LC;
+    h = 16 * LC;
+  }
   __shared__ float sds[kFusedRowsCap];
   __shared__ float dbe_s[512];           // block-level bias-gradient accumulator (h <= 512)
   __shared__ float red[2][kFusedThreads / kWarp];
@@ -796,20 +807,29 @@ extern "C" int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* ero
   if (nnz == 0 || max_row_nnz > kFusedMaxDeg) return DGGB_ERR_UNSUPPORTED;   // use the two-launch entry point
   if (n == 0) return DGGB_OK;
   const int L = lanes_per_edge(h);
-  return dispatch_T(h, L, [&](auto tc) {
-    constexpr int T = decltype(tc)::value;
+  auto go = [&](auto kern) {
     int occ = 0, blocks, epb;
     // the shared-memory slice depends on epb, which depends on the occupancy: size it for the smallest grid first
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgg_fwd_fused_kernel<T>, kFusedThreads,
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads,
                                                   (size_t)(256 + max_row_nnz) * sizeof(float));
     fused_grid(nnz, occ, &blocks, &epb);
     const int cap = epb + max_row_nnz;
     if ((size_t)cap * sizeof(float) > 48 * 1024) return (int)DGGB_ERR_UNSUPPORTED;
-    launch_pdl(dgg_fwd_fused_kernel<T>, dim3(blocks), dim3(kFusedThreads), (size_t)cap * sizeof(float),
-               as_stream(stream), rowptr, erow, col, n, nnz, h, L, epb, cap, y, be, ablation_noise, deg_w, deg_b,
-               hard_k, R, rank, s, k, out);
+    launch_pdl(kern, dim3(blocks), dim3(kFusedThreads), (size_t)cap * sizeof(float), as_stream(stream), rowptr, erow,
+               col, n, nnz, h, L, epb, cap, y, be, ablation_noise, deg_w, deg_b, hard_k, R, rank, s, k, out);
     return launch_status();
-  });
+  };
+  if (h == 16 * L) {   // the usual hidden widths: fully specialised kernels
+    switch (L) {
+      case 1: return go(dgg_fwd_fused_kernel<4, 1>);
+      case 2: return go(dgg_fwd_fused_kernel<4, 2>);
+      case 4: return go(dgg_fwd_fused_kernel<4, 4>);
+      case 8: return go(dgg_fwd_fused_kernel<4, 8>);
+      case 16: return go(dgg_fwd_fused_kernel<4, 16>);
+      default: return go(dgg_fwd_fused_kernel<4, 32>);
+    }
+  }
+  return dispatch_T(h, L, [&](auto tc) { return go(dgg_fwd_fused_kernel<decltype(tc)::value, 0>); });
 }
 
 extern "C" int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
@@ -825,14 +845,23 @@ extern "C" int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* ero
   if (nnz == 0 || max_row_nnz > kFusedMaxDeg) return DGGB_ERR_UNSUPPORTED;
   if (n == 0) return DGGB_OK;
   const int L = lanes_per_edge(h);
-  return dispatch_T(h, L, [&](auto tc) {
-    constexpr int T = decltype(tc)::value;
+  auto go = [&](auto kern) {
     int occ = 0, blocks, epb;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dgg_bwd_fused_kernel<T>, kFusedThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads, 0);
     fused_grid(nnz, occ, &blocks, &epb);
-    launch_pdl(dgg_bwd_fused_kernel<T>, dim3(blocks), dim3(kFusedThreads), 0, as_stream(stream), rowptr, erow, col, n,
-               nnz, h, L, epb, y, be, ablation_noise, hard_k, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, dy, dbe,
-               ddeg);
+    launch_pdl(kern, dim3(blocks), dim3(kFusedThreads), 0, as_stream(stream), rowptr, erow, col, n, nnz, h, L, epb, y,
+               be, ablation_noise, hard_k, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, dy, dbe, ddeg);
     return launch_status();
-  });
+  };
+  if (h == 16 * L) {
+    switch (L) {
+      case 1: return go(dgg_bwd_fused_kernel<4, 1>);
+      case 2: return go(dgg_bwd_fused_kernel<4, 2>);
+      case 4: return go(dgg_bwd_fused_kernel<4, 4>);
+      case 8: return go(dgg_bwd_fused_kernel<4, 8>);
+      case 16: return go(dgg_bwd_fused_kernel<4, 16>);
+      default: return go(dgg_bwd_fused_kernel<4, 32>);
+    }
+  }
+  return dispatch_T(h, L, [&](auto tc) { return go(dgg_bwd_fused_kernel<decltype(tc)::value, 0>); });
 }

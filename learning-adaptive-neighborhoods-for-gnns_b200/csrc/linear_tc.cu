@@ -18,17 +18,26 @@ constexpr int kLinThreads = 192;
 
 using tc::tf32_rna;
 
-// W -> (hi, lo) TF32 split, once per call (W is tiny: H x F)
+// W -> (hi, lo) TF32 split, once per call (W is tiny: H x F); the chained GEMM's W2 is split by the same launch
 // (transposed: w is given as [F, H] and the kernel needs W_eff[h][f] = w[f][h])
 __global__ void split_w_kernel(const float* __restrict__ w, int count, int h, int f, int transposed,
-                               float* __restrict__ hi, float* __restrict__ lo) {
+                               float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w2, int count2,
+                               float* __restrict__ hi2, float* __restrict__ lo2) {
   pdl_trigger();
   pdl_wait();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const float v = transposed ? __ldg(w + (size_t)(i % f) * h + (i / f)) : __ldg(w + i);
-    const float h = tf32_rna(v);
-    hi[i] = h;
-    lo[i] = tf32_rna(v - h);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count + count2; i += gridDim.x * blockDim.x) {
+    if (i < count) {
+      const float v = transposed ? __ldg(w + (size_t)(i % f) * h + (i / f)) : __ldg(w + i);
+      const float hh = tf32_rna(v);
+      hi[i] = hh;
+      lo[i] = tf32_rna(v - hh);
+    } else {
+      const int k = i - count;
+      const float v = __ldg(w2 + k);
+      const float hh = tf32_rna(v);
+      hi2[k] = hh;
+      lo2[k] = tf32_rna(v - hh);
+    }
   }
 }
 
@@ -370,7 +379,12 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   constexpr int XS = DGGB_LIN_XS, WS = DGGB_LIN_WS;   // H <= 64: 64 KB + 3 x 2H x 128 B <= 112 KB so that two CTAs share an SM
   float* w_hi = ws;               // [W_hi ; W_lo] stacked: one [2H, F] matrix, one tensor map
   float* w_lo = ws + (size_t)H * f;
-  launch_pdl(split_w_kernel, dim3((H * f + 255) / 256), dim3(256), 0, st, w, H * f, H, f, w_transposed, w_hi, w_lo);
+  const bool chained = (H == 32 || H == 64) && w2 != nullptr;
+  float* w2_hi = ws + (size_t)2 * H * f;
+  float* w2_lo = w2_hi + (size_t)H * H;
+  const int n_split = H * f + (chained ? H * H : 0);
+  launch_pdl(split_w_kernel, dim3((n_split + 255) / 256), dim3(256), 0, st, w, H * f, H, f, w_transposed, w_hi, w_lo,
+             chained ? w2 : static_cast<const float*>(nullptr), chained ? H * H : 0, w2_hi, w2_lo);
   int rc = launch_status();
   if (rc != DGGB_OK) return rc;
   CUtensorMap tm_x, tm_w, tm_w2hi, tm_w2lo;
@@ -382,11 +396,6 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   const int grid = (n + kLinBM - 1) / kLinBM;
   if constexpr (H == 32 || H == 64) {
     if (w2 != nullptr) {
-      float* w2_hi = ws + (size_t)2 * H * f;
-      float* w2_lo = w2_hi + (size_t)H * H;
-      launch_pdl(split_w_kernel, dim3((H * H + 255) / 256), dim3(256), 0, st, w2, H * H, H, H, 0, w2_hi, w2_lo);
-      rc = launch_status();
-      if (rc != DGGB_OK) return rc;
       rc = make_tmap_2d_f32(&tm_w2hi, w2_hi, (uint64_t)H, (uint64_t)H, H, 32);
       if (rc != DGGB_OK) return rc;
       rc = make_tmap_2d_f32(&tm_w2lo, w2_lo, (uint64_t)H, (uint64_t)H, H, 32);
