@@ -460,6 +460,8 @@ def full_model_epoch(dsets, shape, dev, iters=20):
 def kernel_roofline(m, dsets, shape, iters=30):
     """Time each hand-written kernel of the step alone (CUDA events on the launch stream, rotating
     input sets) and report the dominant one against the measured HBM peak."""
+    import ctypes
+
     import torch.nn.functional as F
 
     from dgg_b200 import CSRGraph
@@ -514,7 +516,8 @@ def kernel_roofline(m, dsets, shape, iters=30):
         if fused:
             check(lib().dggb_dgg_edge_fwd_fused(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz),
                                                 i32(g.max_row_nnz), i32(h), p(y), p(be), p(dw), p(db), p(None),
-                                                i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out), stream()), "fwd")
+                                                i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out), p(None),
+                                                ctypes.c_int64(0), stream()), "fwd")
             return
         check(lib().dggb_dgg_edge_fwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
                                       p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out),
@@ -536,7 +539,6 @@ def kernel_roofline(m, dsets, shape, iters=30):
     t_bwd = timed(bwd)
 
     # the two tensor-core GEMM kernels of the node encoder (forward, weight gradient), outputs preallocated
-    import ctypes
     f_in = shape["f"]
     enc = m.node_encoder[0]
     w_enc, b_enc = enc.weight.detach().contiguous(), enc.bias.detach().contiguous()

@@ -112,7 +112,9 @@ int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* erow, const in
                             int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
                             const float* deg_w, const float* deg_b, const float* ablation_noise,
                             int32_t hard_k, float* R, int32_t* rank, float* s, float* k, float* out,
-                            void* stream);
+                            float* zero_ws /* or NULL: zero_count floats cleared by this launch (the
+                                              backward's dy|dbe|ddeg|ds buffer), saving a fill launch */,
+                            int64_t zero_count, void* stream);
 int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
                             int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
                             const float* deg_w, const float* deg_b, const float* ablation_noise,
@@ -182,7 +184,10 @@ int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, cons
                       const float* addend /* [N,H] */, const float* act_src /* [N,H] */, float slope,
                       int32_t n, int32_t f, int32_t h, float* out,
                       const float* w2 /* [H,H] or NULL */, float* out2 /* [N,H] or NULL */,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      void* workspace, int64_t workspace_bytes,
+                      float* zero_ws /* or NULL: zero_count floats cleared before the GEMM starts (the
+                                        split-K buffers of the weight gradients that follow) */,
+                      int64_t zero_count, void* stream);
 int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
                         int32_t f, int32_t h, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);

@@ -35,6 +35,19 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // path is a chain of ~10-30 us kernels: without this ~2 us of launch latency is exposed at every boundary.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// grid-stride zero fill of a scratch buffer the NEXT kernels accumulate into (gradient buffers): folded into a kernel
+// that runs anyway, instead of a separate fill launch that would also break the dependent-launch chain
+__device__ __forceinline__ void zero_fill(float* p, long long count) {
+  if (p == nullptr) return;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const long long n4 = count >> 2;
+    for (long long i = tid; i < n4; i += nth) reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = (n4 << 2) + tid; i < count; i += nth) p[i] = 0.f;
+  } else {
+    for (long long i = tid; i < count; i += nth) p[i] = 0.f;
+  }
+}
 bool pdl_enabled();   // false when DGGB_NO_PDL is set in the environment (A/B measurements)
 
 template <typename... Params, typename... Args>

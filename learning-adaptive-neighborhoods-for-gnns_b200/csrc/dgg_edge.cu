@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(kFusedThreads)
                          const float* __restrict__ y, const float* __restrict__ be,
                          const float* __restrict__ abl_noise, const float* __restrict__ deg_w,
                          const float* __restrict__ deg_b, int hard_k, float* R, int32_t* __restrict__ rank,
-                         float* __restrict__ s_out, float* __restrict__ k_out, float* __restrict__ out) {
+                         float* __restrict__ s_out, float* __restrict__ k_out, float* __restrict__ out,
+                         float* zero_ws, long long zero_count) {
   pdl_trigger();
   if constexpr (LC > 0) {
     L = LC;
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(kFusedThreads)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = kWarp / L, lg = lane % L, grp = lane / L;
   pdl_wait();
+  zero_fill(zero_ws, zero_count);   // the backward's accumulation buffers (dy | dbe | ddeg | ds)
   fused_row_range(rowptr, erow, n, nnz, epb, rng);
   const int r0 = rng[0], r1 = rng[1], eb0 = rng[2], eb1 = rng[3];
   const int nE = eb1 - eb0;
@@ -799,9 +801,9 @@ extern "C" int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* ero
                                        int32_t nnz, int32_t max_row_nnz, int32_t h, const float* y, const float* be,
                                        const float* deg_w, const float* deg_b, const float* ablation_noise,
                                        int32_t hard_k, float* R, int32_t* rank, float* s, float* k, float* out,
-                                       void* stream) {
+                                       float* zero_ws, int64_t zero_count, void* stream) {
   if (!rowptr || !erow || !col || !y || !be || !deg_w || !deg_b || !R || !rank || !s || !k || !out || n < 0 ||
-      nnz < 0 || h <= 0 || max_row_nnz < 0)
+      nnz < 0 || h <= 0 || max_row_nnz < 0 || zero_count < 0)
     return DGGB_ERR_BAD_ARG;
   if (h % 4 != 0 || h > 512) return DGGB_ERR_BAD_SHAPE;
   if (nnz == 0 || max_row_nnz > kFusedMaxDeg) return DGGB_ERR_UNSUPPORTED;   // use the two-launch entry point
@@ -816,7 +818,8 @@ extern "C" int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* ero
     const int cap = epb + max_row_nnz;
     if ((size_t)cap * sizeof(float) > 48 * 1024) return (int)DGGB_ERR_UNSUPPORTED;
     launch_pdl(kern, dim3(blocks), dim3(kFusedThreads), (size_t)cap * sizeof(float), as_stream(stream), rowptr, erow,
-               col, n, nnz, h, L, epb, cap, y, be, ablation_noise, deg_w, deg_b, hard_k, R, rank, s, k, out);
+               col, n, nnz, h, L, epb, cap, y, be, ablation_noise, deg_w, deg_b, hard_k, R, rank, s, k, out, zero_ws,
+               (long long)zero_count);
     return launch_status();
   };
   if (h == 16 * L) {   // the usual hidden widths: fully specialised kernels

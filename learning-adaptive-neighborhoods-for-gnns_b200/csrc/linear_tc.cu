@@ -22,9 +22,10 @@ using tc::tf32_rna;
 // (transposed: w is given as [F, H] and the kernel needs W_eff[h][f] = w[f][h])
 __global__ void split_w_kernel(const float* __restrict__ w, int count, int h, int f, int transposed,
                                float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w2, int count2,
-                               float* __restrict__ hi2, float* __restrict__ lo2) {
+                               float* __restrict__ hi2, float* __restrict__ lo2, float* zero_ws, long long zero_count) {
   pdl_trigger();
   pdl_wait();
+  zero_fill(zero_ws, zero_count);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count + count2; i += gridDim.x * blockDim.x) {
     if (i < count) {
       const float v = transposed ? __ldg(w + (size_t)(i % f) * h + (i / f)) : __ldg(w + i);
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 template <int H>
 static int launch_linear(const float* x, const float* w, int w_transposed, const float* b, const float* addend,
                          const float* act_src, float slope, int n, int f, float* out, float* ws, const float* w2,
-                         float* out2, cudaStream_t st) {
+                         float* out2, float* zero_ws, long long zero_count, cudaStream_t st) {
 #ifndef DGGB_LIN_XS
 #define DGGB_LIN_XS 4
 #define DGGB_LIN_WS 3
@@ -384,7 +385,7 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   float* w2_lo = w2_hi + (size_t)H * H;
   const int n_split = H * f + (chained ? H * H : 0);
   launch_pdl(split_w_kernel, dim3((n_split + 255) / 256), dim3(256), 0, st, w, H * f, H, f, w_transposed, w_hi, w_lo,
-             chained ? w2 : static_cast<const float*>(nullptr), chained ? H * H : 0, w2_hi, w2_lo);
+             chained ? w2 : static_cast<const float*>(nullptr), chained ? H * H : 0, w2_hi, w2_lo, zero_ws, zero_count);
   int rc = launch_status();
   if (rc != DGGB_OK) return rc;
   CUtensorMap tm_x, tm_w, tm_w2hi, tm_w2lo;
@@ -428,8 +429,9 @@ extern "C" int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h) {
 extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
                                  const float* addend, const float* act_src, float slope, int32_t n, int32_t f,
                                  int32_t h, float* out, const float* w2, float* out2, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
-  if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0 || ((w2 == nullptr) != (out2 == nullptr)))
+                                 int64_t workspace_bytes, float* zero_ws, int64_t zero_count, void* stream) {
+  if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0 || ((w2 == nullptr) != (out2 == nullptr)) ||
+      zero_count < 0)
     return DGGB_ERR_BAD_ARG;
   if (workspace_bytes < dggb_linear_act_workspace_bytes(f, h)) return DGGB_ERR_WORKSPACE;
   if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
@@ -442,10 +444,10 @@ extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_trans
   if (n == 0) return DGGB_OK;
   cudaStream_t st = as_stream(stream);
   switch (h) {
-    case 16: return launch_linear<16>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
-    case 32: return launch_linear<32>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
-    case 64: return launch_linear<64>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
-    case 128: return launch_linear<128>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, st);
+    case 16: return launch_linear<16>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
+    case 32: return launch_linear<32>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
+    case 64: return launch_linear<64>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
+    case 128: return launch_linear<128>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
     default: return DGGB_ERR_BAD_SHAPE;
   }
 }
@@ -453,7 +455,7 @@ extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_trans
 extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
                                    int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, nullptr, nullptr, workspace,
-                           workspace_bytes, stream);
+                           workspace_bytes, nullptr, 0, stream);
 }
 
 #ifdef DGGB_LIN_TRACE

@@ -39,15 +39,24 @@ class _DGGEdge(torch.autograd.Function):
         out = torch.empty(E, dtype=torch.float32, device=dev)
         mx = graph.max_row_nnz
         fused = 0 < mx <= _FUSED_MAX_ROW and E > 0   # no hub rows: one launch per direction
+        zbuf = None
         if fused:
+            if any(ctx.needs_input_grad[:4]):
+                # the backward's accumulation buffers (dy | dbe | ddeg (+pad) | ds) are cleared by the forward
+                # launch: no separate fill kernel between the two fused launches of a training step
+                zbuf = torch.empty(n * h + h + 4 + n, dtype=torch.float32, device=dev)
+            import ctypes
             check(lib().dggb_dgg_edge_fwd_fused(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(mx),
                                                 i32(h), p(y), p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R),
-                                                p(rank), p(s), p(k), p(out), stream()), "dgg_edge_fwd_fused")
+                                                p(rank), p(s), p(k), p(out), p(zbuf),
+                                                ctypes.c_int64(0 if zbuf is None else zbuf.numel()), stream()),
+                  "dgg_edge_fwd_fused")
         else:
             check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(h), p(y),
                                           p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k),
                                           p(out), stream()), "dgg_edge_fwd")
         ctx.graph, ctx.hard_k, ctx.fused_mx = graph, hard_k, (mx if fused else -1)
+        ctx.zbuf = zbuf
         ctx.set_materialize_grads(False)   # k / R / rank never carry gradients: no zero tensors for them per step
         ctx.save_for_backward(y, be, deg_w, deg_b, noise, R, rank, s, k)
         ctx.mark_non_differentiable(k, R, rank)
@@ -60,8 +69,11 @@ class _DGGEdge(torch.autograd.Function):
         y, be, deg_w, deg_b, noise, R, rank, s, k = ctx.saved_tensors
         g = ctx.graph
         n, h = y.shape
-        # one zero-filled buffer (one fill launch): dy | dbe | ddeg (+pad) | ds scratch
-        zbuf = torch.zeros(n * h + h + 4 + n, dtype=torch.float32, device=y.device)
+        # one zero-filled buffer: dy | dbe | ddeg (+pad) | ds scratch (already cleared by the fused forward launch;
+        # a second backward through the same node gets a fresh one)
+        zbuf, ctx.zbuf = getattr(ctx, "zbuf", None), None
+        if zbuf is None:
+            zbuf = torch.zeros(n * h + h + 4 + n, dtype=torch.float32, device=y.device)
         dy = zbuf[:n * h].view(n, h)
         small = zbuf[n * h:]
         dbe, ddeg, ds_ws = small[:h], small[h:h + 2], small[h + 4:]
@@ -264,7 +276,7 @@ class _TallLinear(torch.autograd.Function):
         return dx, dw, db, None
 
 
-def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None, w2=None):
+def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None, w2=None, zero=None):
     """out = epi(x W_eff^T + b + addend) through dggb_linear_fused (tcgen05, 3xTF32); None if the shape is
     not supported.  epi = LeakyReLU(slope), or * LeakyReLU'(act_src) when act_src is given (backward form)."""
     import ctypes
@@ -284,7 +296,8 @@ def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None
     w2c = None if w2 is None else w2.contiguous()
     rc = lib().dggb_linear_fused(p(x), p(w), i32(1 if w_transposed else 0), p(bb), p(ad), p(ac),
                                  ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out), p(w2c), p(out2), p(ws),
-                                 ctypes.c_int64(ws.numel() * 4), stream())
+                                 ctypes.c_int64(ws.numel() * 4), p(zero),
+                                 ctypes.c_int64(0 if zero is None else zero.numel()), stream())
     if rc == -2:
         return None
     check(rc, "linear_fused")
@@ -319,9 +332,12 @@ class _EncodeProject(torch.autograd.Function):
             return (None,) * 5
         g_y = torch.zeros_like(x_enc) if g_y is None else _f32c(g_y)
         g_xenc = None if g_xenc is None else _f32c(g_xenc)
-        dpre = _linear_act_tc(g_y, we, None, ctx.slope, w_transposed=True, addend=g_xenc, act_src=x_enc)
         h, f_in = wn.shape
-        zbuf = torch.zeros(h * h + h * f_in + h, dtype=torch.float32, device=x.device)   # one fill for both GEMMs
+        # split-K accumulators of both weight-gradient GEMMs: cleared by the dpre launch (its weight-split kernel)
+        zbuf = torch.empty(h * h + h * f_in + h, dtype=torch.float32, device=x.device)
+        dpre = _linear_act_tc(g_y, we, None, ctx.slope, w_transposed=True, addend=g_xenc, act_src=x_enc, zero=zbuf)
+        if dpre is None:
+            raise RuntimeError("encode_project backward: shape not supported by the tensor-core kernels")
         dwe, _ = gemm_tn(g_y, x_enc, False, zeroed=zbuf[:h * h])
         dwn, dbn = gemm_tn(dpre, x, True, zeroed=zbuf[h * h:])
         dx = dpre @ wn if ctx.needs_input_grad[0] else None
