@@ -2,10 +2,12 @@
 // Replaces dgm.py:1781-1810 (gather u,v -> Linear+LeakyReLU -> sum -> sigmoid -> dense N x N scatter ->
 // row sum -> Linear(1,1) -> N-long row sort -> tanh first-k -> un-sort scatter -> to_sparse).
 //
-// Two launches per direction so that power-law hub rows cannot serialise a warp:
+// Graphs without hub rows (longest row <= 512 entries: Cora, Citeseer, Pubmed): ONE launch per direction, a block
+// owning a contiguous range of rows and their edges (dgg_fwd_fused_kernel / dgg_bwd_fused_kernel below).
+// Graphs with hub rows: two launches per direction so that a power-law hub cannot serialise a warp:
 //   fwd:  edge_score (edge-parallel, perfectly balanced)  ->  row_rank (warp per CSR row)
 //   bwd:  row_dk     (warp per CSR row)                    ->  edge_grad (edge-parallel, vector reds)
-// HBM-bound.  Algorithmic bytes per launch are listed in DESIGN.md ("dgg_edge").
+// Issue/latency-bound at Pubmed size, HBM-bound at scale.  Algorithmic bytes per launch are listed in DESIGN.md.
 #include "common.cuh"
 
 namespace dggb {
