@@ -2,8 +2,9 @@
 //   out[P,Q] += a[N,P]^T b[N,Q],   colsum[P] += sum_n a[n,:]        (N = nodes, huge; P, Q small)
 // replaces the autograd  dW = dpre^T x  /  db = dpre.sum(0)  of nn.Linear (dgm.py:1741-1744, 1778), which
 // cuBLAS runs on a handful of CTAs because the output is tiny and the reduction dimension is N.
-// Grid = (Q tiles of 128) x (node splits): every SM streams its own slab of rows once.
-// fp32 SIMT (exact fp32 products, fp32 accumulate): 64 x 128 output tile per CTA, 8 x 8 per thread.
+// Grid = (Q tiles) x (node splits) x (P tiles): every SM streams its own slab of rows once.
+// fp32 SIMT (exact fp32 products, fp32 accumulate): 64 x QT output tile per CTA (QT = 128 / 64 / 16 by the width of
+// b), 8 x QT/16 per thread.
 // HBM-bound target: N*(P+Q)*4 bytes read once (+ P*Q*4*splits of reductions).
 #include "common.cuh"
 #include <cstdlib>
