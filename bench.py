@@ -120,26 +120,62 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU oracle leg
-def cpu_oracle_fwd_bwd(sets, state, n_sample):
-    """One DGG fwd+bwd of the CPU oracle (dense reference algorithm) on the first n_sample nodes'
-    induced subgraph of set 0.  Returns seconds."""
-    from oracle import dgg_oracle as O
-
-    s = sets[0]
+def induced_sample(s, n_sample):
+    """The first n_sample nodes' induced subgraph of an input set (the whole set when n_sample == N)."""
     idx = s["idx"]
     if n_sample < s["x"].shape[0]:
         keep = (idx[0] < n_sample) & (idx[1] < n_sample)
-        idx = idx[:, keep]
-        g_vals = s["g_vals"][keep]
-    else:
-        g_vals = s["g_vals"]
-    x = s["x"][:n_sample]
+        return dict(idx=idx[:, keep].contiguous(), val=s["val"][keep], x=s["x"][:n_sample],
+                    g_vals=s["g_vals"][keep], g_xenc=s["g_xenc"][:n_sample])
+    return s
+
+
+def cpu_oracle_fwd_bwd(sets, state, n_sample, want_result=False):
+    """One DGG fwd+bwd of the CPU oracle (dense reference algorithm) on the first n_sample nodes'
+    induced subgraph of set 0.  Returns seconds (and, on request, what it computed: the parity leg)."""
+    from oracle import dgg_oracle as O
+
+    s = induced_sample(sets[0], n_sample)
+    idx, g_vals, x = s["idx"], s["g_vals"], s["x"]
     p = {k: v.detach().clone().requires_grad_(True) for k, v in state.items()}
     t0 = time.perf_counter()
     r = O.dgg_forward(x, idx, n_sample, p)
     vals = r["out"][idx[0], idx[1]]
-    torch.autograd.backward([vals, r["x_enc"]], [g_vals, s["g_xenc"][:n_sample]])
-    return time.perf_counter() - t0
+    torch.autograd.backward([vals, r["x_enc"]], [g_vals, s["g_xenc"]])
+    dt = time.perf_counter() - t0
+    if not want_result:
+        return dt
+    return dt, dict(vals=vals.detach(), R=r["R"].detach(), x_enc=r["x_enc"].detach(),
+                    grads={k: v.grad for k, v in p.items()})
+
+
+def parity_vs_oracle(m, host_set, n_sample, ref, dev):
+    """The GPU module on the SAME inputs the cpu_baseline leg just ran the oracle on: what the JSON line's
+    ``parity`` field reports (tests/test_gpu_bench_shapes.py asserts the same quantities)."""
+    from tests.helpers import near_tie_entries, sparse_ranks
+
+    s = induced_sample(host_set, n_sample)
+    idx = s["idx"]
+    for q in m.parameters():
+        q.grad = None
+    adj = torch.sparse_coo_tensor(idx.to(dev), s["val"].to(dev), (n_sample, n_sample), is_coalesced=True)
+    out, x_enc = m(s["x"].to(dev), adj)
+    torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"].to(dev), s["g_xenc"].to(dev)])
+    vals = out._dgg_vals.detach().cpu()
+    near = near_tie_entries(idx, ref["R"], n_sample)
+    rank_ref = sparse_ranks(idx, ref["R"], n_sample)
+    mism = (m.last_rank.cpu().long() != rank_ref) & ~near
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    grads = {k: rel(q.grad.cpu(), ref["grads"][k]) for k, q in m.named_parameters()}
+    return dict(nodes=int(n_sample), edges=int(idx.shape[1]),
+                support_equal=bool(torch.equal(out.coalesce().indices().cpu(), idx)),
+                max_abs=float((vals - ref["vals"])[~near].abs().max()),
+                max_abs_x_enc=float((x_enc.detach().cpu() - ref["x_enc"]).abs().max()),
+                rank_mismatch_rows=int(torch.unique(idx[0][mism]).numel()),
+                near_tie_entries=int(near.sum()),
+                grad_max_rel_err=max(grads.values()),
+                note="near-tie entries (relative score gap <= 1e-5 to a row neighbour) are excluded from max_abs / "
+                     "rank_mismatch_rows; gradients use the full loss, so they include the effect of any swapped pair")
 
 
 def pick_sample(sets, state, budget_s, n_full):
@@ -350,14 +386,16 @@ def run_ours(args, rank, local_rank, world):
 
     roofline = kernel_roofline(m, dsets, shape)
     epoch = full_model_epoch(dsets, shape, dev) if world == 1 else None
-    cpu = None
+    cpu, parity = None, None
     if world == 1:
         torch.set_num_threads(os.cpu_count())
         n_s = pick_sample(host_sets, state, 12.0, shape["n"])
-        t = cpu_oracle_fwd_bwd(host_sets, state, n_s)
+        t, ref = cpu_oracle_fwd_bwd(host_sets, state, n_s, want_result=True)
         cpu = dict(value=n_s / t, unit="nodes/s", cores=os.cpu_count(), kind="port",
                    sample=f"CPU oracle (dense reference algorithm, dgm.py:1758-1815) fwd+bwd on the {n_s}-node "
                           f"induced subgraph of set 0, 1 run, {t:.1f} s")
+        parity = parity_vs_oracle(m, host_sets[0], n_s, ref, dev)
+        del ref
 
     line = dict(metric=METRIC, value=value, unit="nodes/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -370,7 +408,7 @@ def run_ours(args, rank, local_rank, world):
                                          if world > 1 else "single GPU")),
                 e2e=dict(value=e2e_value, unit="nodes/s", ms_per_step=ms_e2e / args.steps,
                          h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h)),
-                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, clocks=clocks, epoch=epoch)
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, parity=parity, clocks=clocks, epoch=epoch)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -521,7 +559,7 @@ def kernel_roofline(m, dsets, shape, iters=30):
             return
         check(lib().dggb_dgg_edge_fwd(p(g.rowptr), p(g.erow), p(g.col), i32(n), i32(g.nnz), i32(h), p(y), p(be),
                                       p(dw), p(db), p(None), i32(-1), p(R), p(rank), p(s_row), p(k_row), p(out),
-                                      stream()), "fwd")
+                                      p(None), stream()), "fwd")
 
     def bwd(i):   # the backward launch(es); R/rank/s/k of the last forward stand in
         g, y, gv = prepared[i % N_SETS]

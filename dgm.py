@@ -54,7 +54,7 @@ class _EdgeRankerBase(nn.Module):
                                     self.node_encoder[1].negative_slope)                       # dgm.py:1778, 1784
         dd = self.degree_decoder[0]
         out_vals, k, R, rank = K.dgg_edge(y, lin.bias, dd.weight, dd.bias, graph, noise, hard_k)
-        self.last_k = k
+        self.last_k, self.last_rank = k, rank
         return graph, out_vals, x_enc
 
 
@@ -118,14 +118,15 @@ class DGG_LearnableK_SDD(nn.Module):
         z = softmax(LeakyReLU(x W + b));  y_ij = -t |z_i - z_j| + G_ij;  r = descending rank in row i;
         k_i = k_net(x_i) + k_bias;        adj_ij = y_ij * sigmoid(hs_start - interval r + (k_i - 1) interval)
 
-    The first-k sigmoid is exactly 0 in fp32 for r > k + 11.96, so only the top ceil(k_max + 12.6)
-    entries per row can be non-zero: they are selected by a fused tcgen05 GEMM + streaming top-K kernel.
+    The first-k sigmoid is exactly 0 in fp32 for r > k + 11.96 (default hs_start / hs_end), so only the top
+    ceil(k_max + k_window) entries per row can be non-zero: they are selected by a fused tcgen05 GEMM + streaming
+    top-K kernel (more than 64 per row: several passes, see ``_select``).
     forward(x [B,N,F] or [N,F], temp, noise) -> (sparse COO adjacency [N,N] (list if B > 1), k [B,N,1]).
     ``noise``: True -> Gumbel(0,1) noise (sampled on device, or the tensor set via ``set_noise``);
     False -> softmax(log_p / temp) scores (evaluation branch, dgm.py:298)."""
 
-    K_WINDOW = 12.6   # fp32 saturation window of sigmoid(2 - 7 (r - k + 1)) (SURVEY 7.3)
-    KC_MAX = 64
+    KC_MAX = 64          # entries per row one selector pass can return (allpairs kernel limit)
+    SIGMOID_ZERO = 88.73  # torch.sigmoid(-x) == 0.0 in fp32 for x > 88.73 (SURVEY 7.3)
 
     def __init__(self, in_dim=32, latent_dim=64, k_bias=1.0, hard=False, self_loops_noise=False, dist_fn="metric",
                  k_net_input="raw", hs_start=2, hs_end=-5, n_agents=None, learn_k_bias=None, args=None):
@@ -133,6 +134,9 @@ class DGG_LearnableK_SDD(nn.Module):
         torch.manual_seed(0)                                  # reference side effect (dgm.py:207)
         if dist_fn != "metric":
             raise NotImplementedError("only dist_fn='metric' is supported (the 'mlp' branch is log_p == 0)")
+        if hard:
+            raise NotImplementedError("hard=True: the reference's straight-through branch (dgm.py:344-346) builds "
+                                      "dense N x N tensors; only the soft adjacency is provided")
         self.in_dim, self.latent_dim = in_dim, latent_dim
         self.hard, self.self_loops_noise = hard, self_loops_noise
         self.dist_fn, self.k_net_input = dist_fn, k_net_input
@@ -142,38 +146,114 @@ class DGG_LearnableK_SDD(nn.Module):
         self.register_buffer("k_bias", torch.tensor(k_bias))
         self.register_buffer("hs_start", torch.tensor(hs_start))
         self.register_buffer("hs_end", torch.tensor(hs_end))
+        # first_k = sigmoid(hs_start - interval * (r - (k - 1))) is exactly 0 once r - (k - 1) exceeds this
+        # (12.96 for the default hs_start = 2, hs_end = -5); 0.64 ranks of safety margin
+        self.k_window = (float(hs_start) + self.SIGMOID_ZERO) / float(hs_start - hs_end) - 1.0 + 0.64
         import argparse
         kargs = args if args is not None else argparse.Namespace(stochastic_k=False)
         self.k_net = LearnableKEncoder(in_dim=in_dim if k_net_input == "raw" else latent_dim,
                                        latent_dim=latent_dim, args=kargs)
         self._noise = None
         self.precision = 3
+        # Per-row window sizing without a device->host sync on every forward: the number of entries a row can need,
+        # ceil(k_max + k_window), is copied to pinned host memory asynchronously and read by the NEXT forward
+        # (k drifts slowly during training); the selector runs with the bucket 16 / 32 / 64 [/ multiples of 64 in
+        # several passes] that covers the last observed need with 25 % headroom.  A step whose rows needed more
+        # than it was given is reported by ``overflowed()`` / raised at the next forward.  ``exact_kc = True``
+        # restores the synchronous, always-exact sizing.
+        self.exact_kc = False
+        self._need_host = None
+        self._need_event = None
+        self._kc_last = None
 
     def set_noise(self, G):
         """Inject the Gumbel tensor [N,N] used by the next forward (parity tests; the reference's
         injection point is ``gumbel_sample``, dgm.py:14)."""
         self._noise = G
 
+    # ------------------------------------------------------------------ window sizing
+    @staticmethod
+    def _bucket(need):
+        for b in (16, 32, 64):
+            if need <= b:
+                return b
+        return 64 * int(math.ceil(need / 64.0))
+
+    def overflowed(self):
+        """True if the previous forward's rows needed more entries than the selector was run with (synchronises)."""
+        if self._need_event is None:
+            return False
+        self._need_event.synchronize()
+        return int(self._need_host.item()) > self._kc_last
+
+    def _pick_kc(self, k, n):
+        need_dev = torch.ceil(k.detach().max() + self.k_window).clamp(min=1.0)
+        capturing = k.is_cuda and torch.cuda.is_current_stream_capturing()
+        if self.exact_kc and not capturing:
+            need = int(need_dev.item())
+            kc = self._bucket(need)
+        else:
+            if self._need_event is None:
+                if capturing:
+                    raise RuntimeError("DGG_LearnableK_SDD: run one eager forward before capturing a CUDA graph")
+                need = int(need_dev.item())                     # first call: one sync to initialise the hint
+                kc = self._bucket(int(math.ceil(need * 1.25)))
+            else:
+                if not capturing:
+                    self._need_event.synchronize()              # completed long ago: the previous step's copy
+                last_need = int(self._need_host.item())
+                if last_need > self._kc_last and not capturing:
+                    kc_was = self._kc_last
+                    self._kc_last = self._bucket(int(math.ceil(last_need * 1.25)))
+                    raise dgg_b200.DggbError(
+                        "DGG_LearnableK_SDD: K overflow (DGGB_ERR_K_OVERFLOW) in the previous forward: a row needed "
+                        "%d entries, the selector ran with %d; the window has been enlarged, re-run the step "
+                        "(or set exact_kc=True)" % (last_need, kc_was))
+                kc = self._bucket(int(math.ceil(last_need * 1.25)))
+            if not capturing:
+                if self._need_host is None:
+                    self._need_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+                    self._need_event = torch.cuda.Event()
+                self._need_host.copy_(need_dev.reshape(1), non_blocking=True)
+                self._need_event.record()
+        kc = min(kc, n)
+        self._kc_last = kc
+        return kc
+
+    def _select(self, z, kc, **kw):
+        """Top-kc of every row, sorted descending; kc > KC_MAX runs ceil(kc / 64) selector passes, each one
+        restricted to the entries that sort strictly after the last one the previous pass returned (the
+        two-pass fallback of SURVEY 7.3 generalised to any k)."""
+        if kc <= self.KC_MAX:
+            return K.allpairs_topk(z, self.t, kc=kc, precision=self.precision, **kw)
+        outs, after = [], None
+        for p0 in range(0, kc, self.KC_MAX):
+            kp = min(self.KC_MAX, kc - p0)
+            res = K.allpairs_topk(z, self.t, kc=kp, precision=self.precision, after=after, **kw)
+            outs.append(res)
+            after = (res[1][:, -1].detach().contiguous(), res[0][:, -1].contiguous())
+        idx = torch.cat([o[0] for o in outs], dim=1)
+        y = torch.cat([o[1] for o in outs], dim=1)
+        if len(outs[0]) == 3:
+            return idx, y, outs[0][2]
+        return idx, y
+
     def _one(self, x, temp, noise):
         n = x.shape[0]
         z = self.input_project(x)
         k = self.k_net(x if self.k_net_input == "raw" else z) + self.k_bias          # [N,1]
-        k_max = float(k.detach().max())
-        kc = int(min(self.KC_MAX, n, max(1.0, math.ceil(k_max + self.K_WINDOW))))
-        if k_max + self.K_WINDOW > self.KC_MAX and n > self.KC_MAX:
-            raise RuntimeError("DGG_LearnableK_SDD: a row needs more than %d selected entries (k_max=%.1f)"
-                               % (self.KC_MAX, k_max))
+        kc = self._pick_kc(k, n)
         if noise:
             if self._noise is not None:
-                idx, y = K.allpairs_topk(z, self.t, self._noise, kc, self.precision)
+                idx, y = self._select(z, kc, noise=self._noise)
             else:   # Gumbel(0,1) generated inside the kernel (counter-based): no N x N noise tensor
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-                idx, y = K.allpairs_topk(z, self.t, None, kc, self.precision, seed=seed, noise_scale=1.0)
+                idx, y = self._select(z, kc, seed=seed, noise_scale=1.0)
         else:
             # evaluation branch (dgm.py:298): edge_prob = softmax(log_p / temp) over ALL columns.  The ordering is
             # that of log_p; the normaliser sum_j exp(log_p_ij / temp) is accumulated by the same streaming pass.
             # Forward only (inference): the normaliser's gradient would touch all N^2 pairs.
-            idx, logp, zsum = K.allpairs_topk(z, self.t, None, kc, self.precision, inv_temp=1.0 / float(temp))
+            idx, logp, zsum = self._select(z, kc, inv_temp=1.0 / float(temp))
             y = (torch.exp(logp / float(temp)) / zsum.unsqueeze(-1)).detach()
         r = torch.arange(kc, device=x.device, dtype=torch.float32).reshape(1, kc)
         first_k = torch.sigmoid(self.hs_start - self.interval * r + (k - 1) * self.interval)   # dgm.py:315-326
@@ -198,7 +278,7 @@ class DGG_LearnableK_debug(nn.Module):
 
     edge net (dgm.py:1596-1727): u-v-dist, u-v-A_uv, u-v-deg, u-v-deg-dist, edge_conv, A_uv
     k net    (dgm.py:1472-1586): pass, learn_normalized_degree, input_deg, gcn-x-deg, x
-    select   (dgm.py:1352-1435): k_times_edge_prob, edge_p-cdf (identity on the edge probabilities)
+    select   (dgm.py:1352-1435): k_times_edge_prob, k_only, edge_p-cdf (identity on the edge probabilities)
 
     The dense [N,N] scatter / sort / un-sort of the reference is replaced by in-row ranking on the CSR
     support (off-support entries are exact zeros that sort last).  Entries whose soft first-k weight
@@ -206,7 +286,10 @@ class DGG_LearnableK_debug(nn.Module):
     gradients are identical to the reference, which drops them in ``to_sparse()``).
     ``perturb_edge_prob=True`` (Gumbel noise on all N^2 entries) is evaluated exactly on the union of each
     row's edges and its best off-support entries (see ``_perturb``).
-    Not covered: ``k_only`` and ``dgg_hard`` (nondeterministic / buggy in the reference) -- they raise."""
+    ``k_only`` spills a row's window past its degree into its first non-edge columns (``_k_only_spill``).
+    Not covered: ``dgg_hard`` (buggy scatter in the reference) -- it raises."""
+
+    TANH_WINDOW = 8.47   # 1 - 0.5 (1 + tanh(z)) == 0.0 in fp32 for z >= 8.4616 (SURVEY A.2)
 
     def __init__(self, in_dim=32, latent_dim=64, args=None):
         super().__init__()
@@ -264,12 +347,15 @@ class DGG_LearnableK_debug(nn.Module):
         k = self.k_estimate_net(n, graph, vals, x, edge_p, mode=self.k_net_mode)           # [N,1] or None
         pert = edge_p
         if self.args.perturb_edge_prob:
-            if self.args.debug_step == 1 or self.k_select_mode != "k_times_edge_prob":
-                raise NotImplementedError("perturb_edge_prob is covered for debug_step=3 / k_times_edge_prob only")
+            if self.args.debug_step == 1 or self.k_select_mode not in ("k_times_edge_prob", "k_only"):
+                raise NotImplementedError("perturb_edge_prob is covered for debug_step=3 with k_times_edge_prob / "
+                                          "k_only")
             graph, vals, pert = self._perturb(graph, vals, edge_p, k, n)
         elif self.args.debug_step == 1:
             return self.return_hard_or_soft(graph, pert)
         out = self.select_top_k(graph, k, pert, mode=self.k_select_mode, writer=writer, epoch=epoch)
+        if self.k_select_mode == "k_only" and not self.args.perturb_edge_prob:
+            graph, vals, out = self._k_only_spill(graph, vals, out, k, n)
         if writer is not None:
             self.get_adj_diff_stats(graph, vals, out, k, writer=writer, epoch=epoch)
         self.last_k = k
@@ -302,14 +388,17 @@ class DGG_LearnableK_debug(nn.Module):
         idx = graph.coo_indices()
         g_edge = G[idx[0], idx[1]]
         pert_edge = torch.exp(torch.log(edge_p + 1e-8) + g_edge)                               # 1213-1229
-        w = int(math.ceil(float(k.detach().max()) + 8.47)) + 1
-        if w > 64 and n > 64:
-            raise RuntimeError("perturb_edge_prob: window %d exceeds the selector's 64 entries per row" % w)
-        w = min(w, n)
-        masked = G.clone()
-        masked[idx[0], idx[1]] = float("-inf")
+        w = min(int(math.ceil(float(k.detach().max()) + self.TANH_WINDOW)) + 1, n)   # output size is data-dependent
+        G[idx[0], idx[1]] = float("-inf")          # mask the edge positions in place (restored below): one N x N
         zero = torch.zeros(n, 32, device=dev)
-        sel_idx, sel_g = K.allpairs_topk(zero, torch.zeros(1, device=dev), masked, w, 1)
+        tz = torch.zeros(1, device=dev)
+        sel, after = [], None
+        for p0 in range(0, w, 64):                  # > 64 best non-edges per row: continuation passes
+            si, sg = K.allpairs_topk(zero, tz, G, min(64, w - p0), 1, after=after)
+            sel.append((si, sg))
+            after = (sg[:, -1].contiguous(), si[:, -1].contiguous())
+        sel_idx, sel_g = torch.cat([a for a, _ in sel], 1), torch.cat([b for _, b in sel], 1)
+        G[idx[0], idx[1]] = g_edge
         keep = torch.isfinite(sel_g) & (sel_idx >= 0)
         rows = torch.arange(n, device=dev).reshape(n, 1).expand(n, w)[keep]
         cols = sel_idx[keep].long()
@@ -331,13 +420,19 @@ class DGG_LearnableK_debug(nn.Module):
         return graph.to_coo(edge_vals)
 
     def get_adj_diff_stats(self, graph, in_vals, out_vals, k=None, writer=None, epoch=None):
-        """TensorBoard stats of dgm.py:1313-1350 computed on the support only (the reference builds ~8
-        dense N x N temporaries for them on every forward, even with writer=None)."""
+        """TensorBoard stats of dgm.py:1313-1350 on the stored entries (the reference builds ~8 dense N x N
+        temporaries for them on every forward, even with writer=None).  ``graph`` is the structure of the OUTPUT
+        (the union of the input edges and whatever off-support entries the perturbed / k_only modes added, where
+        ``in_vals`` is 0): on-edge = in_adj > 0, off-edge = in_adj == 0 (1321-1328); an entry that is stored in
+        neither matrix has difference 0 and is dropped by the reference's ``diff != 0`` filter as well."""
         diff = (in_vals - out_vals).detach()
-        diff = diff[diff != 0]
+        on, off = diff[in_vals > 0], diff[in_vals == 0]
+        diff, off = on[on != 0], off[off != 0]
         if self.training and writer is not None:
             writer.add_scalar("train_stats/on_edge_mean", diff.mean(), epoch)
             writer.add_scalar("train_stats/on_edge_std", diff.std(), epoch)
+            writer.add_scalar("train_stats/off_edge_mean", off.mean(), epoch)     # NaN when nothing is stored off
+            writer.add_scalar("train_stats/off_edge_std", off.std(), epoch)       # the support, like the reference
             deg = K.row_sum(in_vals.detach(), graph)
             writer.add_scalar("train_stats/in_deg_mean", deg.mean(), epoch)
             if k is not None:
@@ -349,11 +444,55 @@ class DGG_LearnableK_debug(nn.Module):
         if mode == "edge_p-cdf":
             # the reference scatters the *unweighted* sorted values back (dgm.py:1400): identity
             return pert_edge_p
-        if mode == "k_times_edge_prob":
+        if mode in ("k_times_edge_prob", "k_only"):
             if k is None:
-                raise TypeError("unsupported operand type(s) for -: 'Tensor' and 'NoneType'")  # dgm.py:1413
-            return K.row_firstk(pert_edge_p, k.reshape(-1), graph)
+                raise TypeError("unsupported operand type(s) for -: 'Tensor' and 'NoneType'")  # dgm.py:1413, 1430
+            if writer is not None and mode == "k_times_edge_prob":
+                rs = K.row_sum(pert_edge_p.detach(), graph)                                    # dgm.py:1406-1408
+                writer.add_scalar("values/edge_p_std", rs.std(), epoch)
+                writer.add_scalar("values/edge_p_mean", rs.mean(), epoch)
+            return K.row_firstk(pert_edge_p, k.reshape(-1), graph, k_only=(mode == "k_only"))
         raise NotImplementedError("dgg_mode_k_select=%r is not covered (see class docstring)" % (mode,))
+
+    def _k_only_spill(self, graph, vals, out, k, n):
+        """``k_only`` (dgm.py:1423-1435) gives every column of the dense row the weight fk(rank - k_i), not only the
+        edges: a row whose window ceil(k_i + 8.47) is longer than its degree spills into its non-edges, which are
+        exact zeros and therefore rank after all edges in the order the sort leaves them -- ascending column index
+        for a stable sort (what the oracle pins; the reference's order among exact ties is unspecified).  Returns
+        the union structure (edges + spilled columns, coalesced) with the input values (0 off the support) and
+        the output values; gradients reach k through both parts."""
+        kf = k.reshape(-1)
+        deg = (graph.rowptr[1:] - graph.rowptr[:-1]).to(torch.int64)
+        win = torch.ceil(kf.detach() + self.TANH_WINDOW).clamp(min=0, max=n).to(torch.int64)
+        m = (win - deg).clamp(min=0)
+        m = torch.minimum(m, n - deg)                             # non-edges a row can spill into
+        if int(m.sum()) == 0:
+            return graph, vals, out
+        # the first m_i non-edges of row i lie among its first m_i + deg_i columns
+        span = torch.where(m > 0, m + deg, torch.zeros_like(m))
+        rows = torch.repeat_interleave(torch.arange(n, device=out.device), span)
+        start = torch.cumsum(span, 0) - span
+        cols = torch.arange(rows.numel(), device=out.device) - start[rows]
+        eidx = graph.coo_indices()
+        ekey = eidx[0] * n + eidx[1]
+        ckey = rows * n + cols
+        pos = torch.searchsorted(ekey, ckey).clamp(max=ekey.numel() - 1)
+        non_edge = ekey[pos] != ckey
+        order = torch.cumsum(non_edge.to(torch.int64), 0) - 1      # running count of non-edges ...
+        first = torch.zeros(n, dtype=torch.int64, device=out.device)
+        first[span > 0] = (order - non_edge.to(torch.int64) + 1)[start[span > 0]]
+        order = order - first[rows]                               # ... restarted at every row
+        keep = non_edge & (order < m[rows])
+        rows, cols, order = rows[keep], cols[keep], order[keep]
+        r = (deg[rows] + order).to(torch.float32)
+        spill = 1 - 0.5 * (1 + torch.tanh(r - kf[rows]))          # dgm.py:1427-1431
+        key = torch.cat([ekey, rows * n + cols])
+        perm = torch.argsort(key)
+        key = key[perm]
+        u_graph = CSRGraph.from_indices(torch.stack([key // n, key % n]), n)
+        u_out = torch.cat([out, spill])[perm]
+        u_vals = torch.cat([vals, torch.zeros_like(spill)])[perm]
+        return u_graph, u_vals, u_out
 
     # ------------------------------------------------------------------ degree estimator (dgm.py:1472-1586)
     def k_estimate_net(self, N, graph, vals, x, edge_p, mode="calculate"):

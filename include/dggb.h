@@ -36,7 +36,7 @@ typedef enum dggb_status {
   DGGB_ERR_WORKSPACE = -6      /* workspace too small */
 } dggb_status;
 
-int dggb_version(void);                     /* ABI version, currently 1 */
+int dggb_version(void);                     /* ABI version, currently 2 */
 const char* dggb_error_string(int status);
 int dggb_last_cuda_error(void);             /* cudaError_t of the last DGGB_ERR_CUDA */
 int dggb_build_arch(void);                  /* 1000 == compiled for sm_100a */
@@ -90,6 +90,9 @@ int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow /* [E] row of e
                       const float* ablation_noise /* [E] or NULL */, int32_t hard_k /* <0: soft */,
                       float* R /* [E] out (post-noise value) */, int32_t* rank /* [E] out */,
                       float* s /* [N] out */, float* k /* [N] out */, float* out /* [E] out */,
+                      int32_t* long_ws /* NULL, or [N+1] scratch with long_ws[0] == 0: rows longer than 1024
+                                          entries (power-law hubs) are listed there and ranked by a third,
+                                          grid-wide launch instead of one warp each */,
                       void* stream);
 
 /* Backward of the above w.r.t. y, be, deg_w, deg_b given g_out = dL/d out.
@@ -127,12 +130,16 @@ int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* erow, const in
  * on CSR rows with an externally estimated k [N]:
  *   out_e = score_e * (1 - 0.5*(1 + tanh(r_e - k_i))),  r_e = descending in-row rank of score_e.
  * Exact zeros (tanh saturated) stay in the support as explicit zeros.
- * bwd: dscore_e = g_e * fk_e;  dk_i = 0.5 * sum_e g_e score_e sech^2(r_e - k_i)  (both OVERWRITTEN).
+ * mode 1 = "k_only" (dgm.py:1423-1435): out_e = fk(r_e - k_i), the scores only decide the order (no gradient).
+ * bwd: dscore_e = g_e * fk_e;  dk_i = 0.5 * sum_e g_e score_e sech^2(r_e - k_i)  (both OVERWRITTEN;
+ *      mode 1: dscore = 0, dk_i = 0.5 * sum_e g_e sech^2(r_e - k_i)).
  * ---------------------------------------------------------------------------------- */
 int dggb_row_firstk_fwd(const int32_t* rowptr, int32_t n, const float* score /* [E] */,
-                        const float* k /* [N] */, int32_t* rank /* [E] out */, float* out /* [E] out */,
+                        const float* k /* [N] */, int32_t mode /* 0 k_times_edge_prob, 1 k_only */,
+                        int32_t* rank /* [E] out */, float* out /* [E] out */,
+                        int32_t* long_ws /* NULL or [N+1] zero-headed scratch, see dggb_dgg_edge_fwd */,
                         void* stream);
-int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float* score, const float* k,
+int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float* score, const float* k, int32_t mode,
                         const int32_t* rank, const float* g_out, float* dscore /* [E] */,
                         float* dk /* [N] */, void* stream);
 
@@ -239,6 +246,17 @@ int dggb_allpairs_topk_fwd(const float* z /* [n,d] */, int32_t n, int32_t d, int
                            int32_t precision, void* workspace,
                            int64_t workspace_bytes, int32_t* out_idx, float* out_val, float inv_temp,
                            float* out_rowsum /* [row_count] or NULL */, void* stream);
+/* Continuation pass for rows that need more than 64 selected entries (k_i unbounded above): as
+ * dggb_allpairs_topk_fwd, but only entries that sort strictly AFTER (after_val[r], after_idx[r]) -- the last entry
+ * the previous pass returned for row r -- in (value descending, column ascending) order are admitted; pass p + 1 of
+ * a row therefore returns ranks [64 p, 64 (p + 1)).  after_val / after_idx: [row_count], both or neither NULL.
+ * Returns DGGB_ERR_K_OVERFLOW for the d = 128 / 3xTF32 tile shape, which has no continuation kernel. */
+int dggb_allpairs_topk_after_fwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
+                                 const float* t, const float* noise, int64_t noise_ld, uint64_t seed,
+                                 float noise_scale, int32_t kc, int32_t precision, void* workspace,
+                                 int64_t workspace_bytes, const float* after_val, const int32_t* after_idx,
+                                 int32_t* out_idx, float* out_val, float inv_temp, float* out_rowsum,
+                                 void* stream);
 /* Backward by recomputation over the selected pairs only (O(rows*kc*d)):
  * dz[n,d] and dt[1] are ACCUMULATED INTO. */
 int dggb_allpairs_pair_bwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,

@@ -1,5 +1,9 @@
 """ctypes binding of the C-ABI in include/dggb.h.  No CPU fallback: if libdggb.so is missing or a
-call fails, this raises."""
+call fails, this raises.
+
+Every entry point gets its ``argtypes`` / ``restype`` from the prototype in the header (parsed once at load
+time), so a call with the wrong arity or a wrong scalar type raises ``ctypes.ArgumentError`` in Python
+instead of corrupting the callee's stack."""
 from __future__ import annotations
 
 import ctypes
@@ -16,11 +20,44 @@ class DggbError(RuntimeError):
     pass
 
 
+_SCALARS = {
+    "int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+    "uint32_t": ctypes.c_uint32, "float": ctypes.c_float, "double": ctypes.c_double,
+    "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t,
+}
+
+
+def _header_text():
+    text = open(_HEADER).read()
+    return re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+
+
+def prototypes():
+    """{name: (restype, [argtypes])} for every function include/dggb.h declares."""
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(dggb_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", _header_text()):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        protos[name] = (_ctype(ret), [] if params in ("", "void") else [_ctype(a) for a in params.split(",")])
+    return protos
+
+
+def _ctype(decl: str):
+    decl = " ".join(decl.replace("const", " ").split())
+    if "*" in decl:
+        base = decl.split("*")[0].strip()
+        return ctypes.c_char_p if base == "char" else ctypes.c_void_p
+    # "int32_t n" -> "int32_t"; "long long" stays; a bare return type has no name part
+    toks = decl.split()
+    for width in (2, 1):
+        cand = " ".join(toks[:width])
+        if cand in _SCALARS:
+            return _SCALARS[cand]
+    raise DggbError(f"dggb.h: unknown C type in {decl!r}")
+
+
 def declared_symbols():
     """Every entry point include/dggb.h declares (used by the symbol-export test)."""
-    text = open(_HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(dggb_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(dggb_[a-z0-9_]+)\s*\(", _header_text())))
 
 
 def lib():
@@ -29,15 +66,12 @@ def lib():
         if not os.path.isfile(LIB_PATH):
             raise DggbError(
                 f"{LIB_PATH} not built: run `python __graft_entry__.py build` (there is no CPU fallback)")
-        _lib = ctypes.CDLL(LIB_PATH)
-        _lib.dggb_error_string.restype = ctypes.c_char_p
-        for name in declared_symbols():
-            fn = getattr(_lib, name)
-            if name in ("dggb_kernel_launches", "dggb_allpairs_workspace_bytes", "dggb_linear_act_workspace_bytes",
-                        "dggb_gemm_tn_tc_workspace_bytes"):
-                fn.restype = ctypes.c_longlong
-            elif name != "dggb_error_string":
-                fn.restype = ctypes.c_int
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in prototypes().items():
+            fn = getattr(L, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = L
     return _lib
 
 
@@ -52,15 +86,15 @@ def check(status: int, what: str = "") -> None:
 
 def p(t):
     """device pointer of a tensor (or NULL)."""
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+    return None if t is None else t.data_ptr()
 
 
 def stream():
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream
 
 
-i32 = ctypes.c_int32
-i64 = ctypes.c_int64
-f32 = ctypes.c_float
+i32 = int
+i64 = int
+f32 = float

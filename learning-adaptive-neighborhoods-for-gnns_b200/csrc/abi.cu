@@ -11,7 +11,7 @@ bool pdl_enabled() {
 }
 }
 
-extern "C" int dggb_version(void) { return 1; }
+extern "C" int dggb_version(void) { return 2; }
 extern "C" int dggb_last_cuda_error(void) { return dggb::g_last_cuda_error; }
 extern "C" int dggb_build_arch(void) { return 1000; }
 extern "C" long long dggb_kernel_launches(void) { return dggb::g_kernel_launches; }

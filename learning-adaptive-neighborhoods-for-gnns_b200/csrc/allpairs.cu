@@ -262,7 +262,8 @@ __global__ void __launch_bounds__(kAPThreads, 1)
                          const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
                          unsigned long long seed, float noise_scale, int kc, int stages,
                          int32_t* __restrict__ out_idx, float* __restrict__ out_val, float inv_temp,
-                         float* __restrict__ out_rowsum) {
+                         float* __restrict__ out_rowsum, const float* __restrict__ after_val,
+                         const int32_t* __restrict__ after_idx) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-B align WITHOUT laundering the pointer through an integer (keeps it a shared-space pointer, so
   // every access below compiles to LDS/STS instead of generic LD/ST)
@@ -385,6 +386,10 @@ __global__ void __launch_bounds__(kAPThreads, 1)
     const float* nz = (NOISE == 1 && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     const bool wide = kc > 32;
+    // continuation pass (rows that need more than 64 entries): only entries that sort strictly AFTER
+    // (after_val, after_idx) -- the last entry the previous pass returned for this row -- are admitted
+    const float ubv = (after_val != nullptr && row_ok) ? __ldg(after_val + lrow) : INFINITY;
+    const int ubc = (after_idx != nullptr && row_ok) ? __ldg(after_idx + lrow) : -1;
     auto flush = [&](unsigned need) {
       __syncwarp();   // queue entries were written by their owner lanes; the whole warp reads them below
       while (need) {
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(kAPThreads, 1)
               }
               y[c] = yy;
               if (NOISE == 3 && j < n) zsum += __expf(yy * inv_temp);   // evaluation branch only
-              pass |= (j < n && yy > thr) ? (1u << c) : 0u;
+              pass |= (j < n && yy > thr && (yy < ubv || (yy == ubv && j > ubc))) ? (1u << c) : 0u;
             }
             // phase 2 (rare once the list is warm): append the survivors to this row's queue
             if (pass) {
@@ -862,6 +867,18 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
                                       float noise_scale, int32_t kc, int32_t precision, void* workspace,
                                       int64_t workspace_bytes, int32_t* out_idx, float* out_val, float inv_temp,
                                       float* out_rowsum, void* stream) {
+  return dggb_allpairs_topk_after_fwd(z, n, d, row_begin, row_count, t, noise, noise_ld, seed, noise_scale, kc,
+                                      precision, workspace, workspace_bytes, nullptr, nullptr, out_idx, out_val,
+                                      inv_temp, out_rowsum, stream);
+}
+
+extern "C" int dggb_allpairs_topk_after_fwd(const float* z, int32_t n, int32_t d, int32_t row_begin,
+                                            int32_t row_count, const float* t, const float* noise, int64_t noise_ld,
+                                            uint64_t seed, float noise_scale, int32_t kc, int32_t precision,
+                                            void* workspace, int64_t workspace_bytes, const float* after_val,
+                                            const int32_t* after_idx, int32_t* out_idx, float* out_val,
+                                            float inv_temp, float* out_rowsum, void* stream) {
+  if ((after_val == nullptr) != (after_idx == nullptr)) return DGGB_ERR_BAD_ARG;
   if (!z || !t || !workspace || !out_idx || !out_val || n <= 0 || d <= 0 || row_begin < 0 || row_count < 0 || kc <= 0)
     return DGGB_ERR_BAD_ARG;
   if (d > 128 || kc > 64) return DGGB_ERR_BAD_SHAPE;
@@ -895,7 +912,8 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
   // slots (flushed whenever anything is pending) to keep two stages + both groups' lists under 227 KB
   const bool big = (kb == 4 && precision == 3);
   const int qcap = big ? kChunk : kQCap, qflush = big ? 1 : kQFlush;
-  if (kc <= 32 && (want_v2 || big)) {
+  if (after_val != nullptr && big) return DGGB_ERR_K_OVERFLOW;   // continuation passes run on the v1 kernel only
+  if (kc <= 32 && (want_v2 || big) && after_val == nullptr) {
     int st2 = 4;
     AP2Smem L2 = ap2_smem_layout(kb, precision, st2, kc, qcap);
     while (st2 > 2 && L2.total + 1024 > 227 * 1024) L2 = ap2_smem_layout(kb, precision, --st2, kc, qcap);
@@ -947,7 +965,7 @@ extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int3
     if (e != cudaSuccess) return cuda_status(e);                                                                  \
     allpairs_topk_kernel<KB_, SP_, NM_><<<grid, kAPThreads, smem_bytes, st>>>(                                    \
         tm_hi, tm_lo, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld, (unsigned long long)seed,      \
-        noise_scale, kc, stages, out_idx, out_val, inv_temp, out_rowsum);                                         \
+        noise_scale, kc, stages, out_idx, out_val, inv_temp, out_rowsum, after_val, after_idx);                   \
   } while (0)
 #define DGGB_AP_LAUNCH(KB_, SP_)                                                                                  \
   do {                                                                                                            \

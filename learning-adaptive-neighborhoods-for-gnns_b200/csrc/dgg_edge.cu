@@ -136,13 +136,79 @@ __device__ __forceinline__ bool stage_row(const float* __restrict__ R, float* sr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hub rows.  The in-row rank is a count (deg^2 compares); a warp owning a 20 k-entry row (real Reddit hubs) would
+// run 1.3e7 iterations per lane while the rest of the grid idles.  When the caller passes a scratch list
+// (long_ws: [n + 1] int32, long_ws[0] == 0 on entry), the row kernels only compute s / k for rows longer than
+// kRankCap, append them to the list, and long_row_rank_kernel spreads their compares over the whole grid:
+// one thread per entry, the row swept in shared-memory tiles (20 k entries: 80 blocks x 20 k iterations).
+// value modes: 0 out = v * fk(r - k); 1 out = fk(r - k) (k_only); 2 out = v * (fk(r - k) + 1) (class DGG);
+// 3 out = r < hard_k ? v : 0 (ablation)
+// ------------------------------------------------------------------------------------------------
+constexpr int kLongThreads = 256;
+constexpr int kLongTile = 2048;
+
+__device__ __forceinline__ float first_k_tanh_(float r, float k) { return 1.f - 0.5f * (1.f + tanhf(r - k)); }
+
+__device__ __forceinline__ float ranked_value(int mode, float v, int r, float k, int hard_k) {
+  if (mode == 3) return r < hard_k ? v : 0.f;
+  const float fk = first_k_tanh_((float)r, k);
+  return mode == 0 ? v * fk : (mode == 1 ? fk : v * (fk + 1.f));
+}
+
+__device__ __forceinline__ void defer_long_row(int32_t* long_ws, int row, int lane) {
+  if (lane == 0) long_ws[1 + atomicAdd(long_ws, 1)] = row;
+}
+
+__global__ void __launch_bounds__(kLongThreads)
+    long_row_rank_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ R,
+                         const float* __restrict__ k_in, int mode, int hard_k, const int32_t* long_ws,
+                         int32_t* __restrict__ rank, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float tile[kLongTile];
+  const int n_long = long_ws[0];
+  for (int q = 0; q < n_long; ++q) {
+    const int i = long_ws[1 + q];
+    const int beg = __ldg(rowptr + i), deg = __ldg(rowptr + i + 1) - beg;
+    const float k = (mode == 3) ? 0.f : k_in[i];
+    const int chunks = (deg + kLongThreads - 1) / kLongThreads;
+    for (int c = blockIdx.x; c < chunks; c += gridDim.x) {
+      const int m = c * kLongThreads + threadIdx.x;
+      const float mine = (m < deg) ? R[beg + m] : -INFINITY;
+      int cnt = 0;
+      for (int j0 = 0; j0 < deg; j0 += kLongTile) {
+        const int len = min(kLongTile, deg - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < len; j += kLongThreads) tile[j] = R[beg + j0 + j];
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < len; ++j) {
+          const float rj = tile[j];
+          cnt += (rj > mine) || (rj == mine && (j0 + j) < m);
+        }
+      }
+      if (m < deg) {
+        rank[beg + m] = cnt;
+        out[beg + m] = ranked_value(mode, mine, cnt, k, hard_k);
+      }
+    }
+  }
+}
+
+static void launch_long_rows(const int32_t* rowptr, const float* R, const float* k, int mode, int hard_k,
+                             const int32_t* long_ws, int32_t* rank, float* out, cudaStream_t st) {
+  launch_pdl(long_row_rank_kernel, dim3(kNumSMs * 4), dim3(kLongThreads), 0, st, rowptr, R, k, mode, hard_k, long_ws,
+             rank, out);
+}
+
+// ------------------------------------------------------------------------------------------------
 // fwd 2/2: s_i, k_i = LeakyReLU(w s_i + b), in-row rank, out_e = R_e * (first_k + 1)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     dgg_row_rank_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ R,
                         const float* __restrict__ deg_w, const float* __restrict__ deg_b, int hard_k,
                         int32_t* __restrict__ rank, float* __restrict__ s_out, float* __restrict__ k_out,
-                        float* __restrict__ out) {
+                        float* __restrict__ out, int32_t* long_ws) {
   pdl_trigger();
   pdl_wait();
   __shared__ float srow_all[kEdgeWarps * kRankCap];
@@ -155,6 +221,14 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     for (int e = beg + lane; e < end; e += kWarp) s += __ldg(R + e);
     s = warp_sum(s);
     const float k = leaky(w * s + b);  // dgm.py:1791-1792
+    if (lane == 0) {
+      s_out[i] = s;
+      k_out[i] = k;
+    }
+    if (long_ws != nullptr && deg > kRankCap) {   // hub row: ranked by the whole grid afterwards
+      defer_long_row(long_ws, i, lane);
+      continue;
+    }
     const bool staged = stage_row(R, srow, beg, deg, lane);
     for (int mb = 0; mb < deg; mb += kWarp) {
       const int m = mb + lane;
@@ -164,10 +238,6 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
         rank[beg + m] = r;
         out[beg + m] = (hard_k >= 0) ? (r < hard_k ? val : 0.f) : val * first_k_plus_one((float)r, k);
       }
-    }
-    if (lane == 0) {
-      s_out[i] = s;
-      k_out[i] = k;
     }
   }
 }
@@ -342,7 +412,8 @@ __device__ __forceinline__ float first_k_tanh(float r, float k) { return 1.f - 0
 
 __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     row_firstk_fwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
-                          const float* __restrict__ k_in, int32_t* __restrict__ rank, float* __restrict__ out) {
+                          const float* __restrict__ k_in, int mode, int32_t* __restrict__ rank,
+                          float* __restrict__ out, int32_t* long_ws) {
   pdl_trigger();
   pdl_wait();
   __shared__ float srow_all[kEdgeWarps * kRankCap];
@@ -351,13 +422,18 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
   for (int i = blockIdx.x * kEdgeWarps + (threadIdx.x >> 5); i < n; i += gridDim.x * kEdgeWarps) {
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1), deg = end - beg;
     const float k = __ldg(k_in + i);
+    if (long_ws != nullptr && deg > kRankCap) {
+      defer_long_row(long_ws, i, lane);
+      continue;
+    }
     const bool staged = stage_row(score, srow, beg, deg, lane);
     for (int mb = 0; mb < deg; mb += kWarp) {
       const int m = mb + lane;
       const int r = warp_rank(score, srow, staged, beg, deg, m, lane);
       if (m < deg) {
         rank[beg + m] = r;
-        out[beg + m] = __ldg(score + beg + m) * first_k_tanh((float)r, k);
+        const float fk = first_k_tanh((float)r, k);
+        out[beg + m] = mode == 1 ? fk : __ldg(score + beg + m) * fk;
       }
     }
   }
@@ -365,7 +441,7 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
 
 __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     row_firstk_bwd_kernel(const int32_t* __restrict__ rowptr, int n, const float* __restrict__ score,
-                          const float* __restrict__ k_in, const int32_t* __restrict__ rank,
+                          const float* __restrict__ k_in, int mode, const int32_t* __restrict__ rank,
                           const float* __restrict__ g_out, float* __restrict__ dscore, float* __restrict__ dk) {
   pdl_trigger();
   pdl_wait();
@@ -377,8 +453,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
     for (int e = beg + lane; e < end; e += kWarp) {
       const float th = tanhf((float)__ldg(rank + e) - k);
       const float g = __ldg(g_out + e);
-      dscore[e] = g * (1.f - 0.5f * (1.f + th));
-      acc += g * __ldg(score + e) * 0.5f * (1.f - th * th);
+      dscore[e] = mode == 1 ? 0.f : g * (1.f - 0.5f * (1.f + th));      // k_only: no gradient reaches the scores
+      acc += g * (mode == 1 ? 1.f : __ldg(score + e)) * 0.5f * (1.f - th * th);
     }
     acc = warp_sum(acc);
     if (lane == 0) dk[i] = acc;
@@ -735,7 +811,7 @@ using namespace dggb;
 extern "C" int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
                                  int32_t nnz, int32_t h, const float* y, const float* be, const float* deg_w,
                                  const float* deg_b, const float* ablation_noise, int32_t hard_k, float* R,
-                                 int32_t* rank, float* s, float* k, float* out, void* stream) {
+                                 int32_t* rank, float* s, float* k, float* out, int32_t* long_ws, void* stream) {
   if (!rowptr || !erow || !col || !y || !be || !deg_w || !deg_b || !R || !rank || !s || !k || !out || n < 0 ||
       nnz < 0 || h <= 0)
     return DGGB_ERR_BAD_ARG;
@@ -753,7 +829,10 @@ extern "C" int dggb_dgg_edge_fwd(const int32_t* rowptr, const int32_t* erow, con
     if (st != DGGB_OK) return st;
   }
   launch_pdl(dgg_row_rank_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(dgg_row_rank_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
-      rowptr, n, R, deg_w, deg_b, hard_k, rank, s, k, out);
+      rowptr, n, R, deg_w, deg_b, hard_k, rank, s, k, out, long_ws);
+  st = launch_status();
+  if (st != DGGB_OK || long_ws == nullptr) return st;
+  launch_long_rows(rowptr, R, k, hard_k >= 0 ? 3 : 2, hard_k, long_ws, rank, out, as_stream(stream));
   return launch_status();
 }
 
@@ -783,21 +862,27 @@ extern "C" int dggb_dgg_edge_bwd(const int32_t* rowptr, const int32_t* erow, con
 }
 
 extern "C" int dggb_row_firstk_fwd(const int32_t* rowptr, int32_t n, const float* score, const float* k,
-                                   int32_t* rank, float* out, void* stream) {
+                                   int32_t mode, int32_t* rank, float* out, int32_t* long_ws, void* stream) {
   if (!rowptr || !score || !k || !rank || !out || n < 0) return DGGB_ERR_BAD_ARG;
+  if (mode != 0 && mode != 1) return DGGB_ERR_UNSUPPORTED;
   if (n == 0) return DGGB_OK;
-  launch_pdl(row_firstk_fwd_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(row_firstk_fwd_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), rowptr, n, score,
-                                                                                                 k, rank, out);
+  launch_pdl(row_firstk_fwd_kernel,
+             dim3(rows_grid(n, kEdgeWarps, resident_blocks(row_firstk_fwd_kernel, kEdgeWarps * kWarp))),
+             dim3(kEdgeWarps * kWarp), 0, as_stream(stream), rowptr, n, score, k, mode, rank, out, long_ws);
+  const int st = launch_status();
+  if (st != DGGB_OK || long_ws == nullptr) return st;
+  launch_long_rows(rowptr, score, k, mode, -1, long_ws, rank, out, as_stream(stream));
   return launch_status();
 }
 
 extern "C" int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float* score, const float* k,
-                                   const int32_t* rank, const float* g_out, float* dscore, float* dk,
+                                   int32_t mode, const int32_t* rank, const float* g_out, float* dscore, float* dk,
                                    void* stream) {
   if (!rowptr || !score || !k || !rank || !g_out || !dscore || !dk || n < 0) return DGGB_ERR_BAD_ARG;
+  if (mode != 0 && mode != 1) return DGGB_ERR_UNSUPPORTED;
   if (n == 0) return DGGB_OK;
   launch_pdl(row_firstk_bwd_kernel, dim3(rows_grid(n, kEdgeWarps, resident_blocks(row_firstk_bwd_kernel, kEdgeWarps * kWarp))), dim3(kEdgeWarps * kWarp), 0, as_stream(stream), 
-      rowptr, n, score, k, rank, g_out, dscore, dk);
+      rowptr, n, score, k, mode, rank, g_out, dscore, dk);
   return launch_status();
 }
 
@@ -819,8 +904,9 @@ extern "C" int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* ero
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads,
                                                   (size_t)(128 + max_row_nnz) * sizeof(float));
     fused_grid(nnz, occ, &blocks, &epb);
-    const int cap = epb + max_row_nnz;
-    if ((size_t)cap * sizeof(float) > 48 * 1024) return (int)DGGB_ERR_UNSUPPORTED;
+    // shared-memory score window: entries beyond it (bounded-degree graphs with > ~7 M entries make epb large)
+    // are re-read from global memory by the rank phase (the `idx < cap` / `in_s` guards of the kernel)
+    const int cap = min(epb + max_row_nnz, 12288);
     launch_pdl(kern, dim3(blocks), dim3(kFusedThreads), (size_t)cap * sizeof(float), as_stream(stream), rowptr, erow,
                col, n, nnz, h, L, epb, cap, y, be, ablation_noise, deg_w, deg_b, hard_k, R, rank, s, k, out, zero_ws,
                (long long)zero_count);

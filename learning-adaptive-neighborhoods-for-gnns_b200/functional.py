@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import check, i32, lib, p, stream
+from ._lib import check, i32, i64, lib, p, stream
 from .graph import CSRGraph
 
 
@@ -19,6 +19,14 @@ def _require_cuda(*ts):
 
 
 _FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu
+_LONG_ROW = 1024       # kRankCap of csrc/dgg_edge.cu: longer rows are ranked by a grid-wide launch
+
+
+def _long_ws(graph: CSRGraph):
+    """Zero-headed scratch list for hub rows (None when the graph has none: the row kernels then take no detour)."""
+    if graph.max_row_nnz <= _LONG_ROW and graph.max_row_nnz >= 0:
+        return None
+    return torch.zeros(graph.n + 1, dtype=torch.int32, device=graph.rowptr.device)
 
 
 class _DGGEdge(torch.autograd.Function):
@@ -45,16 +53,15 @@ class _DGGEdge(torch.autograd.Function):
                 # the backward's accumulation buffers (dy | dbe | ddeg (+pad) | ds) are cleared by the forward
                 # launch: no separate fill kernel between the two fused launches of a training step
                 zbuf = torch.empty(n * h + h + 4 + n, dtype=torch.float32, device=dev)
-            import ctypes
             check(lib().dggb_dgg_edge_fwd_fused(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(mx),
                                                 i32(h), p(y), p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R),
                                                 p(rank), p(s), p(k), p(out), p(zbuf),
-                                                ctypes.c_int64(0 if zbuf is None else zbuf.numel()), stream()),
+                                                i64(0 if zbuf is None else zbuf.numel()), stream()),
                   "dgg_edge_fwd_fused")
         else:
             check(lib().dggb_dgg_edge_fwd(p(graph.rowptr), p(graph.erow), p(graph.col), i32(n), i32(E), i32(h), p(y),
                                           p(be), p(deg_w), p(deg_b), p(noise), i32(hard_k), p(R), p(rank), p(s), p(k),
-                                          p(out), stream()), "dgg_edge_fwd")
+                                          p(out), p(_long_ws(graph)), stream()), "dgg_edge_fwd")
         ctx.graph, ctx.hard_k, ctx.fused_mx = graph, hard_k, (mx if fused else -1)
         ctx.zbuf = zbuf
         ctx.set_materialize_grads(False)   # k / R / rank never carry gradients: no zero tensors for them per step
@@ -160,10 +167,7 @@ class _AllPairsTopK(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, z, t, noise, kc: int, precision: int, row_begin: int, row_count: int, seed: int,
-                noise_scale: float, inv_temp: float = 0.0):
-        import ctypes
-
-        from ._lib import i64
+                noise_scale: float, inv_temp: float = 0.0, after_val=None, after_idx=None):
         _require_cuda(z, t, noise)
         z, t = _f32c(z), _f32c(t).reshape(-1)
         n, d = z.shape
@@ -176,11 +180,14 @@ class _AllPairsTopK(torch.autograd.Function):
         if noise is not None:
             noise = _f32c(noise)
             assert noise.dim() == 2 and noise.shape[0] == row_count and noise.shape[1] >= n
-        check(L.dggb_allpairs_topk_fwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(t), p(noise),
-                                       i64(0 if noise is None else noise.stride(0)), ctypes.c_uint64(seed),
-                                       ctypes.c_float(noise_scale), i32(kc), i32(precision), p(ws),
-                                       i64(ws_bytes), p(idx), p(val), ctypes.c_float(inv_temp), p(rowsum), stream()),
-              "allpairs_topk_fwd")
+        if after_val is not None:
+            after_val, after_idx = _f32c(after_val), after_idx.to(torch.int32).contiguous()
+            assert after_val.numel() == row_count and after_idx.numel() == row_count
+        check(L.dggb_allpairs_topk_after_fwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(t), p(noise),
+                                             i64(0 if noise is None else noise.stride(0)), int(seed),
+                                             float(noise_scale), i32(kc), i32(precision), p(ws), i64(ws_bytes),
+                                             p(after_val), p(after_idx), p(idx), p(val), float(inv_temp), p(rowsum),
+                                             stream()), "allpairs_topk_fwd")
         ctx.meta = (kc, row_begin, row_count)
         ctx.save_for_backward(z, t, idx)
         ctx.mark_non_differentiable(idx)
@@ -198,49 +205,53 @@ class _AllPairsTopK(torch.autograd.Function):
         dt = torch.zeros(1, dtype=torch.float32, device=z.device)
         check(lib().dggb_allpairs_pair_bwd(p(z), i32(n), i32(d), i32(row_begin), i32(row_count), p(idx),
                                            p(_f32c(gy)), i32(kc), p(t), p(dz), p(dt), stream()), "allpairs_pair_bwd")
-        return dz, dt, None, None, None, None, None, None, None, None
+        return dz, dt, None, None, None, None, None, None, None, None, None, None
 
 
 def allpairs_topk(z, t, noise=None, kc=32, precision=3, row_begin=0, row_count=None, seed=0, noise_scale=0.0,
-                  inv_temp=0.0):
+                  inv_temp=0.0, after=None):
     """-> (idx int32 [rows,kc], y fp32 [rows,kc]) sorted descending per row; differentiable in z and t.
     noise: injected [rows, n] tensor, or None with noise_scale != 0 for in-kernel Philox Gumbel noise.
-    inv_temp != 0 additionally returns rowsum [rows] = sum_j exp(y_ij * inv_temp) over all columns."""
+    inv_temp != 0 additionally returns rowsum [rows] = sum_j exp(y_ij * inv_temp) over all columns.
+    after = (val [rows], idx [rows]): continuation pass, only entries sorting strictly after that one per row."""
     if row_count is None:
         row_count = z.shape[0] - row_begin
+    av, ai = (None, None) if after is None else after
     return _AllPairsTopK.apply(z, t, noise, int(kc), int(precision), int(row_begin), int(row_count), int(seed),
-                               float(noise_scale), float(inv_temp))
+                               float(noise_scale), float(inv_temp), av, ai)
 
 
 class _RowFirstK(torch.autograd.Function):
     """select_top_k(mode="k_times_edge_prob") on CSR rows (dgm.py:1402-1421)."""
 
     @staticmethod
-    def forward(ctx, score, k, graph: CSRGraph):
+    def forward(ctx, score, k, graph: CSRGraph, mode: int):
         _require_cuda(score, k)
         score, k = _f32c(score), _f32c(k).reshape(-1)
         rank = torch.empty(graph.nnz, dtype=torch.int32, device=score.device)
         out = torch.empty_like(score)
-        check(lib().dggb_row_firstk_fwd(p(graph.rowptr), i32(graph.n), p(score), p(k), p(rank), p(out), stream()),
-              "row_firstk_fwd")
-        ctx.graph = graph
+        check(lib().dggb_row_firstk_fwd(p(graph.rowptr), i32(graph.n), p(score), p(k), i32(mode), p(rank), p(out),
+                                        p(_long_ws(graph)), stream()), "row_firstk_fwd")
+        ctx.graph, ctx.mode = graph, mode
         ctx.save_for_backward(score, k, rank)
-        return out
+        ctx.mark_non_differentiable(rank)
+        return out, rank
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _grank):
         score, k, rank = ctx.saved_tensors
         gr = ctx.graph
         dscore = torch.empty_like(score)
         dk = torch.empty_like(k)
-        check(lib().dggb_row_firstk_bwd(p(gr.rowptr), i32(gr.n), p(score), p(k), p(rank), p(_f32c(g)), p(dscore),
-                                        p(dk), stream()), "row_firstk_bwd")
-        return dscore, dk, None
+        check(lib().dggb_row_firstk_bwd(p(gr.rowptr), i32(gr.n), p(score), p(k), i32(ctx.mode), p(rank), p(_f32c(g)),
+                                        p(dscore), p(dk), stream()), "row_firstk_bwd")
+        return (dscore if ctx.mode == 0 else None), dk, None, None
 
 
-def row_firstk(score, k, graph):
-    """out_e = score_e * (1 - 0.5 (1 + tanh(rank_e - k_row)))"""
-    return _RowFirstK.apply(score, k, graph)
+def row_firstk(score, k, graph, k_only=False, return_rank=False):
+    """out_e = score_e * fk_e, fk_e = 1 - 0.5 (1 + tanh(rank_e - k_row));  k_only: out_e = fk_e (dgm.py:1423-1435)."""
+    out, rank = _RowFirstK.apply(score, k, graph, 1 if k_only else 0)
+    return (out, rank) if return_rank else out
 
 
 def row_sum(vals, graph):
@@ -279,8 +290,6 @@ class _TallLinear(torch.autograd.Function):
 def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None, w2=None, zero=None):
     """out = epi(x W_eff^T + b + addend) through dggb_linear_fused (tcgen05, 3xTF32); None if the shape is
     not supported.  epi = LeakyReLU(slope), or * LeakyReLU'(act_src) when act_src is given (backward form)."""
-    import ctypes
-
     h = w.shape[1] if w_transposed else w.shape[0]
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 4 == 0
             and h in (16, 32, 64, 128) and x.shape[0] >= 512):
@@ -295,9 +304,8 @@ def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None
     out2 = torch.empty(n, h, dtype=torch.float32, device=x.device) if w2 is not None else None
     w2c = None if w2 is None else w2.contiguous()
     rc = lib().dggb_linear_fused(p(x), p(w), i32(1 if w_transposed else 0), p(bb), p(ad), p(ac),
-                                 ctypes.c_float(slope), i32(n), i32(f_in), i32(h), p(out), p(w2c), p(out2), p(ws),
-                                 ctypes.c_int64(ws.numel() * 4), p(zero),
-                                 ctypes.c_int64(0 if zero is None else zero.numel()), stream())
+                                 float(slope), i32(n), i32(f_in), i32(h), p(out), p(w2c), p(out2), p(ws),
+                                 i64(ws.numel() * 4), p(zero), i64(0 if zero is None else zero.numel()), stream())
     if rc == -2:
         return None
     check(rc, "linear_fused")
@@ -375,12 +383,10 @@ def gemm_tn(a, b, want_colsum=False, use_tc=None, zeroed=None):
         # wide outputs amortise the transpose pre-pass; narrow ones (dWe, Q = h) stay on the SIMT split-K kernel
         use_tc = n >= 4096 and q % 4 == 0 and q >= 256 and pp in (16, 32, 64, 128)
     if use_tc:
-        import ctypes
-
         L = lib()
         ws_bytes = int(L.dggb_gemm_tn_tc_workspace_bytes(i32(n), i32(pp)))
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=a.device)
-        check(L.dggb_gemm_tn_tc(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), p(ws), ctypes.c_int64(ws_bytes),
+        check(L.dggb_gemm_tn_tc(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), p(ws), i64(ws_bytes),
                                 stream()), "gemm_tn_tc")
     else:
         check(lib().dggb_gemm_tn_splitk(p(a), p(b), i32(n), i32(pp), i32(q), p(out), p(cs), stream()),

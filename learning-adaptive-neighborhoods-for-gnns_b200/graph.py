@@ -68,7 +68,10 @@ class CSRGraph:
         """-> (CSRGraph, values).  Reuses the handle attached by a previous call / by DGG."""
         h = getattr(adj, "_dgg_csr", None)
         if h is not None:
-            return h, getattr(adj, "_dgg_vals", None) if getattr(adj, "_dgg_vals", None) is not None else adj._values()
+            v = getattr(adj, "_dgg_vals", None)
+            if v is None:
+                v = adj._values()
+            return h, (v if v.dtype == torch.float32 else v.to(torch.float32))
         assert adj.is_sparse and adj.dim() == 2 and adj.shape[0] == adj.shape[1]
         if not adj.is_coalesced():
             adj = adj.coalesce()
@@ -95,10 +98,17 @@ class CSRGraph:
             out_col = torch.empty(nnz_out, dtype=torch.int32, device=dev)
             self._loops = CSRGraph(self.n, out_rowptr, out_col)
         g = self._loops
+        if not vals.is_cuda:
+            raise RuntimeError("dgg_b200 ops need CUDA tensors (no CPU fallback)")
+        vals = vals.contiguous() if vals.dtype == torch.float32 else vals.to(torch.float32).contiguous()
         out_val = torch.empty(g.nnz, dtype=torch.float32, device=dev)
-        check(L.dggb_add_self_loops_fill(p(self.rowptr), p(self.col), p(vals.contiguous()), i32(self.n),
+        check(L.dggb_add_self_loops_fill(p(self.rowptr), p(self.col), p(vals), i32(self.n),
                                          p(g.rowptr), p(g.col), p(out_val), stream()), "add_self_loops_fill")
         return g, out_val
+
+    def diag_mask(self) -> torch.Tensor:
+        """bool [nnz]: entries on the diagonal."""
+        return self.erow == self.col
 
     # ------------------------------------------------------------------ export
     def coo_indices(self) -> torch.Tensor:

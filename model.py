@@ -512,3 +512,138 @@ class GAT_DGG_Ablations(GAT_DGG_00):
 
 
 GAT_DGG = GAT_DGG_00   # the north star's name for it; the reference only has GAT_DGG_00
+
+
+# --------------------------------------------------------------------------- non-DGG baselines
+def baseline_normalized_adj(adj):
+    """``normalize_adj`` of the baselines (reference model.py:87-97, 621-630, 981-991): zero the diagonal, add I,
+    D^-1/2 (A + I) D^-1/2 -- on CSR, O(nnz), instead of ``to_dense`` + ``diag`` + ``inverse`` + two N^3 ``mm``."""
+    if not adj.is_sparse:
+        a = adj.clone()
+        a.fill_diagonal_(0)
+        a = a + torch.eye(a.shape[0], device=a.device)
+        d = a.sum(1) ** -0.5
+        return d.unsqueeze(-1) * a * d.unsqueeze(0)
+    g0, v0 = CSRGraph.from_coo(adj)
+    g, v = g0.with_self_loops(v0)
+    v = torch.where(g.diag_mask(), torch.ones_like(v), v)       # existing self loops are reset, not incremented
+    return g.to_coo(K.sym_normalize(v, g))
+
+
+class GCN(torch.nn.Module):
+    """Reference model.py:968-1025 (two GCNConv on the normalised INPUT graph; no DGG)."""
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, **kwargs):
+        super().__init__()
+        self.conv1 = GCNConv(nfeat, nhidden)
+        self.conv2 = GCNConv(nhidden, nclass)
+        self.params1 = list(self.conv1.parameters())
+        self.params2 = list(self.conv2.parameters())
+
+    def normalize_adj(self, A):
+        return baseline_normalized_adj(A)
+
+    def forward(self, x, adj, epoch=None, writer=None, **kwargs):
+        adj = self.normalize_adj(adj)
+        x = F.dropout(self.conv1(x, adj), training=self.training)
+        if writer is not None:
+            writer.add_histogram("gcn_conv1_dist", x, epoch)
+        x = self.conv2(x, adj)
+        if writer is not None:
+            writer.add_histogram("gcn_conv2_dist", x, epoch)
+        return F.log_softmax(x, dim=-1), None, None
+
+
+class GCNII(nn.Module):
+    """Reference model.py:602-646."""
+
+    def __init__(self, nfeat, nlayers, nhidden, nclass, dropout, lamda, alpha, variant, args=None):
+        super().__init__()
+        self.convs = nn.ModuleList()
+        for _ in range(nlayers):
+            self.convs.append(GraphConvolution(nhidden, nhidden, variant=variant))
+        self.fcs = nn.ModuleList()
+        self.fcs.append(nn.Linear(nfeat, nhidden))
+        self.fcs.append(nn.Linear(nhidden, nclass))
+        self.params1 = list(self.convs.parameters())
+        self.params2 = list(self.fcs.parameters())
+        self.act_fn = nn.ReLU()
+        self.dropout = dropout
+        self.alpha = alpha
+        self.lamda = lamda
+
+    def normalize_adj(self, A):
+        return baseline_normalized_adj(A)
+
+    def forward(self, x, adj, epoch=None, writer=None):
+        adj = self.normalize_adj(adj)
+        _layers = []
+        x = F.dropout(x, self.dropout, training=self.training)
+        layer_inner = self.act_fn(self.fcs[0](x))
+        _layers.append(layer_inner)
+        for i, con in enumerate(self.convs):
+            layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+            layer_inner = self.act_fn(con(layer_inner, adj, _layers[0], self.lamda, self.alpha, i + 1))
+        layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+        layer_inner = self.fcs[-1](layer_inner)
+        return F.log_softmax(layer_inner, dim=1)
+
+
+class SAGE(torch.nn.Module):
+    """Reference model.py:80-119."""
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, **kwargs):
+        super().__init__()
+        self.convs = torch.nn.ModuleList()
+        self.convs.append(DenseGraphConv(nfeat, nhidden, aggr="mean"))
+        self.convs.append(DenseGraphConv(nhidden, nclass, aggr="mean"))
+
+    def normalize_adj(self, A):
+        return baseline_normalized_adj(A)
+
+    def forward(self, x, adj, epoch=None, writer=None, **kwargs):
+        adj = self.normalize_adj(adj)
+        for i, conv in enumerate(self.convs):
+            x = conv(x, adj)
+            if i < len(self.convs) - 1:
+                x = x.relu_()
+                x = F.dropout(x, p=0.5, training=self.training)
+        x = F.log_softmax(x, dim=-1)
+        return x.squeeze(0), None, None
+
+
+class GATConv(GATConv_DGG):
+    """Reference model.py:489-531: logits are -1e20 off the edge list, i.e. a true masked softmax over the listed
+    edges -- the ``GATConv_DGG`` evaluation without the dense background term and with A == 1."""
+
+    def forward(self, x, edge_index, adj=None):
+        return self._attend(x, edge_index, None)
+
+
+class GAT(nn.Module):
+    """Reference model.py:286-320."""
+
+    def __init__(self, nfeat=32, nlayers=None, nhidden=32, nclass=10, args=None, nhead=8, nhead_out=1, alpha=0.2,
+                 dropout=0.6, **kwargs):
+        super().__init__()
+        self.attentions = [GATConv(nfeat, nhidden, dropout=dropout, alpha=alpha) for _ in range(nhead)]
+        self.out_atts = [GATConv(nhidden * nhead, nclass, dropout=dropout, alpha=alpha) for _ in range(nhead_out)]
+        for i, attention in enumerate(self.attentions):
+            self.add_module("attention_{}".format(i), attention)
+        for i, attention in enumerate(self.out_atts):
+            self.add_module("out_att{}".format(i), attention)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for att in self.attentions:
+            att.reset_parameters()
+        for att in self.out_atts:
+            att.reset_parameters()
+
+    def forward(self, x, in_adj=None, edge_index=None, epoch=None, writer=None):
+        edge_index, _ = remove_self_loops(edge_index)
+        edge_index, _ = add_self_loops(edge_index, num_nodes=x.size(0))
+        x = torch.cat([att(x, edge_index) for att in self.attentions], dim=1)
+        x = F.elu(x)
+        x = torch.sum(torch.stack([att(x, edge_index) for att in self.out_atts]), dim=0) / len(self.out_atts)
+        return F.log_softmax(x, dim=1), None, None

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from oracle import dgg_oracle as O
-from tests.helpers import coo, random_graph, tie_free_rows
+from tests.helpers import assert_grad_close, coo, near_tie_entries, random_graph, sparse_ranks, tie_free_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -97,27 +97,29 @@ def test_dgg_vs_oracle_random(n, f, h, avg_deg, hubs):
         m.degree_decoder[0].bias.fill_(0.3)
     state = {k: v.clone() for k, v in m.state_dict().items()}
     m = m.cuda()
+    p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    xo = x.clone().requires_grad_(True)
+    r = O.dgg_forward(xo, idx, n, p)
+    ref_vals = r["out"][idx[0], idx[1]]
+    # entries with a near-tied neighbour may legitimately swap ranks under another fp32 summation order: they are
+    # left OUT OF THE LOSS on both sides, so every gradient assert below runs unconditionally
+    rows_ok = ~near_tie_entries(idx, r["R"].detach(), n)
+    assert rows_ok.float().mean() > 0.95
+    wt_e = wt_e * rows_ok
+    ((ref_vals * wt_e).sum() + (r["x_enc"] * wt2).sum()).backward()
+
     xg = x.cuda().requires_grad_(True)
     out, x_enc = m(xg, coo(idx, val, n).cuda())
     vals = out.coalesce().values()
     ((vals * wt_e.cuda()).sum() + (x_enc * wt2.cuda()).sum()).backward()
 
-    p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
-    xo = x.clone().requires_grad_(True)
-    r = O.dgg_forward(xo, idx, n, p)
-    ref_vals = r["out"][idx[0], idx[1]]
-    ((ref_vals * wt_e).sum() + (r["x_enc"] * wt2).sum()).backward()
-
     assert torch.equal(out.coalesce().indices().cpu(), idx)
-    ok = tie_free_rows(O.dense_from_edges(idx, r["R"].detach(), n), idx)
-    assert ok.float().mean() > 0.9
-    rows_ok = ok[idx[0]]
     torch.testing.assert_close(vals.detach().cpu()[rows_ok], ref_vals.detach()[rows_ok], **FWD)
     torch.testing.assert_close(m.last_k.cpu(), r["k"].detach().flatten(), rtol=1e-5, atol=1e-5)
-    if bool(ok.all()):
-        for k, q in m.named_parameters():
-            torch.testing.assert_close(q.grad.cpu(), p[k].grad, rtol=1e-3, atol=2e-4)
-        torch.testing.assert_close(xg.grad.cpu(), xo.grad, rtol=1e-3, atol=2e-5)
+    assert torch.equal(m.last_rank.cpu().long()[rows_ok], sparse_ranks(idx, r["R"].detach(), n)[rows_ok])
+    for k, q in m.named_parameters():
+        assert_grad_close(q.grad.cpu(), p[k].grad, what=k)
+    assert_grad_close(xg.grad.cpu(), xo.grad, what="x")
 
 
 def test_sym_normalize_and_spmm_vs_dense():
@@ -268,23 +270,21 @@ def test_dgg_edge_cases_long_rows_and_empty_rows():
         m.node_encoder[0].weight.mul_(8.0)
     state = {k: v.clone() for k, v in m.state_dict().items()}
     m = m.cuda()
-    out, x_enc = m(x.cuda(), torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).coalesce().cuda())
-    vals = out.coalesce().values()
-    w = torch.randn(idx.shape[1], generator=gen)
-    (vals * w.cuda()).sum().backward()
     p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
     r = O.dgg_forward(x, idx, n, p)
     ref = r["out"][idx[0], idx[1]]
+    rows_ok = ~near_tie_entries(idx, r["R"].detach(), n)
+    assert int(rows_ok[idx[0] == 7].sum()) > 1000       # the hub row stays in the loss (minus its near-tied entries)
+    w = torch.randn(idx.shape[1], generator=gen) * rows_ok   # near-tied entries are left out on both sides
     (ref * w).sum().backward()
-    ok = tie_free_rows(O.dense_from_edges(idx, r["R"].detach(), n), idx)
-    assert bool(ok[7]) or True
-    rows_ok = ok[idx[0]]
+    out, x_enc = m(x.cuda(), torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).coalesce().cuda())
+    vals = out.coalesce().values()
+    (vals * w.cuda()).sum().backward()
     torch.testing.assert_close(vals.detach().cpu()[rows_ok], ref.detach()[rows_ok], **FWD)
     torch.testing.assert_close(m.last_k.cpu(), r["k"].detach().flatten(), rtol=1e-5, atol=1e-5)
-    assert int(rows_ok.sum()) > 0.5 * idx.shape[1]
-    if bool(ok.all()):
-        for k, q in m.named_parameters():
-            torch.testing.assert_close(q.grad.cpu(), p[k].grad, rtol=2e-3, atol=2e-4)
+    assert torch.equal(m.last_rank.cpu().long()[rows_ok], sparse_ranks(idx, r["R"].detach(), n)[rows_ok])
+    for k, q in m.named_parameters():
+        assert_grad_close(q.grad.cpu(), p[k].grad, what=k)
     # single node with a self loop
     one = torch.sparse_coo_tensor(torch.zeros(2, 1, dtype=torch.long), torch.ones(1), (1, 1)).coalesce().cuda()
     o1, _ = m(x[:1].cuda(), one)

@@ -1,23 +1,83 @@
-"""Host-side helpers on the path's input side: the per-step pipeline of the reference
-training loops is  to_scipy_sparse_matrix -> add_noisy_edges -> sparse_mx_to_torch_sparse_tensor -> .to(device)
-(train_small_graphs.py:251-255, 283-289, 305-311), three times per epoch, with a dense N x N numpy RNG draw
-inside ``add_noisy_edges`` that is re-seeded to 0 on every call (reference utils.py:92-110) -- i.e. it returns
-the SAME noisy graph every time at O(N^2) host cost.  These drop-ins keep the reference's behaviour (same numpy
-random stream, same outputs) but memoise the result and never hold more than a row chunk of the random
-matrix; ``cached_device_adj`` additionally keeps the device-side sparse tensor (with its CSR handle) alive
-across epochs.  Only the helpers that touch the DGG path's inputs live here (utils.py:31-35, 81-110, 1260-1268);
-dataset loaders and the other experiment utilities of the reference are out of scope.
+"""Drop-in ``utils`` for the reference's training scripts, input side of the DGG path.
+
+The scripts do ``import utils`` / ``from utils import *`` (train_small_graphs.py:9-10, 18; train_pubmed.py:12) and
+rely on everything the reference's ``utils.py`` exports -- dataset loaders, metrics, and even the ``torch`` / ``np``
+/ ``F`` names it imports.  This module therefore
+
+  1. re-exports the reference's own ``utils.py`` when one is found further down ``sys.path`` (the documented set-up is
+     ``PYTHONPATH=<this repo>:<reference>``): its source is executed in this module's namespace, so loaders, PyG
+     glue and experiment helpers stay the reference's, untouched;
+  2. then overrides the few helpers that sit on the DGG path's input side with B200-friendly versions of identical
+     behaviour: the per-step host pipeline of the training loops is
+         to_scipy_sparse_matrix -> add_noisy_edges -> sparse_mx_to_torch_sparse_tensor -> .to(device)
+     (train_small_graphs.py:251-255, 283-289, 305-311), three times per epoch, with a dense N x N numpy RNG draw
+     inside ``add_noisy_edges`` that is re-seeded to 0 on every call (reference utils.py:92-110) -- i.e. it returns
+     the SAME noisy graph every time at O(N^2) host cost (and crashes on numpy >= 1.24: ``np.float``).  The
+     override keeps the reference's numpy random stream bit for bit, never holds more than a row chunk of the
+     random matrix, and memoises the result; ``cached_device_adj`` additionally keeps the device-side sparse tensor
+     (with its CSR handle) alive across epochs.
+
+Without a reference checkout on ``sys.path`` only the overrides (``accuracy``, ``str2bool``,
+``sparse_mx_to_torch_sparse_tensor``, ``add_noisy_edges``, ``cached_device_adj``, ``clear_caches``) are defined.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
+import os
+import sys
+from collections import OrderedDict
 
 import numpy as np
 import scipy.sparse as sp
 import torch
 
-_NOISY_CACHE = {}
-_DEVICE_CACHE = {}
+
+def _find_reference_utils():
+    """Path of another ``utils.py`` on sys.path that looks like the reference's (defines ``load_citation``)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for entry in sys.path:
+        cand = os.path.join(entry or os.getcwd(), "utils.py")
+        try:
+            if not os.path.isfile(cand) or os.path.samefile(os.path.dirname(os.path.abspath(cand)), here):
+                continue
+            with open(cand) as fh:
+                if "def load_citation" in fh.read():
+                    return cand
+        except OSError:
+            continue
+    return None
+
+
+REFERENCE_UTILS = None if os.environ.get("DGGB_NO_REFERENCE_UTILS") else _find_reference_utils()
+if REFERENCE_UTILS is not None:
+    with open(REFERENCE_UTILS) as _fh:
+        exec(compile(_fh.read(), REFERENCE_UTILS, "exec"), globals())   # the reference's names, unmodified
+    del _fh
+
+_CACHE_SLOTS = 8
+_NOISY_CACHE = OrderedDict()    # content hash -> noisy scipy CSR (bounded LRU)
+_DEVICE_CACHE = OrderedDict()   # content hash -> device sparse tensor (bounded LRU; pins GPU memory)
+
+
+def clear_caches():
+    """Drop the memoised noisy graphs and the device-resident adjacencies."""
+    _NOISY_CACHE.clear()
+    _DEVICE_CACHE.clear()
+
+
+def _lru_get(cache, key):
+    hit = cache.get(key)
+    if hit is not None:
+        cache.move_to_end(key)
+    return hit
+
+
+def _lru_put(cache, key, value):
+    cache[key] = value
+    cache.move_to_end(key)
+    while len(cache) > _CACHE_SLOTS:
+        cache.popitem(last=False)
 
 
 def accuracy(output, labels):
@@ -46,11 +106,16 @@ def sparse_mx_to_torch_sparse_tensor(sparse_mx):
     return torch.sparse_coo_tensor(indices, values, torch.Size(sparse_mx.shape))
 
 
-def _graph_key(adj):
-    adj = sp.coo_matrix(adj)
-    h = hash((adj.shape, adj.nnz, adj.row[:64].tobytes(), adj.col[:64].tobytes(), adj.row[-64:].tobytes(),
-              adj.col[-64:].tobytes(), float(adj.data.sum())))
-    return h, adj
+def _content_key(*arrays, extra=()):
+    """Full-content fingerprint (O(E), far below the O(N^2) draw it guards): two graphs that differ anywhere
+    get different keys."""
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str((a.shape, a.dtype.str)).encode())
+        h.update(a.tobytes())
+    h.update(repr(extra).encode())
+    return h.hexdigest()
 
 
 def add_noisy_edges(adj, noise_level=0.1, chunk_rows=1024):
@@ -58,9 +123,9 @@ def add_noisy_edges(adj, noise_level=0.1, chunk_rows=1024):
     (seed 0), except on existing edges and on the diagonal.  Same random stream (numpy fills row-major, so
     drawing the matrix in row chunks after one ``seed(0)`` is bit-identical), O(chunk * N) memory instead of
     three dense N x N arrays, and memoised: the reference recomputes the identical result on every call."""
-    key, adj = _graph_key(adj)
-    key = (key, float(noise_level))
-    hit = _NOISY_CACHE.get(key)
+    adj = sp.coo_matrix(adj)
+    key = _content_key(adj.row, adj.col, adj.data, extra=(adj.shape, float(noise_level)))
+    hit = _lru_get(_NOISY_CACHE, key)
     if hit is not None:
         return hit.copy()
     level = noise_level * 10
@@ -90,18 +155,18 @@ def add_noisy_edges(adj, noise_level=0.1, chunk_rows=1024):
         rows = cols = np.zeros(0, dtype=np.int64)
     noise = sp.coo_matrix((np.ones(len(rows), dtype=np.float64), (rows, cols)), shape=adj.shape)
     noisy = sp.csr_matrix(adj.astype(np.float64) + noise)
-    _NOISY_CACHE[key] = noisy
+    _lru_put(_NOISY_CACHE, key, noisy)
     return noisy.copy()
 
 
 def cached_device_adj(edge_index, num_nodes, noise_level=0.0, device="cuda"):
     """The whole per-step host pipeline, once: edge_index [2,E] -> (optionally noisy) coalesced sparse COO on
-    ``device`` carrying the CSR handle the DGG modules reuse.  Later calls with the same graph return the same
-    device tensor (no host work, no H2D copy)."""
+    ``device`` carrying the CSR handle the DGG modules reuse.  Later calls with the same graph (same content)
+    return the same device tensor (no host work, no H2D copy).  At most ``_CACHE_SLOTS`` graphs stay resident;
+    ``clear_caches()`` releases them."""
     ei = edge_index.detach().cpu().numpy()
-    key = (int(num_nodes), ei.shape[1], hash(ei[:, :64].tobytes()), hash(ei[:, -64:].tobytes()), float(noise_level),
-           str(device))
-    hit = _DEVICE_CACHE.get(key)
+    key = _content_key(ei, extra=(int(num_nodes), float(noise_level), str(device)))
+    hit = _lru_get(_DEVICE_CACHE, key)
     if hit is not None:
         return hit
     adj = sp.coo_matrix((np.ones(ei.shape[1], dtype=np.float32), (ei[0], ei[1])), shape=(num_nodes, num_nodes))
@@ -112,5 +177,5 @@ def cached_device_adj(edge_index, num_nodes, noise_level=0.0, device="cuda"):
         from dgg_b200 import CSRGraph
 
         CSRGraph.from_coo(t)       # build + attach the int32 CSR once
-    _DEVICE_CACHE[key] = t
+    _lru_put(_DEVICE_CACHE, key, t)
     return t
