@@ -522,12 +522,43 @@ class DGG_LearnableK_debug(nn.Module):
 
     # ------------------------------------------------------------------ edge probabilities (dgm.py:1596-1727)
     def edge_prob_net(self, graph, vals, x, mode=None):
+        """Per-edge probabilities [E] in CSR order.  The E x (2h + M) concat / gather / Linear / LeakyReLU / Linear /
+        sigmoid chain of the reference becomes: node encoder (tensor cores), ONE tall GEMM for the per-node halves
+        of the first Linear, one fused per-edge kernel (``K.edge_mlp``; see include/dggb.h for the algebra)."""
         if mode == "A_uv":
             return torch.sigmoid(self.adj_project(vals.unsqueeze(-1)).flatten())
         if mode not in ("u-v-dist", "u-v-A_uv", "u-v-deg", "u-v-deg-dist", "edge_conv"):
             raise Exception("mode not found")
+        enc = self.node_encode_for_edges
+        xe = K.encoder_linear(x, enc[0].weight, enc[0].bias, enc[1].negative_slope)      # dgm.py:1609
+        h = xe.shape[1]
+        if h % 4 != 0 or vals.requires_grad:
+            return self._edge_prob_net_eager(graph, vals, xe, mode)
+        if mode == "u-v-dist":
+            return K.edge_dist_score(xe, graph, 0.05)                                      # dgm.py:1618-1623
+        if mode == "edge_conv":                                                            # dgm.py:1703-1719
+            wt, wp = self.edge_conv_theta, self.edge_conv_phi
+            p_uv = K.tall_linear(xe, torch.cat([wp.weight - wt.weight, wt.weight], dim=0))
+            return K.edge_mlp(p_uv, None, wt.bias + wp.bias, self.edge_conv_encode.weight,
+                              self.edge_conv_encode.bias, graph, flags=0, slope=1.0)
+        l1, act, l2 = self.edge_encode[0], self.edge_encode[1], self.edge_encode[2]
+        p_uv = K.tall_linear(xe, torch.cat([l1.weight[:, :h], l1.weight[:, h:2 * h]], dim=0))
+        wx = l1.weight[:, 2 * h:]
+        if mode == "u-v-A_uv":
+            return K.edge_mlp(p_uv, wx, l1.bias, l2.weight, l2.bias, graph, edge_val=vals, flags=K.EX_VAL,
+                              slope=act.negative_slope)
+        deg = K.row_sum(vals, graph)                                                       # raw degrees (1653)
+        if mode == "u-v-deg":
+            return K.edge_mlp(p_uv, wx, l1.bias, l2.weight, l2.bias, graph, deg=deg, flags=K.EX_DEG,
+                              slope=act.negative_slope)
+        return K.edge_mlp(p_uv, wx, l1.bias, l2.weight, l2.bias, graph, deg=deg, xe=xe, flags=K.EX_DEG | K.EX_DIST,
+                          slope=act.negative_slope, dist_scale=1.0)                       # u-v-deg-dist (1671-1702)
+
+    def _edge_prob_net_eager(self, graph, vals, xe, mode):
+        """The same formulas as plain tensor ops: hidden widths that are not a multiple of 4, and input adjacencies
+        whose VALUES carry gradients (``dgg_adj_input != "input_adj"``: the fused kernels treat the input graph
+        as a constant)."""
         idx = graph.coo_indices()
-        xe = self.node_encode_for_edges(x)
         u, v = xe[idx[0]], xe[idx[1]]
         if mode == "u-v-dist":
             return torch.exp(-0.05 * torch.linalg.vector_norm(u - v, dim=-1, ord=2))

@@ -144,6 +144,41 @@ int dggb_row_firstk_bwd(const int32_t* rowptr, int32_t n, const float* score, co
                         float* dk /* [N] */, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * edge_prob_net of DGG_LearnableK_debug (dgm.py:1596-1727; a8), one fused kernel per direction.
+ *
+ * The first Linear of edge_encode acts on the concatenation [x_u ; x_v ; extra], so it splits into per-NODE
+ * projections computed once by a tall GEMM (p_uv = x_enc [W1_u ; W1_v]^T, [N, ldp], u half in columns [0, w),
+ * v half in [w, 2w)) plus a per-edge rank-M update:
+ *     score_e = sigmoid( b2 + sum_c w2[c] * act( p_uv[u, c] + p_uv[v, w + c] + b1[c] + sum_m wx[c, m] extra_m(e) ) )
+ * act = LeakyReLU(slope) (slope == 1: identity).  flags select the extra features, in this order:
+ *     1 (DGGB_EX_VAL)   extra = (A_uv)                                  "u-v-A_uv"      dgm.py:1628-1644
+ *     2 (DGGB_EX_DEG)   extra = (deg[u], deg[v])                         "u-v-deg"       dgm.py:1645-1670
+ *     2|4 (.. | DIST)   extra = (deg[u], deg[v], exp(-dist_scale |xe_u - xe_v|))  "u-v-deg-dist"  1671-1702
+ *     0                 no extras: "edge_conv" with p_uv = xe [W_phi - W_theta ; W_theta]^T, b1 = b_theta + b_phi,
+ *                       slope = 1, w2 / b2 = edge_conv_encode                              dgm.py:1703-1719
+ *     8 (DGGB_DIST_ONLY) score_e = exp(-dist_scale |xe_u - xe_v|_2), nothing else is read   "u-v-dist"  1618-1623
+ * wx: [w, M] row-major (the last M columns of edge_encode.0.weight).  w, hx multiples of 4 and <= 512.
+ * bwd: g_score = dL/dscore; d_p_uv [N, ldp], d_xe [N, hx], d_wx, d_b1, d_w2, d_b2 are ACCUMULATED INTO (zero them);
+ * pre-activations are recomputed from the gathered rows, no [E, w] tensor is stored.  d_xe may be NULL (distance
+ * feature treated as a constant) except with DGGB_DIST_ONLY.
+ * ---------------------------------------------------------------------------------- */
+#define DGGB_EX_VAL 1
+#define DGGB_EX_DEG 2
+#define DGGB_EX_DIST 4
+#define DGGB_DIST_ONLY 8
+int dggb_edge_mlp_fwd(const int32_t* erow, const int32_t* col, int32_t nnz, int32_t w, int32_t ldp,
+                      const float* p_uv, const float* xe /* [N,hx] or NULL */, int32_t hx,
+                      const float* edge_val /* [E] or NULL */, const float* deg /* [N] or NULL */,
+                      const float* wx, const float* b1, const float* w2, const float* b2, float slope,
+                      float dist_scale, int32_t flags, float* score /* [E] out */, void* stream);
+int dggb_edge_mlp_bwd(const int32_t* erow, const int32_t* col, int32_t nnz, int32_t w, int32_t ldp,
+                      const float* p_uv, const float* xe, int32_t hx, const float* edge_val, const float* deg,
+                      const float* wx, const float* b1, const float* w2, const float* b2, float slope,
+                      float dist_scale, int32_t flags, const float* score, const float* g_score,
+                      float* d_p_uv, float* d_xe, float* d_wx, float* d_b1, float* d_w2, float* d_b2,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
  * normalize_adj: Ahat_ij = A_ij * s_i^-1/2 * s_j^-1/2 with s = ROW sums on both sides
  * (model.py:1215-1218, 146-149, 687-690, 1347-1350; dgm.py:1172-1175; a13, A.6).
  * Replaces diag + two dense N^3 torch.mm with O(nnz) work.

@@ -9,28 +9,12 @@
 //   bwd:  row_dk     (warp per CSR row)                    ->  edge_grad (edge-parallel, vector reds)
 // Issue/latency-bound at Pubmed size, HBM-bound at scale.  Algorithmic bytes per launch are listed in DESIGN.md.
 #include "common.cuh"
+#include "edge_common.cuh"
 #include <cstdlib>
 
 namespace dggb {
 
 constexpr int kEdgeWarps = 8;  // warps per block
-
-// Lane layout: the 32 lanes split into G = 32/L groups of L lanes.  A warp owns 32 consecutive edges;
-// group `grp` walks the PER = 32/G consecutive edges [grp*PER, (grp+1)*PER) of that chunk, and lane `lg`
-// of the group owns float4 chunks c = 4*(lg + L*t), t < T, of the H-long feature row.
-template <int T>
-struct RowSlice {
-  float4 v[T];
-};
-
-template <int T>
-__device__ __forceinline__ void load_slice(RowSlice<T>& s, const float* row, int h, int lg, int L) {
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int c = 4 * (lg + L * t);
-    s.v[t] = (c < h) ? ldg4(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
 
 // sum over this lane's chunks of LeakyReLU(y_u - y_v + be); out-of-range chunks contribute exactly 0.
 template <int T>
@@ -777,24 +761,6 @@ static void fused_grid(int nnz, int blocks_per_sm, int* blocks, int* epb) {
   if (b < 1) b = 1;
   *epb = (int)((nnz + b - 1) / b);
   *blocks = (nnz + *epb - 1) / *epb;
-}
-
-// Lanes per edge.  These kernels are issue-bound, not bandwidth-bound (ncu: 4.6 M warp instructions for 108 k edges
-// with 16 lanes x 1 float4 per edge at h = 64): four float4 chunks per lane amortise the index shuffles, address
-// arithmetic, group reduction and sigmoid over 4x more channels per instruction.
-static int lanes_per_edge(int h) {
-  int L = 1;
-  while (L < 32 && 16 * L < h) L *= 2;
-  return L;
-}
-
-template <typename F>
-static int dispatch_T(int h, int L, F&& f) {
-  const int T = (h + 4 * L - 1) / (4 * L);
-  if (T == 1) return f(std::integral_constant<int, 1>{});
-  if (T == 2) return f(std::integral_constant<int, 2>{});
-  if (T <= 4) return f(std::integral_constant<int, 4>{});
-  return DGGB_ERR_BAD_SHAPE;
 }
 
 static int edges_grid(long long nnz, int blocks_per_sm = 8) {

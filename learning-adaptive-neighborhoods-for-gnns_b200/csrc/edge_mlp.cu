@@ -1,0 +1,423 @@
+// Per-edge probability networks of DGG_LearnableK_debug.edge_prob_net (dgm.py:1596-1727), one fused kernel per
+// direction instead of  gather x[u], x[v] -> concat [E, 2h + M] -> Linear -> LeakyReLU -> Linear -> sigmoid.
+//
+// The first Linear is linear in its concatenated input, so it is split algebraically:
+//     W1 [x_u ; x_v ; extra] + b1  =  Pu[u] + Pv[v] + Wx extra + b1,      [Pu | Pv] = x_enc [W1_u ; W1_v]^T
+// ([N, 2W], ONE tall GEMM on the tensor cores instead of an E x (2h + M) x h one), and the kernel does per edge
+//     score_e = sigmoid( b2 + sum_c w2[c] * act( Pu[u,c] + Pv[v,c] + b1[c] + sum_m Wx[c,m] extra_m(e) ) )
+// with act = LeakyReLU(slope) (slope = 1: identity).  That covers
+//     u-v-A_uv      extra = (A_uv)                                   dgm.py:1628-1644
+//     u-v-deg       extra = (deg_u, deg_v)                            dgm.py:1645-1670
+//     u-v-deg-dist  extra = (deg_u, deg_v, exp(-|x_u - x_v|))          dgm.py:1671-1702
+//     edge_conv     theta(x_v - x_u) + phi(x_u) = (Phi - Theta)[u] + Theta[v], no activation, w2 = edge_conv_encode
+//                                                                    dgm.py:1703-1719
+// and, with `dist_only`, u-v-dist: score_e = exp(-dist_scale |x_u - x_v|)  (dgm.py:1618-1623).
+// HBM-bound at scale (E * (8 idx + 2 W * 4 gathered [+ 2 h * 4 for the distance]) + E * 4 out); at citation-graph
+// sizes the gathered rows are L2-resident and the kernel is issue-bound like the class-DGG edge kernels.
+// Backward: everything is recomputed from the gathered rows (no [E, W] tensor is stored); row gradients go out as
+// 128-bit vector reductions, parameter gradients are reduced per block in shared memory first.
+#include "common.cuh"
+#include "edge_common.cuh"
+
+namespace dggb {
+
+constexpr int kMlpWarps = 8;
+constexpr int kMlpMaxExtra = 3;
+
+enum : int { kExVal = 1, kExDeg = 2, kExDist = 4, kDistOnly = 8 };
+
+__device__ __forceinline__ float act_f(float v, float slope) { return v > 0.f ? v : slope * v; }
+__device__ __forceinline__ float act_g(float v, float slope) { return v > 0.f ? 1.f : slope; }
+
+struct EdgeMlpArgs {
+  const int32_t* erow;
+  const int32_t* col;
+  int nnz;
+  int w;                 // hidden width of the edge MLP (channels of Pu / Pv)
+  int ldp;               // row pitch of P (floats); Pu = P[:, 0:w], Pv = P[:, w:2w]
+  int L;                 // lanes per edge
+  const float* P;
+  const float* xe;       // [N, hx] node embeddings (distance feature) or NULL
+  int hx;
+  const float* edge_val; // [E] or NULL
+  const float* deg;      // [N] or NULL
+  const float* wx;       // [w, M] extra-feature columns of W1
+  const float* b1;       // [w]
+  const float* w2;       // [w]
+  const float* b2;       // [1]
+  float slope;
+  float dist_scale;
+  int flags;
+  int m;                 // number of extra features
+};
+
+// squared distance partial of this lane's chunks (chunks >= hx contribute 0)
+template <int T>
+__device__ __forceinline__ float dist2_partial(const RowSlice<T>& a, const RowSlice<T>& b) {
+  float z = 0.f;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float dx = a.v[t].x - b.v[t].x, dy = a.v[t].y - b.v[t].y, dz = a.v[t].z - b.v[t].z, dw = a.v[t].w - b.v[t].w;
+    z += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  return z;
+}
+
+// extras of edge e into ex[0..m): [val] | [deg_u, deg_v] | [dist feature]
+__device__ __forceinline__ void gather_extras(const EdgeMlpArgs& A, int e, int u, int v, float distf, float* ex) {
+  int m = 0;
+  if (A.flags & kExVal) ex[m++] = __ldg(A.edge_val + e);
+  if (A.flags & kExDeg) {
+    ex[m++] = __ldg(A.deg + u);
+    ex[m++] = __ldg(A.deg + v);
+  }
+  if (A.flags & kExDist) ex[m++] = distf;
+  for (; m < kMlpMaxExtra; ++m) ex[m] = 0.f;
+}
+
+template <int T>
+__global__ void __launch_bounds__(kMlpWarps* kWarp) edge_mlp_fwd_kernel(EdgeMlpArgs A, float* __restrict__ score) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
+  const int groups_total = gridDim.x * kMlpWarps * G;
+  const bool dist_only = A.flags & kDistOnly;
+  const bool need_dist = dist_only || (A.flags & kExDist);
+  RowSlice<T> b1, w2, wxm[kMlpMaxExtra];
+  if (!dist_only) {
+    load_slice<T>(b1, A.b1, A.w, lg, L);
+    load_slice<T>(w2, A.w2, A.w, lg, L);
+#pragma unroll
+    for (int m = 0; m < kMlpMaxExtra; ++m)
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int c = 4 * (lg + L * t);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < A.m && c < A.w)
+          q = make_float4(__ldg(A.wx + (c + 0) * A.m + m), __ldg(A.wx + (c + 1) * A.m + m),
+                          __ldg(A.wx + (c + 2) * A.m + m), __ldg(A.wx + (c + 3) * A.m + m));
+        wxm[m].v[t] = q;
+      }
+  }
+  const float b2 = dist_only ? 0.f : __ldg(A.b2);
+  // contiguous runs of edges per group: consecutive edges share their source row (CSR order)
+  const long long per = ((long long)A.nnz + groups_total - 1) / groups_total;
+  const long long gid = (long long)(blockIdx.x * kMlpWarps + (threadIdx.x >> 5)) * G + grp;
+  const long long e0 = gid * per;
+#pragma unroll 2
+  for (long long it = 0; it < per; ++it) {
+    const long long e = e0 + it;
+    const bool valid = e < A.nnz;                      // group-uniform
+    const int ee = valid ? (int)e : 0;
+    const int u = valid ? __ldg(A.erow + ee) : 0, v = valid ? __ldg(A.col + ee) : 0;
+    float distf = 0.f;
+    if (need_dist) {
+      RowSlice<T> xu, xv;
+      load_slice<T>(xu, A.xe + (size_t)u * A.hx, A.hx, lg, L);
+      load_slice<T>(xv, A.xe + (size_t)v * A.hx, A.hx, lg, L);
+      const float d2 = group_sum(dist2_partial<T>(xu, xv), L);
+      distf = expf(-A.dist_scale * sqrtf(d2));
+    }
+    float out;
+    if (dist_only) {
+      out = distf;
+    } else {
+      float ex[kMlpMaxExtra];
+      gather_extras(A, ee, u, v, distf, ex);
+      RowSlice<T> pu, pv;
+      load_slice<T>(pu, A.P + (size_t)u * A.ldp, A.w, lg, L);
+      load_slice<T>(pv, A.P + (size_t)v * A.ldp + A.w, A.w, lg, L);
+      float z = 0.f;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        float4 pre;
+        pre.x = pu.v[t].x + pv.v[t].x + b1.v[t].x;
+        pre.y = pu.v[t].y + pv.v[t].y + b1.v[t].y;
+        pre.z = pu.v[t].z + pv.v[t].z + b1.v[t].z;
+        pre.w = pu.v[t].w + pv.v[t].w + b1.v[t].w;
+#pragma unroll
+        for (int m = 0; m < kMlpMaxExtra; ++m) {
+          pre.x = fmaf(wxm[m].v[t].x, ex[m], pre.x);
+          pre.y = fmaf(wxm[m].v[t].y, ex[m], pre.y);
+          pre.z = fmaf(wxm[m].v[t].z, ex[m], pre.z);
+          pre.w = fmaf(wxm[m].v[t].w, ex[m], pre.w);
+        }
+        z += w2.v[t].x * act_f(pre.x, A.slope) + w2.v[t].y * act_f(pre.y, A.slope) +
+             w2.v[t].z * act_f(pre.z, A.slope) + w2.v[t].w * act_f(pre.w, A.slope);
+      }
+      out = sigmoidf_(group_sum(z, L) + b2);
+    }
+    if (valid && lg == 0) score[ee] = out;
+  }
+}
+
+struct EdgeMlpGrads {
+  const float* score;    // [E] forward output
+  const float* g;        // [E] dL/dscore
+  float* dP;             // [N, ldp] accumulated into (NULL with dist_only)
+  float* dxe;            // [N, hx] accumulated into, or NULL
+  float* dwx;            // [w, M]
+  float* db1;            // [w]
+  float* dw2;            // [w]
+  float* db2;            // [1]
+};
+
+template <int T>
+__global__ void __launch_bounds__(kMlpWarps* kWarp) edge_mlp_bwd_kernel(EdgeMlpArgs A, EdgeMlpGrads Gd) {
+  pdl_trigger();
+  // block-level accumulators: [db1 (w) | dw2 (w) | dwx (w * 3) | db2]
+  extern __shared__ float acc_s[];
+  const int W = A.w;
+  for (int c = threadIdx.x; c < 5 * W + 1; c += blockDim.x) acc_s[c] = 0.f;
+  pdl_wait();
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
+  const int groups_total = gridDim.x * kMlpWarps * G;
+  const bool dist_only = A.flags & kDistOnly;
+  const bool need_dist = dist_only || (A.flags & kExDist);
+  const int m_dist = A.m - 1;      // the distance feature is always the last extra
+  RowSlice<T> b1, w2, wxm[kMlpMaxExtra], db1a, dw2a, dwxa[kMlpMaxExtra], accu;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    db1a.v[t] = dw2a.v[t] = accu.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < kMlpMaxExtra; ++m) dwxa[m].v[t] = wxm[m].v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    b1.v[t] = w2.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (!dist_only) {
+    load_slice<T>(b1, A.b1, W, lg, L);
+    load_slice<T>(w2, A.w2, W, lg, L);
+#pragma unroll
+    for (int m = 0; m < kMlpMaxExtra; ++m)
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int c = 4 * (lg + L * t);
+        if (m < A.m && c < W)
+          wxm[m].v[t] = make_float4(__ldg(A.wx + (c + 0) * A.m + m), __ldg(A.wx + (c + 1) * A.m + m),
+                                    __ldg(A.wx + (c + 2) * A.m + m), __ldg(A.wx + (c + 3) * A.m + m));
+      }
+  }
+  float db2a = 0.f;
+  const long long per = ((long long)A.nnz + groups_total - 1) / groups_total;
+  const long long gid = (long long)(blockIdx.x * kMlpWarps + (threadIdx.x >> 5)) * G + grp;
+  const long long e0 = gid * per;
+  int cur_u = -1;                  // source row whose dPu contributions are being accumulated in `accu`
+  auto flush_u = [&]() {
+    if (cur_u >= 0) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int c = 4 * (lg + L * t);
+        if (c < W) red_add4(Gd.dP + (size_t)cur_u * A.ldp + c, accu.v[t]);
+        accu.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
+  for (long long it = 0; it < per; ++it) {
+    const long long e = e0 + it;
+    const bool valid = e < A.nnz;
+    const int ee = valid ? (int)e : 0;
+    const int u = valid ? __ldg(A.erow + ee) : 0, v = valid ? __ldg(A.col + ee) : 0;
+    const float sc = valid ? __ldg(Gd.score + ee) : 0.f;
+    const float g = valid ? __ldg(Gd.g + ee) : 0.f;
+    RowSlice<T> xu, xv;
+    float distf = 0.f, dist = 0.f;
+    if (need_dist) {
+      load_slice<T>(xu, A.xe + (size_t)u * A.hx, A.hx, lg, L);
+      load_slice<T>(xv, A.xe + (size_t)v * A.hx, A.hx, lg, L);
+      dist = sqrtf(group_sum(dist2_partial<T>(xu, xv), L));
+      distf = expf(-A.dist_scale * dist);
+    }
+    float d_distf = 0.f;           // dL / d(exp(-scale * dist))
+    if (dist_only) {
+      d_distf = g;
+    } else {
+      float ex[kMlpMaxExtra];
+      gather_extras(A, ee, u, v, distf, ex);
+      RowSlice<T> pu, pv;
+      load_slice<T>(pu, A.P + (size_t)u * A.ldp, W, lg, L);
+      load_slice<T>(pv, A.P + (size_t)v * A.ldp + W, W, lg, L);
+      const float ds = g * sc * (1.f - sc);            // through the sigmoid
+      db2a += (lg == 0) ? ds : 0.f;
+      if (valid && u != cur_u) {
+        flush_u();
+        cur_u = u;
+      }
+      float dd = 0.f;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int c = 4 * (lg + L * t);
+        float pre[4] = {pu.v[t].x + pv.v[t].x + b1.v[t].x, pu.v[t].y + pv.v[t].y + b1.v[t].y,
+                        pu.v[t].z + pv.v[t].z + b1.v[t].z, pu.v[t].w + pv.v[t].w + b1.v[t].w};
+        const float wxv[kMlpMaxExtra][4] = {{wxm[0].v[t].x, wxm[0].v[t].y, wxm[0].v[t].z, wxm[0].v[t].w},
+                                            {wxm[1].v[t].x, wxm[1].v[t].y, wxm[1].v[t].z, wxm[1].v[t].w},
+                                            {wxm[2].v[t].x, wxm[2].v[t].y, wxm[2].v[t].z, wxm[2].v[t].w}};
+        const float w2v[4] = {w2.v[t].x, w2.v[t].y, w2.v[t].z, w2.v[t].w};
+        float dpre[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int m = 0; m < kMlpMaxExtra; ++m) pre[q] = fmaf(wxv[m][q], ex[m], pre[q]);
+          dpre[q] = ds * w2v[q] * act_g(pre[q], A.slope);
+        }
+        dw2a.v[t].x += ds * act_f(pre[0], A.slope); dw2a.v[t].y += ds * act_f(pre[1], A.slope);
+        dw2a.v[t].z += ds * act_f(pre[2], A.slope); dw2a.v[t].w += ds * act_f(pre[3], A.slope);
+        db1a.v[t].x += dpre[0]; db1a.v[t].y += dpre[1]; db1a.v[t].z += dpre[2]; db1a.v[t].w += dpre[3];
+#pragma unroll
+        for (int m = 0; m < kMlpMaxExtra; ++m) {
+          dwxa[m].v[t].x += dpre[0] * ex[m]; dwxa[m].v[t].y += dpre[1] * ex[m];
+          dwxa[m].v[t].z += dpre[2] * ex[m]; dwxa[m].v[t].w += dpre[3] * ex[m];
+        }
+        if (A.flags & kExDist)
+          dd += dpre[0] * wxv[kMlpMaxExtra - 1][0] * 0.f;   // placeholder keeps the unrolled shape; real sum below
+        accu.v[t].x += dpre[0]; accu.v[t].y += dpre[1]; accu.v[t].z += dpre[2]; accu.v[t].w += dpre[3];
+        if (valid && c < W) red_add4(Gd.dP + (size_t)v * A.ldp + W + c, make_float4(dpre[0], dpre[1], dpre[2], dpre[3]));
+        if (A.flags & kExDist) {
+          // d distf += sum_c dpre_c * Wx[c, m_dist]; m_dist is runtime (1 for u-v-A_uv never has dist; 2 for deg-dist)
+          const float* wd = (m_dist == 0) ? wxv[0] : (m_dist == 1 ? wxv[1] : wxv[2]);
+          dd += dpre[0] * wd[0] + dpre[1] * wd[1] + dpre[2] * wd[2] + dpre[3] * wd[3];
+        }
+      }
+      if (A.flags & kExDist) d_distf = group_sum(dd, L);
+    }
+    if (need_dist && Gd.dxe != nullptr) {
+      // distf = exp(-scale * dist): d dist = -scale * distf * d_distf;  d x_u = d dist * (x_u - x_v) / dist (0 at dist == 0)
+      const float coef = (valid && dist > 0.f) ? (-A.dist_scale * distf * d_distf) / dist : 0.f;
+      if (coef != 0.f) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < A.hx) {
+            const float4 d = make_float4(coef * (xu.v[t].x - xv.v[t].x), coef * (xu.v[t].y - xv.v[t].y),
+                                         coef * (xu.v[t].z - xv.v[t].z), coef * (xu.v[t].w - xv.v[t].w));
+            red_add4(Gd.dxe + (size_t)u * A.hx + c, d);
+            red_add4(Gd.dxe + (size_t)v * A.hx + c, make_float4(-d.x, -d.y, -d.z, -d.w));
+          }
+        }
+      }
+    }
+  }
+  if (!dist_only) {
+    flush_u();
+    // combine the G groups of the warp, then one shared-memory atomic per channel per warp
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      auto fold = [&](float4& q) {
+        for (int o = L; o < kWarp; o <<= 1) {
+          q.x += __shfl_xor_sync(0xffffffffu, q.x, o); q.y += __shfl_xor_sync(0xffffffffu, q.y, o);
+          q.z += __shfl_xor_sync(0xffffffffu, q.z, o); q.w += __shfl_xor_sync(0xffffffffu, q.w, o);
+        }
+      };
+      fold(db1a.v[t]);
+      fold(dw2a.v[t]);
+#pragma unroll
+      for (int m = 0; m < kMlpMaxExtra; ++m) fold(dwxa[m].v[t]);
+      const int c = 4 * (lg + L * t);
+      if (grp == 0 && c < W) {
+        const float b[4] = {db1a.v[t].x, db1a.v[t].y, db1a.v[t].z, db1a.v[t].w};
+        const float w[4] = {dw2a.v[t].x, dw2a.v[t].y, dw2a.v[t].z, dw2a.v[t].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          atomicAdd(&acc_s[c + q], b[q]);
+          atomicAdd(&acc_s[W + c + q], w[q]);
+        }
+#pragma unroll
+        for (int m = 0; m < kMlpMaxExtra; ++m) {
+          const float x[4] = {dwxa[m].v[t].x, dwxa[m].v[t].y, dwxa[m].v[t].z, dwxa[m].v[t].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) atomicAdd(&acc_s[2 * W + (c + q) * kMlpMaxExtra + m], x[q]);
+        }
+      }
+    }
+    db2a = warp_sum(db2a);
+    if (lane == 0) atomicAdd(&acc_s[5 * W], db2a);
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+      atomicAdd(Gd.db1 + c, acc_s[c]);
+      atomicAdd(Gd.dw2 + c, acc_s[W + c]);
+      for (int m = 0; m < A.m; ++m) atomicAdd(Gd.dwx + c * A.m + m, acc_s[2 * W + c * kMlpMaxExtra + m]);
+    }
+    if (threadIdx.x == 0) atomicAdd(Gd.db2, acc_s[5 * W]);
+  }
+}
+
+static int mlp_grid(long long nnz, int L, int blocks_per_sm) {
+  const int G = kWarp / L;
+  long long need = (nnz + (long long)kMlpWarps * G * 4 - 1) / ((long long)kMlpWarps * G * 4);   // >= 4 edges per group
+  long long cap = (long long)kNumSMs * (blocks_per_sm < 1 ? 1 : blocks_per_sm);
+  long long g = need < cap ? need : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+static int check_mlp_args(const EdgeMlpArgs& A) {
+  if (!A.erow || !A.col || A.nnz < 0) return DGGB_ERR_BAD_ARG;
+  const bool dist_only = A.flags & kDistOnly;
+  if (A.flags & ~(kExVal | kExDeg | kExDist | kDistOnly)) return DGGB_ERR_UNSUPPORTED;
+  int m = ((A.flags & kExVal) ? 1 : 0) + ((A.flags & kExDeg) ? 2 : 0) + ((A.flags & kExDist) ? 1 : 0);
+  if (dist_only) {
+    if (A.flags != kDistOnly) return DGGB_ERR_UNSUPPORTED;
+    if (!A.xe || A.hx <= 0) return DGGB_ERR_BAD_ARG;
+    if (A.hx % 4 != 0 || A.hx > 512) return DGGB_ERR_BAD_SHAPE;
+    return DGGB_OK;
+  }
+  if (m != A.m || m > kMlpMaxExtra) return DGGB_ERR_BAD_ARG;
+  if (!A.P || !A.b1 || !A.w2 || !A.b2 || A.w <= 0 || (m > 0 && !A.wx)) return DGGB_ERR_BAD_ARG;
+  if (((A.flags & kExVal) && !A.edge_val) || ((A.flags & kExDeg) && !A.deg)) return DGGB_ERR_BAD_ARG;
+  if ((A.flags & kExDist) && (!A.xe || A.hx <= 0)) return DGGB_ERR_BAD_ARG;
+  if (A.w % 4 != 0 || A.w > 512 || A.ldp % 4 != 0 || A.ldp < 2 * A.w || ((uintptr_t)A.P % 16)) return DGGB_ERR_BAD_SHAPE;
+  if ((A.flags & kExDist) && (A.hx % 4 != 0 || A.hx > A.w * 1 + 0 && A.hx > 512)) return DGGB_ERR_BAD_SHAPE;
+  return DGGB_OK;
+}
+
+}  // namespace dggb
+using namespace dggb;
+
+extern "C" int dggb_edge_mlp_fwd(const int32_t* erow, const int32_t* col, int32_t nnz, int32_t w, int32_t ldp,
+                                 const float* p_uv, const float* xe, int32_t hx, const float* edge_val,
+                                 const float* deg, const float* wx, const float* b1, const float* w2,
+                                 const float* b2, float slope, float dist_scale, int32_t flags, float* score,
+                                 void* stream) {
+  EdgeMlpArgs A{erow, col, nnz, w, ldp, 1, p_uv, xe, hx, edge_val, deg, wx, b1, w2, b2, slope, dist_scale, flags, 0};
+  A.m = ((flags & kExVal) ? 1 : 0) + ((flags & kExDeg) ? 2 : 0) + ((flags & kExDist) ? 1 : 0);
+  int rc = check_mlp_args(A);
+  if (rc != DGGB_OK) return rc;
+  if (!score) return DGGB_ERR_BAD_ARG;
+  if (nnz == 0) return DGGB_OK;
+  const int width = (flags & kDistOnly) ? hx : (w > hx ? w : hx);
+  A.L = lanes_per_edge(width);
+  return dispatch_T(width, A.L, [&](auto tc) {
+    auto kern = edge_mlp_fwd_kernel<decltype(tc)::value>;
+    const int grid = mlp_grid(nnz, A.L, resident_blocks(kern, kMlpWarps * kWarp));
+    launch_pdl(kern, dim3(grid), dim3(kMlpWarps * kWarp), 0, as_stream(stream), A, score);
+    return launch_status();
+  });
+}
+
+extern "C" int dggb_edge_mlp_bwd(const int32_t* erow, const int32_t* col, int32_t nnz, int32_t w, int32_t ldp,
+                                 const float* p_uv, const float* xe, int32_t hx, const float* edge_val,
+                                 const float* deg, const float* wx, const float* b1, const float* w2,
+                                 const float* b2, float slope, float dist_scale, int32_t flags, const float* score,
+                                 const float* g_score, float* d_p_uv, float* d_xe, float* d_wx, float* d_b1,
+                                 float* d_w2, float* d_b2, void* stream) {
+  EdgeMlpArgs A{erow, col, nnz, w, ldp, 1, p_uv, xe, hx, edge_val, deg, wx, b1, w2, b2, slope, dist_scale, flags, 0};
+  A.m = ((flags & kExVal) ? 1 : 0) + ((flags & kExDeg) ? 2 : 0) + ((flags & kExDist) ? 1 : 0);
+  int rc = check_mlp_args(A);
+  if (rc != DGGB_OK) return rc;
+  if (!score || !g_score) return DGGB_ERR_BAD_ARG;
+  const bool dist_only = flags & kDistOnly;
+  if (!dist_only && (!d_p_uv || !d_b1 || !d_w2 || !d_b2 || (A.m > 0 && !d_wx))) return DGGB_ERR_BAD_ARG;
+  if (dist_only && !d_xe) return DGGB_ERR_BAD_ARG;
+  if (nnz == 0) return DGGB_OK;
+  const int width = dist_only ? hx : (w > hx ? w : hx);
+  A.L = lanes_per_edge(width);
+  if (dist_only) A.w = 0;
+  EdgeMlpGrads Gd{score, g_score, d_p_uv, d_xe, d_wx, d_b1, d_w2, d_b2};
+  return dispatch_T(width, A.L, [&](auto tc) {
+    auto kern = edge_mlp_bwd_kernel<decltype(tc)::value>;
+    const size_t smem = (size_t)(5 * A.w + 1) * sizeof(float);
+    const int grid = mlp_grid(nnz, A.L, resident_blocks(kern, kMlpWarps * kWarp, smem));
+    launch_pdl(kern, dim3(grid), dim3(kMlpWarps * kWarp), smem, as_stream(stream), A, Gd);
+    return launch_status();
+  });
+}

@@ -254,6 +254,104 @@ def row_firstk(score, k, graph, k_only=False, return_rank=False):
     return (out, rank) if return_rank else out
 
 
+EX_VAL, EX_DEG, EX_DIST, DIST_ONLY = 1, 2, 4, 8
+
+
+class _EdgeMLP(torch.autograd.Function):
+    """edge_prob_net of DGG_LearnableK_debug on CSR entries (dgm.py:1596-1727); see include/dggb.h."""
+
+    @staticmethod
+    def forward(ctx, p_uv, xe, wx, b1, w2, b2, graph: CSRGraph, edge_val, deg, flags: int, slope: float,
+                dist_scale: float):
+        dist_only = bool(flags & DIST_ONLY)
+        _require_cuda(p_uv, xe, edge_val, deg)
+        if dist_only:
+            xe = _f32c(xe)
+            w, ldp = 0, 0
+        else:
+            p_uv, b1, w2, b2 = _f32c(p_uv), _f32c(b1).reshape(-1), _f32c(w2).reshape(-1), _f32c(b2).reshape(-1)
+            w, ldp = b1.numel(), p_uv.shape[1]
+            wx = None if wx is None or wx.numel() == 0 else _f32c(wx)
+            xe = None if xe is None else _f32c(xe)
+        edge_val = None if edge_val is None else _f32c(edge_val)
+        deg = None if deg is None else _f32c(deg).reshape(-1)
+        hx = 0 if xe is None else xe.shape[1]
+        dev = (xe if dist_only else p_uv).device
+        score = torch.empty(graph.nnz, dtype=torch.float32, device=dev)
+        check(lib().dggb_edge_mlp_fwd(p(graph.erow), p(graph.col), i32(graph.nnz), i32(w), i32(ldp), p(p_uv), p(xe),
+                                      i32(hx), p(edge_val), p(deg), p(wx), p(b1), p(w2), p(b2), float(slope),
+                                      float(dist_scale), i32(flags), p(score), stream()), "edge_mlp_fwd")
+        ctx.graph, ctx.meta = graph, (flags, slope, dist_scale, w, ldp, hx)
+        ctx.save_for_backward(p_uv, xe, wx, b1, w2, b2, edge_val, deg, score)
+        return score
+
+    @staticmethod
+    def backward(ctx, g):
+        p_uv, xe, wx, b1, w2, b2, edge_val, deg, score = ctx.saved_tensors
+        flags, slope, dist_scale, w, ldp, hx = ctx.meta
+        gr = ctx.graph
+        dist_only = bool(flags & DIST_ONLY)
+        dev = score.device
+        need_xe = xe is not None and ctx.needs_input_grad[1]
+        d_xe = torch.zeros_like(xe) if need_xe else None
+        if dist_only:
+            d_p = d_wx = d_b1 = d_w2 = d_b2 = None
+        else:
+            m = 0 if wx is None else wx.shape[1]
+            d_p = torch.zeros_like(p_uv)
+            small = torch.zeros(w * (2 + m) + 1, dtype=torch.float32, device=dev)
+            d_b1, d_w2, d_b2 = small[:w], small[w:2 * w], small[2 * w + w * m:]
+            d_wx = small[2 * w:2 * w + w * m].view(w, m) if m else None
+        check(lib().dggb_edge_mlp_bwd(p(gr.erow), p(gr.col), i32(gr.nnz), i32(w), i32(ldp), p(p_uv), p(xe), i32(hx),
+                                      p(edge_val), p(deg), p(wx), p(b1), p(w2), p(b2), float(slope),
+                                      float(dist_scale), i32(flags), p(score), p(_f32c(g)), p(d_p), p(d_xe), p(d_wx),
+                                      p(d_b1), p(d_w2), p(d_b2), stream()), "edge_mlp_bwd")
+        return d_p, d_xe, d_wx, d_b1, d_w2, d_b2, None, None, None, None, None, None
+
+
+def edge_mlp(p_uv, wx, b1, w2, b2, graph, edge_val=None, deg=None, xe=None, flags=0, slope=0.01, dist_scale=1.0):
+    """score_e = sigmoid(b2 + w2 . act(p_uv[u, :w] + p_uv[v, w:] + b1 + wx extra_e)); extras per ``flags``
+    (EX_VAL: edge_val, EX_DEG: deg[u], deg[v], EX_DIST: exp(-dist_scale |xe_u - xe_v|)).  Differentiable in p_uv, xe
+    and the weights; edge_val / deg are constants (the input graph)."""
+    return _EdgeMLP.apply(p_uv, xe, wx, b1, w2, b2, graph, edge_val, deg, int(flags), float(slope), float(dist_scale))
+
+
+def edge_dist_score(xe, graph, dist_scale):
+    """score_e = exp(-dist_scale |xe_u - xe_v|_2)  ("u-v-dist", dgm.py:1618-1623)."""
+    return _EdgeMLP.apply(None, xe, None, None, None, None, graph, None, None, DIST_ONLY, 1.0, float(dist_scale))
+
+
+_PAD_CACHE = {}
+
+
+def pad_features(x):
+    """[N, F] -> [N, ceil4(F)] zero-padded copy, made ONCE per feature tensor (node features are static across
+    epochs): the TMA-fed tensor-core encoder needs 16-byte row pitches (Cora F = 1433, Citeseer F = 3703).  The
+    source tensor is kept alive by the cache so its address cannot be recycled; 4 slots."""
+    f = x.shape[1]
+    if f % 4 == 0 or x.requires_grad:
+        return x
+    key = (x.data_ptr(), tuple(x.shape), x._version, x.dtype)
+    hit = _PAD_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    xp = torch.nn.functional.pad(x, (0, 4 - f % 4)).contiguous()
+    if len(_PAD_CACHE) >= 4:
+        _PAD_CACHE.pop(next(iter(_PAD_CACHE)))
+    _PAD_CACHE[key] = (xp, x)
+    return xp
+
+
+def encoder_linear(x, w, b, slope):
+    """LeakyReLU_slope(x W^T + b) for the tall node encoders: on tcgen05 also when F % 4 != 0 (features padded once,
+    weight padded per call -- it is [h, F], tiny)."""
+    f = x.shape[1]
+    if f % 4 != 0 and x.is_cuda and not x.requires_grad:
+        x = pad_features(x)
+        w = torch.nn.functional.pad(w, (0, x.shape[1] - f))
+    return tall_linear(x, w, b, slope)
+
+
 def row_sum(vals, graph):
     """Row sums of a CSR matrix (in_adj.to_dense().sum(-1), dgm.py:1568) without densifying."""
     ones = torch.ones(graph.n, 1, dtype=torch.float32, device=vals.device)

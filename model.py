@@ -389,6 +389,25 @@ class _GATPlan:
         self.graph = graph
 
 
+def _edge_list_plan(edge_list, n):
+    """Plan of the plain ``GATConv``: the (coalesced) edge list IS the structure; cached on the edge tensor's
+    identity like ``_gat_plan``."""
+    key = (edge_list.data_ptr(), edge_list.shape[1], n, edge_list._version)
+    hit = _EDGE_PLANS.get(key)
+    if hit is not None:
+        return hit[0]
+    order = torch.argsort(edge_list[0] * n + edge_list[1])
+    graph = CSRGraph.from_indices(edge_list[:, order].contiguous(), n)
+    plan = _GATPlan(edge_list, graph)
+    if len(_EDGE_PLANS) >= 8:
+        _EDGE_PLANS.clear()
+    _EDGE_PLANS[key] = (plan, edge_list)     # the tensor is kept alive: its address cannot be recycled while cached
+    return plan
+
+
+_EDGE_PLANS = {}
+
+
 def _gat_plan(edge_list, adj):
     graph, vals = CSRGraph.from_coo(adj)
     cache = getattr(adj, "_gat_plan", None)
@@ -435,17 +454,27 @@ class GATConv_DGG(nn.Module):
         nn.init.xavier_uniform_(self.a.data, gain=1.414)
 
     def forward(self, x, edge_list, adj):
+        return self._attend(x, edge_list, adj)
+
+    def _attend(self, x, edge_list, adj):
+        """adj = the DGG adjacency (dense-background softmax, model.py:565-569) or None (plain ``GATConv``:
+        logits are -1e20 off the edge list, a true masked softmax, model.py:519-522)."""
         x = F.dropout(x, self.dropout, training=self.training)
         h = torch.matmul(x, self.weight)
         n, f = h.shape
-        plan, avals = _gat_plan(edge_list, adj)
+        background = adj is not None
+        if background:
+            plan, avals = _gat_plan(edge_list, adj)
+        else:
+            plan, avals = _edge_list_plan(edge_list, n), None
         # e_ij = LeakyReLU(a^T [h_i || h_j]) = LeakyReLU(p_i + q_j): two N-vectors instead of an E x 2F gather
         pq = torch.mm(h, torch.cat([self.a[:f], self.a[f:]], dim=1))                       # [N,2]
         src, dst = edge_list[0][plan.e_sel], edge_list[1][plan.e_sel]
         e = F.leaky_relu(pq[src, 0] + pq[dst, 1], negative_slope=self.alpha)
-        s = e * avals[plan.a_sel]
-        m = torch.zeros(n, device=h.device).scatter_reduce(0, plan.rows_a, s.detach(), "amax", include_self=True)
-        em = torch.exp(-m)
+        s = e * avals[plan.a_sel] if background else e
+        floor = torch.zeros(n, device=h.device) if background else torch.full((n,), -1e30, device=h.device)
+        m = floor.scatter_reduce(0, plan.rows_a, s.detach(), "amax", include_self=True)
+        em = torch.exp(-m) if background else torch.zeros(n, device=h.device)
         w = torch.exp(s - m[plan.rows_a]) - em[plan.rows_a]
         hd = F.dropout(h, self.dropout, training=self.training)
         if self.training and self.dropout > 0:
