@@ -206,6 +206,30 @@ int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, const float* va
                       float* dval, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * GATConv_DGG (model.py:534-577; a19) and GATConv (model.py:489-531) aggregation, all heads in one
+ * launch.  hd [N, ldh]: head k owns columns [k F, (k+1) F); pq [N, heads, 2] = (h_i . a[:F], h_i . a[F:]);
+ * the CSR (rowptr, col) is the listed edge set, adj_val [E] the DGG weights A_ij on it (NULL: 1).
+ *   s_e = LeakyReLU_alpha(p_i + q_j) * A_ij ;  m_i = max(0, max_e s_e) ;  x_e = exp(s_e - m_i) ;  em_i = exp(-m_i)
+ *   Z_i = sum_e (x_e - em_i) + bg_count * em_i
+ *   out_i = [ sum_e (keep_e x_e - em_i) hd_j + em_i htot ] / Z_i + bias
+ * -- the closed form of the reference's DENSE softmax: its mask is applied by multiplication, so a non-listed pair
+ * has logit -1e20 * 0 = -0.0 and every row's softmax runs over all bg_count = N columns.  bg_count == 0 is the plain
+ * masked softmax of GATConv (em := 0, m_i = max_e s_e).  keep [heads, E] (NULL: 1): attention-dropout multipliers
+ * on the listed entries (the background keeps its expectation).  htot [heads F] = column sums of hd.
+ * F % 4 == 0, F <= 512.  m_out / z_out [N, heads] are saved for the backward.
+ * bwd: d_hd [N, ldh], d_pq [N, heads, 2], d_adj_val [E] (or NULL), d_htot [heads F] (or NULL) ACCUMULATED INTO.
+ * ---------------------------------------------------------------------------------- */
+int dggb_gat_aggregate_fwd(const int32_t* rowptr, const int32_t* col, int32_t n, int64_t nnz, int32_t heads,
+                           int32_t f, const float* hd, int32_t ldh, const float* pq, const float* adj_val,
+                           const float* keep, const float* htot, const float* bias, float alpha, float bg_count,
+                           float* out /* [N, ldo] */, int32_t ldo, float* m_out, float* z_out, void* stream);
+int dggb_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* col, int32_t n, int64_t nnz, int32_t heads,
+                           int32_t f, const float* hd, int32_t ldh, const float* pq, const float* adj_val,
+                           const float* keep, const float* bias, float alpha, float bg_count, const float* out,
+                           const float* g_out, int32_t ldo, const float* m_in, const float* z_in, float* d_hd,
+                           float* d_pq, float* d_adj_val, float* d_htot, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)
  * -- nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126 and the
  * y = x_enc We^T product.  tcgen05 tensor cores with an in-kernel 3xTF32 split (fp32-level

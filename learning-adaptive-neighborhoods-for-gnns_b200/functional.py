@@ -352,6 +352,51 @@ def encoder_linear(x, w, b, slope):
     return tall_linear(x, w, b, slope)
 
 
+class _GatAggregate(torch.autograd.Function):
+    """GATConv_DGG / GATConv attention + aggregation for all heads (model.py:556-577); see include/dggb.h."""
+
+    @staticmethod
+    def forward(ctx, hd, pq, avals, htot, bias, graph: CSRGraph, heads: int, f: int, alpha: float, bg: float, keep):
+        _require_cuda(hd, pq, avals, htot, bias, keep)
+        hd, pq = _f32c(hd), _f32c(pq)
+        avals = None if avals is None else _f32c(avals)
+        htot = None if htot is None else _f32c(htot).reshape(-1)
+        bias = None if bias is None else _f32c(bias).reshape(-1)
+        keep = None if keep is None else _f32c(keep)
+        n = graph.n
+        out = torch.empty(n, heads * f, dtype=torch.float32, device=hd.device)
+        mz = torch.empty(2, n, heads, dtype=torch.float32, device=hd.device)
+        check(lib().dggb_gat_aggregate_fwd(p(graph.rowptr), p(graph.col), i32(n), i64(graph.nnz), i32(heads), i32(f),
+                                           p(hd), i32(hd.shape[1]), p(pq), p(avals), p(keep), p(htot), p(bias),
+                                           float(alpha), float(bg), p(out), i32(out.shape[1]), p(mz[0]), p(mz[1]),
+                                           stream()), "gat_aggregate_fwd")
+        ctx.graph, ctx.meta = graph, (heads, f, alpha, bg)
+        ctx.save_for_backward(hd, pq, avals, htot, bias, keep, out, mz)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        hd, pq, avals, htot, bias, keep, out, mz = ctx.saved_tensors
+        heads, f, alpha, bg = ctx.meta
+        gr = ctx.graph
+        g = _f32c(g)
+        d_hd = torch.zeros_like(hd)
+        d_pq = torch.zeros_like(pq)
+        d_av = torch.zeros_like(avals) if (avals is not None and ctx.needs_input_grad[2]) else None
+        d_ht = torch.zeros_like(htot) if (htot is not None and ctx.needs_input_grad[3]) else None
+        check(lib().dggb_gat_aggregate_bwd(p(gr.rowptr), p(gr.col), i32(gr.n), i64(gr.nnz), i32(heads), i32(f), p(hd),
+                                           i32(hd.shape[1]), p(pq), p(avals), p(keep), p(bias), float(alpha),
+                                           float(bg), p(out), p(g), i32(out.shape[1]), p(mz[0]), p(mz[1]), p(d_hd),
+                                           p(d_pq), p(d_av), p(d_ht), stream()), "gat_aggregate_bwd")
+        d_bias = g.sum(0) if (bias is not None and ctx.needs_input_grad[4]) else None
+        return d_hd, d_pq, d_av, d_ht, d_bias, None, None, None, None, None, None
+
+
+def gat_aggregate(hd, pq, graph, heads, f, avals=None, htot=None, bias=None, alpha=0.2, bg=0.0, keep=None):
+    """-> out [N, heads * f].  hd [N, heads * f] (head k in columns [k f, (k + 1) f)), pq [N, heads, 2]."""
+    return _GatAggregate.apply(hd, pq, avals, htot, bias, graph, int(heads), int(f), float(alpha), float(bg), keep)
+
+
 def row_sum(vals, graph):
     """Row sums of a CSR matrix (in_adj.to_dense().sum(-1), dgm.py:1568) without densifying."""
     ones = torch.ones(graph.n, 1, dtype=torch.float32, device=vals.device)

@@ -16,7 +16,7 @@ from ._lib import check, i32, i64, lib, p, stream
 class CSRGraph:
     """rowptr int32 [n+1], col int32 [nnz]; rows sorted by column (coalesced COO order)."""
 
-    __slots__ = ("n", "nnz", "rowptr", "col", "indices", "_loops", "_erow", "_max_row_nnz")
+    __slots__ = ("n", "nnz", "rowptr", "col", "indices", "_loops", "_erow", "_max_row_nnz", "aux")
 
     def __init__(self, n, rowptr, col, indices=None):
         self.n = int(n)
@@ -27,6 +27,7 @@ class CSRGraph:
         self._loops = None
         self._erow = None
         self._max_row_nnz = None
+        self.aux = {}   # per-structure caches of the consumers (e.g. GAT edge-list plans), alive as long as the graph
 
     @property
     def erow(self) -> torch.Tensor:

@@ -389,36 +389,85 @@ class _GATPlan:
         self.graph = graph
 
 
-def _edge_list_plan(edge_list, n):
-    """Plan of the plain ``GATConv``: the (coalesced) edge list IS the structure; cached on the edge tensor's
-    identity like ``_gat_plan``."""
-    key = (edge_list.data_ptr(), edge_list.shape[1], n, edge_list._version)
-    hit = _EDGE_PLANS.get(key)
+_EDGE_CACHE = {}
+
+
+def _cached(cache, key, keep_alive, build, slots=8):
+    """Small identity-keyed cache: the key tensors are kept alive so their addresses cannot be recycled."""
+    hit = cache.get(key)
     if hit is not None:
         return hit[0]
-    order = torch.argsort(edge_list[0] * n + edge_list[1])
-    graph = CSRGraph.from_indices(edge_list[:, order].contiguous(), n)
-    plan = _GATPlan(edge_list, graph)
-    if len(_EDGE_PLANS) >= 8:
-        _EDGE_PLANS.clear()
-    _EDGE_PLANS[key] = (plan, edge_list)     # the tensor is kept alive: its address cannot be recycled while cached
-    return plan
+    val = build()
+    if len(cache) >= slots:
+        cache.pop(next(iter(cache)))
+    cache[key] = (val, keep_alive)
+    return val
 
 
-_EDGE_PLANS = {}
+def _tensor_key(t):
+    return (t.data_ptr(), tuple(t.shape), t._version, t.dtype)
+
+
+def canonical_edges(edge_index, n):
+    """remove_self_loops + add_self_loops (model.py:385-386), once per edge_index tensor: the training loops pass the
+    same ``data.edge_index`` every epoch, and every cache below hangs off the tensor returned here."""
+    if not torch.is_tensor(edge_index):        # e.g. train_pubmed's positional epoch landing here (SURVEY 2.4)
+        raise TypeError("edge_index must be a [2, E] tensor, got %s" % type(edge_index).__name__)
+
+    def build():
+        ei, _ = remove_self_loops(edge_index)
+        ei, _ = add_self_loops(ei, num_nodes=n)
+        return ei.contiguous()
+    return _cached(_EDGE_CACHE, ("canon", n) + _tensor_key(edge_index), edge_index, build)
+
+
+def _edge_list_plan(edge_list, n):
+    """Plan of the plain ``GATConv``: the (coalesced) edge list IS the structure."""
+    def build():
+        order = torch.argsort(edge_list[0] * n + edge_list[1])
+        graph = CSRGraph.from_indices(edge_list[:, order].contiguous(), n)
+        return _GATPlan(edge_list, graph)
+    return _cached(_EDGE_CACHE, ("plan", n) + _tensor_key(edge_list), edge_list, build)
 
 
 def _gat_plan(edge_list, adj):
+    """Plan relating the listed edges to the stored entries of ``adj``; cached on the adjacency's STRUCTURE (the
+    CSR handle DGG attaches survives across epochs, the value tensor does not)."""
     graph, vals = CSRGraph.from_coo(adj)
-    cache = getattr(adj, "_gat_plan", None)
-    if cache is None or cache[0] != (edge_list.data_ptr(), edge_list.shape[1]):
-        plan = _GATPlan(edge_list, graph)
-        try:
-            adj._gat_plan = ((edge_list.data_ptr(), edge_list.shape[1]), plan)
-        except Exception:
-            pass
-        return plan, vals
-    return cache[1], vals
+    plan = _cached(graph.aux, ("gat_plan",) + _tensor_key(edge_list), edge_list, lambda: _GATPlan(edge_list, graph))
+    return plan, vals
+
+
+def gat_heads(convs, x, edge_list, adj):
+    """All heads of one attention layer: ONE fused edge-softmax-aggregate launch per direction when the listed edges
+    coincide with the stored entries of the adjacency (always, unless ``in_adj`` got noisy edges that the edge list
+    did not); the general case goes head by head through the tensor-op closed form.  -> [N, heads * F_out]"""
+    c0, heads, n = convs[0], len(convs), x.shape[0]
+    f, p_drop, training = c0.out_features, c0.dropout, c0.training
+    background = adj is not None
+    plan, avals = _gat_plan(edge_list, adj) if background else (_edge_list_plan(edge_list, n), None)
+    if not plan.csr_aligned or any(c.bias is None for c in convs):
+        return torch.cat([c._attend_eager(x, edge_list, adj) for c in convs], dim=1)
+    if training and p_drop > 0:      # every head draws its own input-dropout mask (model.py:558 inside each conv)
+        h = torch.stack([torch.matmul(F.dropout(x, p_drop, training=True), c.weight) for c in convs], dim=1)
+    else:
+        h = torch.matmul(x, torch.cat([c.weight for c in convs], dim=1)).view(n, heads, f)
+    a = torch.stack([torch.cat([c.a[:f], c.a[f:]], dim=1) for c in convs])              # [heads, F, 2]
+    pq = torch.einsum("nkf,kfc->nkc", h, a)       # e_ij = LeakyReLU(a^T [h_i || h_j]) = LeakyReLU(p_i + q_j)
+    hd = F.dropout(h, p_drop, training=training)
+    bias = torch.stack([c.bias for c in convs])
+    fp = (f + 3) // 4 * 4                         # 128-bit gathers: pad e.g. the 3 / 7 class logits to 4 / 8
+    if fp != f:
+        hd, bias = F.pad(hd, (0, fp - f)), F.pad(bias, (0, fp - f))
+    hd = hd.reshape(n, heads * fp)
+    keep = None
+    if training and p_drop > 0:      # attention dropout on the listed entries; the background keeps its expectation
+        keep = F.dropout(torch.ones(heads, plan.graph.nnz, device=x.device), p_drop, training=True)
+    out = K.gat_aggregate(hd, pq, plan.graph, heads, fp, avals=avals, htot=hd.sum(0) if background else None,
+                          bias=bias.reshape(-1), alpha=c0.alpha, bg=float(n) if background else 0.0, keep=keep)
+    if fp != f:
+        out = out.view(n, heads, fp)[:, :, :f].reshape(n, heads * f)
+    return out
 
 
 class GATConv_DGG(nn.Module):
@@ -430,8 +479,9 @@ class GATConv_DGG(nn.Module):
         out_i = [ sum_(a) w_ij h_j + exp(-m_i) (sum_j h_j - sum_(d) h_j) ] / [ sum_(a) w_ij + exp(-m_i) (N - |d_i|) ]
 
     an O(E F) edge softmax + SpMM plus one rank-1 background term, instead of 5 dense N x N temporaries.
-    Training-mode attention dropout is applied to the listed entries; the background term keeps its
-    expectation (the reference draws an N x N mask) -- parity is asserted in eval mode."""
+    Training-mode attention dropout is applied to the listed entries (after normalisation, like the reference);
+    the background term keeps its expectation (the reference draws an N x N mask, whose exact evaluation is
+    inherently O(N^2) per head) -- parity is asserted in eval mode and with dropout = 0."""
 
     def __init__(self, in_features, out_features, dropout, alpha, bias=True):
         super().__init__()
@@ -454,10 +504,11 @@ class GATConv_DGG(nn.Module):
         nn.init.xavier_uniform_(self.a.data, gain=1.414)
 
     def forward(self, x, edge_list, adj):
-        return self._attend(x, edge_list, adj)
+        return gat_heads([self], x, edge_list, adj)
 
-    def _attend(self, x, edge_list, adj):
-        """adj = the DGG adjacency (dense-background softmax, model.py:565-569) or None (plain ``GATConv``:
+    def _attend_eager(self, x, edge_list, adj):
+        """The closed form with plain tensor ops (edge lists that do not coincide with the adjacency's support).
+        adj = the DGG adjacency (dense-background softmax, model.py:565-569) or None (plain ``GATConv``:
         logits are -1e20 off the edge list, a true masked softmax, model.py:519-522)."""
         x = F.dropout(x, self.dropout, training=self.training)
         h = torch.matmul(x, self.weight)
@@ -475,10 +526,9 @@ class GATConv_DGG(nn.Module):
         floor = torch.zeros(n, device=h.device) if background else torch.full((n,), -1e30, device=h.device)
         m = floor.scatter_reduce(0, plan.rows_a, s.detach(), "amax", include_self=True)
         em = torch.exp(-m) if background else torch.zeros(n, device=h.device)
-        w = torch.exp(s - m[plan.rows_a]) - em[plan.rows_a]
+        xw = torch.exp(s - m[plan.rows_a])
+        w = xw - em[plan.rows_a]
         hd = F.dropout(h, self.dropout, training=self.training)
-        if self.training and self.dropout > 0:
-            w = F.dropout(w, self.dropout, training=True)
         htot = hd.sum(0, keepdim=True)
         bg_cnt = torch.full((n,), float(n), device=h.device)
         if plan.d_sel.numel():
@@ -487,6 +537,10 @@ class GATConv_DGG(nn.Module):
         else:
             hbg = htot
         denom = em * bg_cnt + torch.zeros(n, device=h.device).index_add(0, plan.rows_a, w)
+        if self.training and self.dropout > 0:
+            # the reference drops entries of the NORMALISED attention (model.py:570): the normaliser is untouched;
+            # listed entries get their own mask, the background keeps its expectation
+            w = F.dropout(xw, self.dropout, training=True) - em[plan.rows_a]
         if plan.csr_aligned:
             num = K.spmm(w, hd, plan.graph)
         else:
@@ -522,14 +576,13 @@ class GAT_DGG_00(nn.Module, _NormalizeMixin):
             att.reset_parameters()
 
     def forward(self, x, in_adj=None, edge_index=None, epoch=None, writer=None):
-        edge_index, _ = remove_self_loops(edge_index)
-        edge_index, _ = add_self_loops(edge_index, num_nodes=x.size(0))
+        edge_index = canonical_edges(edge_index, x.size(0))
         in_adj = add_self_loops_coo(in_adj)
         unnorm_adj, x_dgg = self.dgg(x=x, adj=in_adj)
         x = x_dgg
-        x = torch.cat([att(x, edge_index, unnorm_adj) for att in self.attentions], dim=1)
+        x = gat_heads(self.attentions, x, edge_index, unnorm_adj)                 # == cat of the heads (model.py:398)
         x = F.elu(x)
-        x = torch.sum(torch.stack([att(x, edge_index, unnorm_adj) for att in self.out_atts]), dim=0) / len(
+        x = gat_heads(self.out_atts, x, edge_index, unnorm_adj).view(x.shape[0], len(self.out_atts), -1).sum(1) / len(
             self.out_atts)
         return F.log_softmax(x, dim=1), unnorm_adj, x_dgg
 
@@ -646,7 +699,7 @@ class GATConv(GATConv_DGG):
     edges -- the ``GATConv_DGG`` evaluation without the dense background term and with A == 1."""
 
     def forward(self, x, edge_index, adj=None):
-        return self._attend(x, edge_index, None)
+        return gat_heads([self], x, edge_index, None)
 
 
 class GAT(nn.Module):
@@ -670,9 +723,9 @@ class GAT(nn.Module):
             att.reset_parameters()
 
     def forward(self, x, in_adj=None, edge_index=None, epoch=None, writer=None):
-        edge_index, _ = remove_self_loops(edge_index)
-        edge_index, _ = add_self_loops(edge_index, num_nodes=x.size(0))
-        x = torch.cat([att(x, edge_index) for att in self.attentions], dim=1)
+        edge_index = canonical_edges(edge_index, x.size(0))
+        x = gat_heads(self.attentions, x, edge_index, None)
         x = F.elu(x)
-        x = torch.sum(torch.stack([att(x, edge_index) for att in self.out_atts]), dim=0) / len(self.out_atts)
+        x = gat_heads(self.out_atts, x, edge_index, None).view(x.shape[0], len(self.out_atts), -1).sum(1) / len(
+            self.out_atts)
         return F.log_softmax(x, dim=1), None, None

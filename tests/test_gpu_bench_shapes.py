@@ -122,7 +122,8 @@ def test_allpairs_continuation_passes_more_than_64_per_row():
     want_i, want_v, y = _dense_rows_topk(z, torch.arange(n), t, noise, kc)
     srt = torch.sort(y, dim=-1, descending=True).values[:, :kc + 1]
     ok = ((srt[:, :-1] - srt[:, 1:]) > 2e-5).all(-1)
-    assert ok.float().mean() > 0.5
+    assert ok.float().mean() > 0.1      # 150 of 3000 values per row: most rows hold SOME pair closer than 2e-5
     assert torch.equal(got_i[ok], want_i[ok])
     torch.testing.assert_close(got_v, want_v, rtol=0, atol=2e-5)
+    assert float((got_i == want_i).float().mean()) > 0.98
     assert bool((got_v[:, 1:] <= got_v[:, :-1]).all())          # still one descending list across the passes
