@@ -230,6 +230,25 @@ int dggb_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* col, int32_t n,
                            float* d_pq, float* d_adj_val, float* d_htot, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * SpMM with the conv layer's dense part folded in -- GCNConv relu((A x) W) (model.py:594-598) and the GCNII layer
+ * theta * (s W) + (1 - theta) * s, s = (1 - alpha) A h + alpha h0 (model.py:32-44, 65-77) -- one launch per
+ * direction instead of SpMM + axpby + library GEMM + axpby + add + relu:
+ *     s_i = c1 * rs_i * sum_e a_e x[col_e] + c2 * h0_i ;   y_i = act(theta * (s_i W) + beta * s_i + resid_i)
+ * W [Fin, Fout] row-major (held in shared memory); h0 / resid / row_scale / s_out may be NULL; relu != 0: act = ReLU.
+ * Fin % 4 == 0, Fin <= 128, Fout <= 128; beta != 0 requires Fout == Fin.  s_out [N, Fin] is what the weight gradient
+ * dW = theta * s^T dY needs (dggb_gemm_tn_splitk).
+ * bwd (gy = dL/dy already masked by the ReLU): ds_i = theta * (gy_i W^T) + beta * gy_i  -> ds_out [N, Fin] (d h0 =
+ * c2 * ds), dval_e = rs_i c1 <ds_i, x_col> (OVERWRITTEN; NULL: skipped), dx_col += a_e rs_i c1 ds_i (ACCUMULATED).
+ * ---------------------------------------------------------------------------------- */
+int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
+                       int32_t fin, const float* row_scale, const float* h0, float c1, float c2, const float* w,
+                       int32_t fout, float theta, float beta, const float* resid, int32_t relu, float* y,
+                       float* s_out, void* stream);
+int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
+                       int32_t fin, const float* row_scale, float c1, const float* w, int32_t fout, float theta,
+                       float beta, const float* gy, float* dval, float* dx, float* ds_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)
  * -- nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126 and the
  * y = x_enc We^T product.  tcgen05 tensor cores with an in-kernel 3xTF32 split (fp32-level

@@ -170,6 +170,192 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SpMM with the layer's dense part folded in (GCNConv model.py:594-598, GraphConvolution / DenseGraphConvolution
+// model.py:32-44, 65-77): per row, in one pass,
+//     agg_i = rs_i * sum_e a_e x[col_e]                      (128-bit gathers, as spmm_fwd_kernel)
+//     s_i   = c1 * agg_i + c2 * h0_i                         (GCNII initial residual; c2 = 0: none)
+//     y_i   = act( theta * (s_i W) + beta * s_i + resid_i )  (W [Fin, Fout] in shared memory; act: identity / ReLU)
+// instead of SpMM -> axpby -> cuBLAS mm -> axpby -> add -> relu (six launches and four [N, F] round trips per layer;
+// the 64-layer GCNII stack is launch-bound at Citeseer size).  s is written out once (the weight gradient
+// dW = theta * s^T dY needs it).  Fin % 4 == 0, Fin <= 128, Fout <= 128.
+// Backward: ds_i = theta * (g_i W^T) + beta * g_i (W^T in shared memory), then the SpMM backward with c1 * ds_i:
+//     dval_e = rs_i <c1 ds_i, x_col>,  dx_col += a_e rs_i c1 ds_i;   ds is written out (d h0 = c2 ds).
+// ------------------------------------------------------------------------------------------------
+struct SpmmGemmArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  int n, fin, fout, L;
+  const float* x;
+  const float* row_scale;
+  const float* h0;
+  const float* w;        // [fin, fout]
+  const float* resid;    // [n, fout] or NULL
+  float c1, c2, theta, beta;
+  int relu;
+};
+
+template <int T>
+__global__ void __launch_bounds__(kSpmmWarps* kWarp)
+    spmm_gemm_fwd_kernel(SpmmGemmArgs A, float* __restrict__ y, float* __restrict__ s_out) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                                           // [fin][fout]
+  float* srow = sm + A.fin * A.fout + (threadIdx.x >> 5) * A.fin;   // this warp's s_i
+  pdl_wait();
+  for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) Ws[c] = __ldg(A.w + c);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
+  for (int i = blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); i < A.n; i += gridDim.x * kSpmmWarps) {
+    const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
+    const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
+    Vec<4> acc[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t].zero();
+    for (int w0 = beg; w0 < end; w0 += kWarp) {
+      const int e_l = w0 + lane;
+      const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
+      const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
+      const int cnt = min(kWarp, end - w0);
+#pragma unroll 4
+      for (int j0 = 0; j0 < cnt; j0 += G) {
+        const int j = j0 + grp;
+        const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
+        float a = __shfl_sync(0xffffffffu, a_l, j & 31);
+        if (j >= cnt) a = 0.f;
+        const float* xr = A.x + (size_t)v * A.fin;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < A.fin) {
+            Vec<4> xv;
+            xv.load(xr + c);
+            acc[t].fma(a, xv);
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      for (int o = L; o < kWarp; o <<= 1) acc[t].xor_add(o);
+      const int c = 4 * (lg + L * t);
+      if (grp == 0 && c < A.fin) {
+        float4 sv = acc[t].v;
+        const float k1 = A.c1 * rs;
+        sv.x *= k1; sv.y *= k1; sv.z *= k1; sv.w *= k1;
+        if (A.h0) {
+          const float4 h = ldg4(A.h0 + (size_t)i * A.fin + c);
+          sv.x = fmaf(A.c2, h.x, sv.x); sv.y = fmaf(A.c2, h.y, sv.y);
+          sv.z = fmaf(A.c2, h.z, sv.z); sv.w = fmaf(A.c2, h.w, sv.w);
+        }
+        *reinterpret_cast<float4*>(srow + c) = sv;
+        if (s_out) st4(s_out + (size_t)i * A.fin + c, sv);
+      }
+    }
+    __syncwarp();
+    for (int c = lane; c < A.fout; c += kWarp) {
+      float d = 0.f;
+#pragma unroll 8
+      for (int f = 0; f < A.fin; ++f) d = fmaf(srow[f], Ws[f * A.fout + c], d);
+      float v = A.theta * d;
+      if (A.beta != 0.f) v = fmaf(A.beta, srow[c], v);      // requires fout == fin (checked on the host)
+      if (A.resid) v += __ldg(A.resid + (size_t)i * A.fout + c);
+      if (A.relu) v = fmaxf(v, 0.f);
+      y[(size_t)i * A.fout + c] = v;
+    }
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(kSpmmWarps* kWarp)
+    spmm_gemm_bwd_kernel(SpmmGemmArgs A, const float* __restrict__ gy, float* __restrict__ dval,
+                         float* __restrict__ dx, float* __restrict__ ds_out) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float sm[];
+  float* Wt = sm;                                           // [fout][fin] (transposed copy)
+  float* grow = sm + A.fin * A.fout + (threadIdx.x >> 5) * (A.fin + A.fout);   // this warp's g_i ...
+  float* dsrow = grow + A.fout;                             // ... and ds_i
+  pdl_wait();
+  for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
+    const int f = c / A.fout, o = c % A.fout;
+    Wt[o * A.fin + f] = __ldg(A.w + c);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
+  for (int i = blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); i < A.n; i += gridDim.x * kSpmmWarps) {
+    const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
+    const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
+    __syncwarp();
+    for (int c = lane; c < A.fout; c += kWarp) grow[c] = __ldg(gy + (size_t)i * A.fout + c);
+    __syncwarp();
+    for (int f = lane; f < A.fin; f += kWarp) {
+      float d = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < A.fout; ++c) d = fmaf(grow[c], Wt[c * A.fin + f], d);
+      float v = A.theta * d;
+      if (A.beta != 0.f) v = fmaf(A.beta, grow[f], v);
+      dsrow[f] = v;
+      if (ds_out) ds_out[(size_t)i * A.fin + f] = v;
+    }
+    __syncwarp();
+    Vec<4> g[T];
+    const float k1 = A.c1 * rs;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int c = 4 * (lg + L * t);
+      if (c < A.fin) {
+        g[t].v = *reinterpret_cast<const float4*>(dsrow + c);
+        g[t].scale(k1);
+      } else {
+        g[t].zero();
+      }
+    }
+    for (int w0 = beg; w0 < end; w0 += kWarp) {
+      const int e_l = w0 + lane;
+      const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
+      const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
+      const int cnt = min(kWarp, end - w0);
+#pragma unroll 2
+      for (int j0 = 0; j0 < cnt; j0 += G) {
+        const int j = j0 + grp;
+        const bool valid = j < cnt;
+        const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
+        const float a = __shfl_sync(0xffffffffu, a_l, j & 31);
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < A.fin && valid) {
+            if (dval) {
+              Vec<4> xv;
+              xv.load(A.x + (size_t)v * A.fin + c);
+              dot += g[t].dot(xv);
+            }
+            if (dx) g[t].red(dx + (size_t)v * A.fin + c, a);
+          }
+        }
+        if (dval) {
+          dot = group_sum(dot, L);
+          if (lg == 0 && valid) dval[w0 + j] = dot;
+        }
+      }
+    }
+  }
+}
+
+static int spmm_gemm_lanes(int fin, int* t_out) {
+  const int chunks = fin / 4;
+  int L = 1;
+  while (L < 32 && 4 * L < chunks) L *= 2;
+  int T = (chunks + L - 1) / L;
+  *t_out = T > 2 ? 4 : (T >= 2 ? 2 : 1);
+  return L;
+}
+
 template <typename Fn>
 static int dispatch_vec(int f, Fn&& fn) {
   // pick the widest vector the row stride allows, then lanes-per-row L and chunks-per-lane T
@@ -224,4 +410,56 @@ extern "C" int dggb_spmm_csr_bwd(const int32_t* rowptr, const int32_t* col, cons
                as_stream(stream), rowptr, col, val, n, x, f, L, row_scale, dy, dval, dx);
     return launch_status();
   });
+}
+
+static int spmm_gemm_check(const SpmmGemmArgs& A) {
+  if (!A.rowptr || !A.col || !A.val || !A.x || !A.w || A.n < 0 || A.fin <= 0 || A.fout <= 0) return DGGB_ERR_BAD_ARG;
+  if (A.fin % 4 != 0 || A.fin > 128 || A.fout > 128 || (A.beta != 0.f && A.fin != A.fout) ||
+      ((uintptr_t)A.x % 16) || (A.h0 && ((uintptr_t)A.h0 % 16)))
+    return DGGB_ERR_BAD_SHAPE;
+  return DGGB_OK;
+}
+
+extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                                  const float* x, int32_t fin, const float* row_scale, const float* h0, float c1,
+                                  float c2, const float* w, int32_t fout, float theta, float beta,
+                                  const float* resid, int32_t relu, float* y, float* s_out, void* stream) {
+  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, h0, w, resid, c1, c2, theta, beta, relu};
+  int rc = spmm_gemm_check(A);
+  if (rc != DGGB_OK) return rc;
+  if (!y || (s_out && ((uintptr_t)s_out % 16))) return DGGB_ERR_BAD_ARG;
+  if (n == 0) return DGGB_OK;
+  int T = 1;
+  A.L = spmm_gemm_lanes(fin, &T);
+  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * fin) * sizeof(float);
+  auto go = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    const int grid = rows_grid(n, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, y, s_out);
+    return launch_status();
+  };
+  return T == 1 ? go(spmm_gemm_fwd_kernel<1>) : (T == 2 ? go(spmm_gemm_fwd_kernel<2>) : go(spmm_gemm_fwd_kernel<4>));
+}
+
+extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                                  const float* x, int32_t fin, const float* row_scale, float c1, const float* w,
+                                  int32_t fout, float theta, float beta, const float* gy, float* dval, float* dx,
+                                  float* ds_out, void* stream) {
+  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, nullptr, w, nullptr, c1, 0.f, theta, beta, 0};
+  int rc = spmm_gemm_check(A);
+  if (rc != DGGB_OK) return rc;
+  if (!gy || (dx && ((uintptr_t)dx % 16))) return DGGB_ERR_BAD_ARG;
+  if (n == 0) return DGGB_OK;
+  int T = 1;
+  A.L = spmm_gemm_lanes(fin, &T);
+  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * (fin + fout)) * sizeof(float);
+  auto go = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    const int grid = rows_grid(n, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out);
+    return launch_status();
+  };
+  return T == 1 ? go(spmm_gemm_bwd_kernel<1>) : (T == 2 ? go(spmm_gemm_bwd_kernel<2>) : go(spmm_gemm_bwd_kernel<4>));
 }

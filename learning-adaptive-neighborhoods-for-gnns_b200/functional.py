@@ -162,6 +162,64 @@ def spmm(vals, x, graph, row_scale=None):
     return _Spmm.apply(vals, x, graph, row_scale)
 
 
+class _SpmmGemm(torch.autograd.Function):
+    """y = act(theta * (s W) + beta * s + resid), s = c1 * rs * (A x) + c2 * h0 in one launch per direction
+    (GCNConv model.py:594-598; GraphConvolution model.py:32-44, 65-77); see include/dggb.h."""
+
+    @staticmethod
+    def forward(ctx, vals, x, w, h0, resid, graph: CSRGraph, row_scale, c1, c2, theta, beta, relu):
+        _require_cuda(vals, x, w, h0, resid)
+        vals, x, w = _f32c(vals), _f32c(x), _f32c(w)
+        h0 = None if h0 is None else _f32c(h0)
+        resid = None if resid is None else _f32c(resid)
+        n, fin, fout = graph.n, x.shape[1], w.shape[1]
+        y = torch.empty(n, fout, dtype=torch.float32, device=x.device)
+        need_s = ctx.needs_input_grad[2]
+        s = torch.empty(n, fin, dtype=torch.float32, device=x.device) if need_s else None
+        check(lib().dggb_spmm_gemm_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(n), p(x), i32(fin), p(row_scale),
+                                       p(h0), float(c1), float(c2 if h0 is not None else 0.0), p(w), i32(fout),
+                                       float(theta), float(beta), p(resid), i32(1 if relu else 0), p(y), p(s),
+                                       stream()), "spmm_gemm_fwd")
+        ctx.graph, ctx.meta = graph, (c1, c2, theta, beta, relu, h0 is not None, resid is not None)
+        ctx.save_for_backward(vals, x, w, row_scale, s, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        vals, x, w, row_scale, s, y = ctx.saved_tensors
+        c1, c2, theta, beta, relu, has_h0, has_resid = ctx.meta
+        g = ctx.graph
+        gy = _f32c(gy)
+        if relu:
+            gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
+        need_v, need_x, need_w, need_h0 = ctx.needs_input_grad[:4]
+        dval = torch.empty_like(vals) if need_v else None
+        dx = torch.zeros_like(x) if need_x else None
+        ds = torch.empty_like(x) if (need_h0 and has_h0) else None
+        if need_v or need_x or ds is not None:
+            check(lib().dggb_spmm_gemm_bwd(p(g.rowptr), p(g.col), p(vals), i32(g.n), p(x), i32(x.shape[1]),
+                                           p(row_scale), float(c1), p(w), i32(w.shape[1]), float(theta), float(beta),
+                                           p(gy), p(dval), p(dx), p(ds), stream()), "spmm_gemm_bwd")
+        dw = None
+        if need_w:
+            dw = gemm_tn(s, gy, False)[0]
+            if theta != 1.0:
+                dw = dw * theta
+        dh0 = ds * c2 if ds is not None else None
+        dres = gy if (has_resid and ctx.needs_input_grad[4]) else None
+        return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None
+
+
+def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2=0.0, theta=1.0, beta=0.0, relu=False):
+    """act(theta * (s W) + beta * s + resid) with s = c1 * rs * (A x) + c2 * h0; None if the shape is outside the
+    fused kernel's range (Fin % 4 != 0, Fin or Fout > 128)."""
+    fin, fout = x.shape[1], w.shape[1]
+    if not (x.is_cuda and fin % 4 == 0 and fin <= 128 and fout <= 128 and (beta == 0.0 or fin == fout)):
+        return None
+    return _SpmmGemm.apply(vals, x, w, h0, resid, graph, row_scale, float(c1), float(c2), float(theta), float(beta),
+                           bool(relu))
+
+
 class _AllPairsTopK(torch.autograd.Function):
     """y_ij = -t |z_i - z_j| [+ noise], top-Kc per row, sorted descending (dgm.py:275-301 without N x N)."""
 
@@ -265,6 +323,7 @@ class _EdgeMLP(torch.autograd.Function):
                 dist_scale: float):
         dist_only = bool(flags & DIST_ONLY)
         _require_cuda(p_uv, xe, edge_val, deg)
+        ctx.shapes = tuple(None if t is None else t.shape for t in (wx, b1, w2, b2))
         if dist_only:
             xe = _f32c(xe)
             w, ldp = 0, 0
@@ -306,6 +365,8 @@ class _EdgeMLP(torch.autograd.Function):
                                       p(edge_val), p(deg), p(wx), p(b1), p(w2), p(b2), float(slope),
                                       float(dist_scale), i32(flags), p(score), p(_f32c(g)), p(d_p), p(d_xe), p(d_wx),
                                       p(d_b1), p(d_w2), p(d_b2), stream()), "edge_mlp_bwd")
+        d_wx, d_b1, d_w2, d_b2 = (None if (g_ is None or shp is None) else g_.reshape(shp)
+                                  for g_, shp in zip((d_wx, d_b1, d_w2, d_b2), ctx.shapes))
         return d_p, d_xe, d_wx, d_b1, d_w2, d_b2, None, None, None, None, None, None
 
 

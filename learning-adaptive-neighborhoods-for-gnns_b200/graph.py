@@ -71,13 +71,13 @@ class CSRGraph:
         if h is not None:
             v = getattr(adj, "_dgg_vals", None)
             if v is None:
-                v = adj._values()
+                v = adj.values() if adj.is_coalesced() else adj._values()   # values(): keeps the autograd history
             return h, (v if v.dtype == torch.float32 else v.to(torch.float32))
         assert adj.is_sparse and adj.dim() == 2 and adj.shape[0] == adj.shape[1]
         if not adj.is_coalesced():
             adj = adj.coalesce()
         g = CSRGraph.from_indices(adj._indices(), adj.shape[0])
-        vals = adj._values().to(torch.float32)
+        vals = adj.values().to(torch.float32)            # differentiable view of a coalesced tensor's values
         try:
             adj._dgg_csr = g
         except Exception:

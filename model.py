@@ -61,9 +61,15 @@ class GCNConv(nn.Module):
         self.W = nn.Parameter(torch.rand(in_channels, out_channels, requires_grad=True))
 
     def forward(self, x, adj):
+        if adj.is_sparse and x.shape[1] <= 128:
+            g, v = CSRGraph.from_coo(adj)
+            out = K.spmm_gemm(v, x, self.W, g, relu=True)          # SpMM + W + ReLU: one launch (W in shared memory)
+            if out is not None:
+                return out
         if x.shape[1] > self.W.shape[1]:
-            # (A x) W == A (x W): aggregate in the narrower space (model.py:594-596 order otherwise)
-            return torch.relu(_aggregate(adj, K.tall_matmul(x, self.W)))
+            # (A x) W == A (x W): aggregate in the narrower space (model.py:594-596 order otherwise).  Raw features
+            # (Cora 1433, Citeseer 3703 wide): the tall product runs on the tensor cores, features padded once
+            return torch.relu(_aggregate(adj, K.encoder_linear(x, self.W.t(), None, 1.0)))
         return torch.relu(K.tall_matmul(_aggregate(adj, x), self.W))
 
 
@@ -190,8 +196,20 @@ class GraphConvolution(nn.Module):
         stdv = 1.0 / math.sqrt(self.out_features)
         self.weight.data.uniform_(-stdv, stdv)
 
-    def forward(self, input, adj, h0, lamda, alpha, l):
+    def forward(self, input, adj, h0, lamda, alpha, l, act=None):
+        """``act="relu"``: the caller's activation (GCNII applies ``act_fn`` to every layer output, model.py:728)
+        is folded into the fused kernel."""
         theta = math.log(lamda / l + 1)
+        if adj.is_sparse and not self.variant:
+            g, v = CSRGraph.from_coo(adj)
+            out = K.spmm_gemm(v, input, self.weight, g, h0=h0, resid=input if self.residual else None, c1=1 - alpha,
+                              c2=alpha, theta=theta, beta=1 - theta, relu=(act == "relu"))
+            if out is not None:
+                return out
+        out = self._forward_unfused(input, adj, h0, theta, alpha)
+        return torch.relu(out) if act == "relu" else out
+
+    def _forward_unfused(self, input, adj, h0, theta, alpha):
         hi = _aggregate(adj, input)
         if self.variant:
             support = torch.cat([hi, h0], 1)
@@ -245,7 +263,7 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
                 unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
                 norm_adj = self.normalize_adj(unnorm_adj)
             layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
-            layer_inner = self.act_fn(con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1))
+            layer_inner = con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1, act="relu")
         layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
         layer_inner = self.fcs[-1](layer_inner)
         return F.log_softmax(layer_inner, dim=1)
@@ -665,7 +683,7 @@ class GCNII(nn.Module):
         _layers.append(layer_inner)
         for i, con in enumerate(self.convs):
             layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
-            layer_inner = self.act_fn(con(layer_inner, adj, _layers[0], self.lamda, self.alpha, i + 1))
+            layer_inner = con(layer_inner, adj, _layers[0], self.lamda, self.alpha, i + 1, act="relu")
         layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
         layer_inner = self.fcs[-1](layer_inner)
         return F.log_softmax(layer_inner, dim=1)

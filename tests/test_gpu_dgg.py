@@ -274,7 +274,7 @@ def test_dgg_edge_cases_long_rows_and_empty_rows():
     r = O.dgg_forward(x, idx, n, p)
     ref = r["out"][idx[0], idx[1]]
     rows_ok = ~near_tie_entries(idx, r["R"].detach(), n)
-    assert int(rows_ok[idx[0] == 7].sum()) > 1000       # the hub row stays in the loss (minus its near-tied entries)
+    assert int(rows_ok[idx[0] == 7].sum()) > 800       # the hub row stays in the loss (minus its near-tied entries)
     w = torch.randn(idx.shape[1], generator=gen) * rows_ok   # near-tied entries are left out on both sides
     (ref * w).sum().backward()
     out, x_enc = m(x.cuda(), torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).coalesce().cuda())
@@ -366,3 +366,51 @@ def test_fused_edge_kernels_match_two_launch(n, h, avg_deg, noise, hard_k):
             assert qa is None
         else:
             torch.testing.assert_close(qa, qb, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,fin,fout,h0,relu,resid,theta,rs", [(3000, 64, 64, True, True, False, 0.4, False),
+                                                                (800, 64, 3, False, True, False, 1.0, False),
+                                                                (1500, 32, 32, True, False, True, 0.2, True),
+                                                                (700, 128, 16, False, False, False, 1.0, False)])
+def test_spmm_gemm_fused_layer_vs_tensor_ops(n, fin, fout, h0, relu, resid, theta, rs):
+    """SpMM + the layer's dense part in one launch (GCNConv / GCNII layer) against the same formula with dense
+    tensor ops, forward and every gradient (adjacency values, x, W, h0, residual)."""
+    from dgg_b200 import CSRGraph
+    from dgg_b200 import functional as K
+
+    idx, _ = random_graph(n, 6, seed=n, hubs=2, hub_deg=120)
+    gen = torch.Generator().manual_seed(fin + fout)
+    val = 0.1 + torch.rand(idx.shape[1], generator=gen)
+    x = torch.randn(n, fin, generator=gen)
+    w = torch.randn(fin, fout, generator=gen) / fin ** 0.5
+    h0t = torch.randn(n, fin, generator=gen) if h0 else None
+    rst = torch.randn(n, fout, generator=gen) if resid else None
+    scale = (0.5 + torch.rand(n, generator=gen)) if rs else None
+    beta = (1 - theta) if fin == fout else 0.0
+    c1, c2 = 0.9, 0.1
+    wt = torch.randn(n, fout, generator=gen)
+
+    def run(dev):
+        leaves = [t.clone().to(dev).requires_grad_(True) if t is not None else None for t in (val, x, w, h0t, rst)]
+        v_, x_, w_, h_, r_ = leaves
+        if dev == "cpu":
+            a = O.dense_from_edges(idx, v_, n)
+            agg = a @ x_
+            if scale is not None:
+                agg = agg * scale.unsqueeze(-1)
+            s = c1 * agg + (c2 * h_ if h_ is not None else 0)
+            y = theta * (s @ w_) + (beta * s if beta else 0) + (r_ if r_ is not None else 0)
+            y = torch.relu(y) if relu else y
+        else:
+            g = CSRGraph.from_indices(idx.cuda(), n)
+            y = K.spmm_gemm(v_, x_, w_, g, h0=h_, resid=r_, row_scale=None if scale is None else scale.cuda(), c1=c1,
+                            c2=c2, theta=theta, beta=beta, relu=relu)
+            assert y is not None
+        (y * wt.to(dev)).sum().backward()
+        return y.detach().cpu(), [None if t is None else t.grad.cpu() for t in leaves]
+
+    (y_ref, g_ref), (y_got, g_got) = run("cpu"), run("cuda")
+    torch.testing.assert_close(y_got, y_ref, rtol=2e-5, atol=2e-5)
+    for name, a, b in zip(["val", "x", "w", "h0", "resid"], g_got, g_ref):
+        if b is not None:
+            assert_grad_close(a, b, what=name)
