@@ -276,8 +276,9 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* Wt = sm;                                           // [fout][fin] (transposed copy)
-  float* grow = sm + A.fin * A.fout + (threadIdx.x >> 5) * (A.fin + A.fout);   // this warp's g_i ...
-  float* dsrow = grow + A.fout;                             // ... and ds_i
+  const int fo4 = (A.fout + 3) & ~3;                        // keeps ds_i 16-byte aligned for the float4 reads below
+  float* grow = sm + ((A.fin * A.fout + 3) & ~3) + (threadIdx.x >> 5) * (A.fin + fo4);   // this warp's g_i ...
+  float* dsrow = grow + fo4;                                // ... and ds_i
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
     const int f = c / A.fout, o = c % A.fout;
@@ -453,7 +454,7 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
   if (n == 0) return DGGB_OK;
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
-  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * (fin + fout)) * sizeof(float);
+  const size_t smem = ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * (fin + ((fout + 3) & ~3))) * sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
