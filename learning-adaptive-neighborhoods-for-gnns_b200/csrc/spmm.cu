@@ -196,89 +196,162 @@ struct SpmmGemmArgs {
   int relu;
 };
 
-template <int T>
+constexpr int kRB = 4;   // rows per warp iteration: the W tile is read from shared memory once per kRB rows
+
+// dense part for kRB rows at once: out[r][c] = sum_f S[r][f] * M[f][c];  lane owns columns c = lane + 32 q (q < 4).
+// S rows are read as broadcast float4, M as conflict-free scalars: 3 LDS per 8 (kRB * 2) FMAs at 64 columns.
+template <int Q>
+__device__ __forceinline__ void dense_rows(const float* __restrict__ S, int ld_s, const float* __restrict__ M, int k_dim,
+                                           int n_cols, int lane, float (&acc)[kRB][Q]) {
+#pragma unroll
+  for (int r = 0; r < kRB; ++r)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[r][q] = 0.f;
+  for (int f = 0; f < k_dim; f += 4) {
+    float4 sv[kRB];
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) sv[r] = *reinterpret_cast<const float4*>(S + r * ld_s + f);
+#pragma unroll
+    for (int ff = 0; ff < 4; ++ff) {
+      float mv[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int c = lane + 32 * q;
+        mv[q] = (c < n_cols) ? M[(f + ff) * n_cols + c] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < kRB; ++r) {
+        const float sf = ff == 0 ? sv[r].x : (ff == 1 ? sv[r].y : (ff == 2 ? sv[r].z : sv[r].w));
+#pragma unroll
+        for (int q = 0; q < Q; ++q) acc[r][q] = fmaf(sf, mv[q], acc[r][q]);
+      }
+    }
+  }
+}
+
+// same with a reduction length that need not be a multiple of 4 (the S rows are zero-padded to ld_s)
+template <int Q>
+__device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld_s, const float* __restrict__ M,
+                                             int k_dim, int n_cols, int lane, float (&acc)[kRB][Q]) {
+#pragma unroll
+  for (int r = 0; r < kRB; ++r)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[r][q] = 0.f;
+  for (int f = 0; f < k_dim; ++f) {
+    float mv[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int c = lane + 32 * q;
+      mv[q] = (c < n_cols) ? M[f * n_cols + c] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) {
+      const float sf = S[r * ld_s + f];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) acc[r][q] = fmaf(sf, mv[q], acc[r][q]);
+    }
+  }
+}
+
+template <int T, int Q>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_fwd_kernel(SpmmGemmArgs A, float* __restrict__ y, float* __restrict__ s_out) {
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
-  float* Ws = sm;                                           // [fin][fout]
-  float* srow = sm + A.fin * A.fout + (threadIdx.x >> 5) * A.fin;   // this warp's s_i
+  float* Ws = sm;                                                     // [fin][fout]
+  float* srows = sm + A.fin * A.fout + (threadIdx.x >> 5) * kRB * A.fin;   // this warp's kRB rows of s
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) Ws[c] = __ldg(A.w + c);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  for (int i = blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); i < A.n; i += gridDim.x * kSpmmWarps) {
-    const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
-    const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
-    Vec<4> acc[T];
+  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * kRB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * kRB) {
+    __syncwarp();
+    for (int r = 0; r < kRB; ++r) {
+      const int i = i0 + r;
+      float* srow = srows + r * A.fin;
+      if (i >= A.n) {                                                 // ragged last block: zero rows
+        for (int c = lane; c < A.fin; c += kWarp) srow[c] = 0.f;
+        continue;
+      }
+      const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
+      const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
+      Vec<4> acc[T];
 #pragma unroll
-    for (int t = 0; t < T; ++t) acc[t].zero();
-    for (int w0 = beg; w0 < end; w0 += kWarp) {
-      const int e_l = w0 + lane;
-      const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
-      const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
-      const int cnt = min(kWarp, end - w0);
+      for (int t = 0; t < T; ++t) acc[t].zero();
+      for (int w0 = beg; w0 < end; w0 += kWarp) {
+        const int e_l = w0 + lane;
+        const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
+        const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
+        const int cnt = min(kWarp, end - w0);
 #pragma unroll 4
-      for (int j0 = 0; j0 < cnt; j0 += G) {
-        const int j = j0 + grp;
-        const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
-        float a = __shfl_sync(0xffffffffu, a_l, j & 31);
-        if (j >= cnt) a = 0.f;
-        const float* xr = A.x + (size_t)v * A.fin;
+        for (int j0 = 0; j0 < cnt; j0 += G) {
+          const int j = j0 + grp;
+          const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
+          float a = __shfl_sync(0xffffffffu, a_l, j & 31);
+          if (j >= cnt) a = 0.f;
+          const float* xr = A.x + (size_t)v * A.fin;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int c = 4 * (lg + L * t);
-          if (c < A.fin) {
-            Vec<4> xv;
-            xv.load(xr + c);
-            acc[t].fma(a, xv);
+          for (int t = 0; t < T; ++t) {
+            const int c = 4 * (lg + L * t);
+            if (c < A.fin) {
+              Vec<4> xv;
+              xv.load(xr + c);
+              acc[t].fma(a, xv);
+            }
           }
         }
       }
-    }
-    __syncwarp();
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      for (int o = L; o < kWarp; o <<= 1) acc[t].xor_add(o);
-      const int c = 4 * (lg + L * t);
-      if (grp == 0 && c < A.fin) {
-        float4 sv = acc[t].v;
-        const float k1 = A.c1 * rs;
-        sv.x *= k1; sv.y *= k1; sv.z *= k1; sv.w *= k1;
-        if (A.h0) {
-          const float4 h = ldg4(A.h0 + (size_t)i * A.fin + c);
-          sv.x = fmaf(A.c2, h.x, sv.x); sv.y = fmaf(A.c2, h.y, sv.y);
-          sv.z = fmaf(A.c2, h.z, sv.z); sv.w = fmaf(A.c2, h.w, sv.w);
+      for (int t = 0; t < T; ++t) {
+        for (int o = L; o < kWarp; o <<= 1) acc[t].xor_add(o);
+        const int c = 4 * (lg + L * t);
+        if (grp == 0 && c < A.fin) {
+          float4 sv = acc[t].v;
+          const float k1 = A.c1 * rs;
+          sv.x *= k1; sv.y *= k1; sv.z *= k1; sv.w *= k1;
+          if (A.h0) {
+            const float4 h = ldg4(A.h0 + (size_t)i * A.fin + c);
+            sv.x = fmaf(A.c2, h.x, sv.x); sv.y = fmaf(A.c2, h.y, sv.y);
+            sv.z = fmaf(A.c2, h.z, sv.z); sv.w = fmaf(A.c2, h.w, sv.w);
+          }
+          *reinterpret_cast<float4*>(srow + c) = sv;
+          if (s_out) st4(s_out + (size_t)i * A.fin + c, sv);
         }
-        *reinterpret_cast<float4*>(srow + c) = sv;
-        if (s_out) st4(s_out + (size_t)i * A.fin + c, sv);
       }
     }
     __syncwarp();
-    for (int c = lane; c < A.fout; c += kWarp) {
-      float d = 0.f;
-#pragma unroll 8
-      for (int f = 0; f < A.fin; ++f) d = fmaf(srow[f], Ws[f * A.fout + c], d);
-      float v = A.theta * d;
-      if (A.beta != 0.f) v = fmaf(A.beta, srow[c], v);      // requires fout == fin (checked on the host)
-      if (A.resid) v += __ldg(A.resid + (size_t)i * A.fout + c);
-      if (A.relu) v = fmaxf(v, 0.f);
-      y[(size_t)i * A.fout + c] = v;
+    float d[kRB][Q];
+    dense_rows<Q>(srows, A.fin, Ws, A.fin, A.fout, lane, d);
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) {
+      const int i = i0 + r;
+      if (i >= A.n) break;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int c = lane + 32 * q;
+        if (c < A.fout) {
+          float v = A.theta * d[r][q];
+          if (A.beta != 0.f) v = fmaf(A.beta, srows[r * A.fin + c], v);      // fout == fin (checked on the host)
+          if (A.resid) v += __ldg(A.resid + (size_t)i * A.fout + c);
+          if (A.relu) v = fmaxf(v, 0.f);
+          y[(size_t)i * A.fout + c] = v;
+        }
+      }
     }
   }
 }
 
-template <int T>
+template <int T, int Q>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_bwd_kernel(SpmmGemmArgs A, const float* __restrict__ gy, float* __restrict__ dval,
                          float* __restrict__ dx, float* __restrict__ ds_out) {
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* Wt = sm;                                           // [fout][fin] (transposed copy)
-  const int fo4 = (A.fout + 3) & ~3;                        // keeps ds_i 16-byte aligned for the float4 reads below
-  float* grow = sm + ((A.fin * A.fout + 3) & ~3) + (threadIdx.x >> 5) * (A.fin + fo4);   // this warp's g_i ...
-  float* dsrow = grow + fo4;                                // ... and ds_i
+  const int fo4 = (A.fout + 3) & ~3;                        // 16-byte aligned rows for the float4 reads below
+  float* grows = sm + ((A.fin * A.fout + 3) & ~3) + (threadIdx.x >> 5) * kRB * (A.fin + fo4);   // kRB rows of g ...
+  float* dsrows = grows + kRB * fo4;                        // ... and of ds
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
     const int f = c / A.fout, o = c % A.fout;
@@ -287,61 +360,77 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  for (int i = blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); i < A.n; i += gridDim.x * kSpmmWarps) {
-    const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
-    const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
+  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * kRB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * kRB) {
     __syncwarp();
-    for (int c = lane; c < A.fout; c += kWarp) grow[c] = __ldg(gy + (size_t)i * A.fout + c);
-    __syncwarp();
-    for (int f = lane; f < A.fin; f += kWarp) {
-      float d = 0.f;
-#pragma unroll 8
-      for (int c = 0; c < A.fout; ++c) d = fmaf(grow[c], Wt[c * A.fin + f], d);
-      float v = A.theta * d;
-      if (A.beta != 0.f) v = fmaf(A.beta, grow[f], v);
-      dsrow[f] = v;
-      if (ds_out) ds_out[(size_t)i * A.fin + f] = v;
+    for (int r = 0; r < kRB; ++r) {
+      const int i = i0 + r;
+      for (int c = lane; c < fo4; c += kWarp)
+        grows[r * fo4 + c] = (i < A.n && c < A.fout) ? __ldg(gy + (size_t)i * A.fout + c) : 0.f;
     }
     __syncwarp();
-    Vec<4> g[T];
-    const float k1 = A.c1 * rs;
+    // ds[r][f] = theta * sum_c g[r][c] Wt[c][f] + beta * g[r][f]
+    float d[kRB][Q];
+    dense_rows_k<Q>(grows, fo4, Wt, A.fout, A.fin, lane, d);
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int c = 4 * (lg + L * t);
-      if (c < A.fin) {
-        g[t].v = *reinterpret_cast<const float4*>(dsrow + c);
-        g[t].scale(k1);
-      } else {
-        g[t].zero();
+    for (int r = 0; r < kRB; ++r) {
+      const int i = i0 + r;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int f = lane + 32 * q;
+        if (f < A.fin) {
+          float v = A.theta * d[r][q];
+          if (A.beta != 0.f) v = fmaf(A.beta, grows[r * fo4 + f], v);
+          dsrows[r * A.fin + f] = v;
+          if (ds_out && i < A.n) ds_out[(size_t)i * A.fin + f] = v;
+        }
       }
     }
-    for (int w0 = beg; w0 < end; w0 += kWarp) {
-      const int e_l = w0 + lane;
-      const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
-      const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
-      const int cnt = min(kWarp, end - w0);
-#pragma unroll 2
-      for (int j0 = 0; j0 < cnt; j0 += G) {
-        const int j = j0 + grp;
-        const bool valid = j < cnt;
-        const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
-        const float a = __shfl_sync(0xffffffffu, a_l, j & 31);
-        float dot = 0.f;
+    __syncwarp();
+    for (int r = 0; r < kRB; ++r) {
+      const int i = i0 + r;
+      if (i >= A.n) break;
+      const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
+      const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
+      Vec<4> g[T];
+      const float k1 = A.c1 * rs;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const int c = 4 * (lg + L * t);
-          if (c < A.fin && valid) {
-            if (dval) {
-              Vec<4> xv;
-              xv.load(A.x + (size_t)v * A.fin + c);
-              dot += g[t].dot(xv);
-            }
-            if (dx) g[t].red(dx + (size_t)v * A.fin + c, a);
-          }
+      for (int t = 0; t < T; ++t) {
+        const int c = 4 * (lg + L * t);
+        if (c < A.fin) {
+          g[t].v = *reinterpret_cast<const float4*>(dsrows + r * A.fin + c);
+          g[t].scale(k1);
+        } else {
+          g[t].zero();
         }
-        if (dval) {
-          dot = group_sum(dot, L);
-          if (lg == 0 && valid) dval[w0 + j] = dot;
+      }
+      for (int w0 = beg; w0 < end; w0 += kWarp) {
+        const int e_l = w0 + lane;
+        const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
+        const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
+        const int cnt = min(kWarp, end - w0);
+#pragma unroll 2
+        for (int j0 = 0; j0 < cnt; j0 += G) {
+          const int j = j0 + grp;
+          const bool valid = j < cnt;
+          const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
+          const float a = __shfl_sync(0xffffffffu, a_l, j & 31);
+          float dot = 0.f;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const int c = 4 * (lg + L * t);
+            if (c < A.fin && valid) {
+              if (dval) {
+                Vec<4> xv;
+                xv.load(A.x + (size_t)v * A.fin + c);
+                dot += g[t].dot(xv);
+              }
+              if (dx) g[t].red(dx + (size_t)v * A.fin + c, a);
+            }
+          }
+          if (dval) {
+            dot = group_sum(dot, L);
+            if (lg == 0 && valid) dval[w0 + j] = dot;
+          }
         }
       }
     }
@@ -432,15 +521,18 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
   if (n == 0) return DGGB_OK;
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
-  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * fin) * sizeof(float);
+  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * kRB * fin) * sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = rows_grid(n, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    const int grid = rows_grid((n + kRB - 1) / kRB, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, y, s_out);
     return launch_status();
   };
-  return T == 1 ? go(spmm_gemm_fwd_kernel<1>) : (T == 2 ? go(spmm_gemm_fwd_kernel<2>) : go(spmm_gemm_fwd_kernel<4>));
+  const int Q = fout <= 32 ? 1 : (fout <= 64 ? 2 : 4);
+#define DGGB_SG_F(T_) (Q == 1 ? go(spmm_gemm_fwd_kernel<T_, 1>) : (Q == 2 ? go(spmm_gemm_fwd_kernel<T_, 2>) : go(spmm_gemm_fwd_kernel<T_, 4>)))
+  return T == 1 ? DGGB_SG_F(1) : (T == 2 ? DGGB_SG_F(2) : DGGB_SG_F(4));
+#undef DGGB_SG_F
 }
 
 extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
@@ -454,13 +546,17 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
   if (n == 0) return DGGB_OK;
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
-  const size_t smem = ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * (fin + ((fout + 3) & ~3))) * sizeof(float);
+  const size_t smem =
+      ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * kRB * (fin + ((fout + 3) & ~3))) * sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = rows_grid(n, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    const int grid = rows_grid((n + kRB - 1) / kRB, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out);
     return launch_status();
   };
-  return T == 1 ? go(spmm_gemm_bwd_kernel<1>) : (T == 2 ? go(spmm_gemm_bwd_kernel<2>) : go(spmm_gemm_bwd_kernel<4>));
+  const int Q = fin <= 32 ? 1 : (fin <= 64 ? 2 : 4);
+#define DGGB_SG_B(T_) (Q == 1 ? go(spmm_gemm_bwd_kernel<T_, 1>) : (Q == 2 ? go(spmm_gemm_bwd_kernel<T_, 2>) : go(spmm_gemm_bwd_kernel<T_, 4>)))
+  return T == 1 ? DGGB_SG_B(1) : (T == 2 ? DGGB_SG_B(2) : DGGB_SG_B(4));
+#undef DGGB_SG_B
 }

@@ -18,6 +18,9 @@ def _require_cuda(*ts):
             raise RuntimeError("dgg_b200 ops need CUDA tensors (no CPU fallback)")
 
 
+import os as _os
+
+_NO_FUSED_CONV = bool(_os.environ.get("DGGB_NO_FUSED_CONV"))
 _FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu
 _LONG_ROW = 1024       # kRankCap of csrc/dgg_edge.cu: longer rows are ranked by a grid-wide launch
 
@@ -215,6 +218,8 @@ def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2
     fused kernel's range (Fin % 4 != 0, Fin or Fout > 128)."""
     fin, fout = x.shape[1], w.shape[1]
     if not (x.is_cuda and fin % 4 == 0 and fin <= 128 and fout <= 128 and (beta == 0.0 or fin == fout)):
+        return None
+    if _NO_FUSED_CONV:      # A/B measurements: DGGB_NO_FUSED_CONV=1 selects SpMM + library GEMM + elementwise ops
         return None
     return _SpmmGemm.apply(vals, x, w, h0, resid, graph, row_scale, float(c1), float(c2), float(theta), float(beta),
                            bool(relu))
