@@ -63,10 +63,11 @@ def declared_symbols():
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.isfile(LIB_PATH):
+        path = os.environ.get("DGGB_LIB", LIB_PATH)      # an alternative build of the same ABI (A/B measurements)
+        if not os.path.isfile(path):
             raise DggbError(
-                f"{LIB_PATH} not built: run `python __graft_entry__.py build` (there is no CPU fallback)")
-        L = ctypes.CDLL(LIB_PATH)
+                f"{path} not built: run `python __graft_entry__.py build` (there is no CPU fallback)")
+        L = ctypes.CDLL(path)
         for name, (restype, argtypes) in prototypes().items():
             fn = getattr(L, name)
             fn.restype = restype

@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc not found: cannot build libdggb.so")
     # no -lcuda: the one driver call (cuTensorMapEncodeTiled) is resolved through cudaGetDriverEntryPoint
     extra = os.environ.get("DGGB_NVCC_EXTRA", "").split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    out = os.environ.get("DGGB_LIB_OUT", LIB_PATH)      # e.g. an instrumented build next to the product library
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

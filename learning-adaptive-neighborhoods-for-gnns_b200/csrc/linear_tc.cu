@@ -1,10 +1,13 @@
 // Node-encoder GEMM on the 5th-gen tensor cores:  out[N,H] = act(x[N,F] W[H,F]^T + b),  act = LeakyReLU(slope)
 // (nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126, and y = x_enc We^T).
 //
-// fp32 in / fp32 out with ~fp32 accuracy: the x tile is split into TF32 hi + lo parts by four converter warps
-// (thread == row: swizzled LDS -> registers -> tcgen05.st into TENSOR MEMORY) and the product is accumulated as
-// hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator (3xTF32) by "TS" MMAs (A from TMEM, B = pre-split W from
-// shared memory).  x is read from HBM exactly once (no pre-split copy): N*F*4 + N*H*4 bytes.
+// fp32 in / fp32 out with ~fp32 accuracy (3xTF32: hi*hi + hi*lo + lo*hi in one fp32 TMEM accumulator):
+//   * hi * [W_hi ; W_lo]: the tensor core reads the RAW fp32 x tile straight from the TMA-filled shared memory
+//     ("SS" MMA).  kind::tf32 ignores the low 13 mantissa bits of its operands, i.e. it computes with
+//     hi = trunc_tf32(x) -- no conversion pass sits between the TMA and this, the larger, product;
+//   * lo * W_hi: four converter warps (thread == row) read the same tile, form lo = x - trunc_tf32(x) (one AND, one
+//     SUB per element, exact in fp32) and hand it to the tensor core through TENSOR MEMORY (tcgen05.st -> "TS" MMA).
+// x is read from HBM exactly once (no pre-split copy): N*F*4 + N*H*4 bytes.
 //
 // CTA = 128 rows of x.  warp 0: TMA producer (x box 128x32 ring + [W_hi ; W_lo] box 2Hx32 ring per k-block),
 // warps 2-5: converters, then epilogue (tcgen05.ld -> bias -> LeakyReLU -> global), warp 1: MMA issuer + TMEM.
@@ -53,8 +56,15 @@ using tc::tmem_st_wait;
 //
 // Pipeline (clock64 trace of the previous single-ring version: the k-loop ran at ~1200 cycles per k-block because
 // a stage was only recycled after TMA latency + conversion + MMA, 3 stages deep):
-//   * x ring (XS x 16 KB, HBM stream) is released by the converters as soon as the tile is in registers;
-//   * W ring (WS x [W_hi ; W_lo] stacked along N, L2-resident) is released by the MMA commit;
+//   * x ring (XS x 16 KB, HBM stream): a stage is released once the converters have it in registers AND the hi MMAs
+//     that read it have retired;
+//   * W ring (WS x [W_hi ; W_lo] stacked along N, L2-resident) is released by the commit of the lo MMAs;
+//   * the hi MMAs of k-block k+1 are issued BEFORE the lo MMAs of k-block k: the only work that waits for the
+//     converters is the small lo product, and four TMEM lo buffers keep their tcgen05.st off the critical path.
+//     Measured (profiles/r02_linear_trace.md): the k-block period is ~1050 cycles either way -- each tcgen05.mma
+//     takes ~95 cycles to issue because the operand reads, the TMA writes and the converters' LDS share the SM's
+//     shared-memory bandwidth (88 KB per k-block here, 72 KB when both A halves went through TMEM); the HBM rate
+//     would allow 720;
 //   * one producer thread polls both rings; the first XS + WS loads are issued before the TMEM allocation.
 //   * 3xTF32 as TWO MMAs per k-step instead of three: A_hi x [W_hi ; W_lo]^T (N = 2H: hi*hi | hi*lo side by side
 //     in the accumulator) and A_lo x W_hi^T (N = H, accumulated onto the hi*hi columns); the epilogue adds the two
@@ -83,7 +93,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   constexpr uint32_t kWStage = 2 * kWBytes;        // [W_hi ; W_lo]: 2H rows
   constexpr uint32_t kRing = XS * kXBytes + WS * kWStage;
   constexpr uint32_t kAccCols = 2 * H;             // hi*hi (+ lo*hi) | hi*lo
-  constexpr uint32_t kTmemCols = (kAccCols + 128 <= 256) ? 256 : 512;   // + 2 x (A hi 32 cols | A lo 32 cols)
+  constexpr int kAB = 4;                           // TMEM buffers of the lo operand (32 columns each)
+  constexpr uint32_t kTmemCols = (kAccCols + 128 <= 256) ? 256 : 512;   // + kAB x (A lo 32 cols)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing);
   pdl_trigger();
@@ -92,12 +103,12 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   if (threadIdx.x == 0 && blockIdx.x < 1024) { uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_lin_smid[blockIdx.x] = (int)sm; }
 #endif
   uint64_t* x_full = bars;                    // [XS] TMA landed
-  uint64_t* x_empty = x_full + XS;            // [XS] 4 converter warps have the tile in registers
+  uint64_t* x_empty = x_full + XS;            // [XS] 4 converter warps have the tile in registers + hi MMAs retired
   uint64_t* w_full = x_empty + XS;            // [WS]
   uint64_t* w_empty = w_full + WS;            // [WS] MMAs that read it retired (commit)
-  uint64_t* a_full = w_empty + WS;            // [2] A (hi/lo) written to TMEM by the 4 converter warps
-  uint64_t* a_empty = a_full + 2;             // [2] MMAs that read it retired
-  uint64_t* acc_full = a_empty + 2;
+  uint64_t* a_full = w_empty + WS;            // [kAB] lo operand written to TMEM by the 4 converter warps
+  uint64_t* a_empty = a_full + kAB;           // [kAB] MMAs that read it retired
+  uint64_t* acc_full = a_empty + kAB;
   uint64_t* w2_full = acc_full + 1;           // W2 hi/lo landed (second GEMM)
   uint64_t* a2_full = acc_full + 2;           // activated tile written to TMEM by the 4 epilogue warps
   uint64_t* acc2_full = acc_full + 3;
@@ -124,13 +135,13 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tc::tma_prefetch_desc(&tm_w);
     for (int s = 0; s < XS; ++s) {
       tc::mbar_init(x_full + s, 1);
-      tc::mbar_init(x_empty + s, 4);
+      tc::mbar_init(x_empty + s, 5);
     }
     for (int s = 0; s < WS; ++s) {
       tc::mbar_init(w_full + s, 1);
       tc::mbar_init(w_empty + s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAB; ++s) {
       tc::mbar_init(a_full + s, 4);
       tc::mbar_init(a_empty + s, 1);
     }
@@ -186,26 +197,39 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     if (lane == 0) {
       constexpr uint32_t idesc2 = tc::idesc_tf32(kLinBM, 2 * H);
       constexpr uint32_t idesc1 = tc::idesc_tf32(kLinBM, H);
-      uint32_t acc = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int ab = kb & 1, ws = kb % WS;
-        tc::mbar_wait_backoff(a_full + ab, (kb >> 1) & 1);    // x hi/lo of this k-block in tensor memory
-        LTRACE(136 + kb);
-        tc::mbar_wait_backoff(w_full + ws, (kb / WS) & 1);    // [W_hi ; W_lo] of this k-block in shared memory
+      // hi(kb): raw x tile (shared memory, truncated to tf32 by the tensor core) x [W_hi ; W_lo] -> [hi*hi | hi*lo]
+      auto issue_hi = [&](int kb) {
+        const int xs = kb % XS, ws = kb % WS;
+        tc::mbar_wait_backoff(x_full + xs, (kb / XS) & 1);
+        tc::mbar_wait_backoff(w_full + ws, (kb / WS) & 1);
         LTRACE(24 + kb);
         tc::fence_after_sync();
+        const uint32_t xst = tc::smem_u32(smem + xs * kXBytes);
         const uint32_t wst = tc::smem_u32(smem + XS * kXBytes + ws * kWStage);
-        const uint32_t ah = tmem_a0 + ab * 64, al = ah + 32;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t bdesc = tc::smem_desc_k128(wst + ks * 32);
-          mma_tf32_ts(tmem_base, ah + ks * 8, bdesc, idesc2, acc);   // [hi*hi | hi*lo]
-          mma_tf32_ts(tmem_base, al + ks * 8, bdesc, idesc1, 1u);    // hi*hi columns += lo*hi
-          acc = 1;
-        }
+        for (int ks = 0; ks < 4; ++ks)
+          tc::mma_tf32(tmem_base, tc::smem_desc_k128(xst + ks * 32), tc::smem_desc_k128(wst + ks * 32), idesc2,
+                       (kb | ks) ? 1u : 0u);
+        tc::mma_commit(x_empty + xs);
+      };
+      // lo(kb): lo operand (tensor memory) x W_hi, accumulated onto the hi*hi columns
+      auto issue_lo = [&](int kb) {
+        const int ab = kb % kAB, ws = kb % WS;
+        tc::mbar_wait_backoff(a_full + ab, (kb / kAB) & 1);
+        LTRACE(136 + kb);
+        tc::fence_after_sync();
+        const uint32_t wst = tc::smem_u32(smem + XS * kXBytes + ws * kWStage);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          mma_tf32_ts(tmem_base, tmem_a0 + ab * 32 + ks * 8, tc::smem_desc_k128(wst + ks * 32), idesc1, 1u);
         tc::mma_commit(w_empty + ws);
         tc::mma_commit(a_empty + ab);
         LTRACE(40 + kb);
+      };
+      issue_hi(0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        if (kb + 1 < num_kb) issue_hi(kb + 1);
+        issue_lo(kb);
       }
       tc::mma_commit(acc_full);
       if (FUSE2) {
@@ -232,27 +256,26 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     const int r_in_tile = q * 32 + lane;          // == TMEM lane this thread may access
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int kb = 0; kb < num_kb; ++kb) {
-      const int ab = kb & 1, xs = kb % XS;
+      const int ab = kb % kAB, xs = kb % XS;
       tc::mbar_wait(x_full + xs, (kb / XS) & 1);
       if (threadIdx.x == 64) LTRACE(72 + kb);
       // row r of the box: 128 B at r*128, its 16-B chunk c stored at chunk position c ^ (r & 7)
       const uint8_t* rowp = smem + xs * kXBytes + r_in_tile * 128;
-      uint32_t hi[32], lo[32];
+      uint32_t lo[32];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r_in_tile & 7)) << 4));
-        const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
-        hi[4 * c + 0] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
-        hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-        lo[4 * c + 0] = __float_as_uint(tf32_rna(v.x - h0)); lo[4 * c + 1] = __float_as_uint(tf32_rna(v.y - h1));
-        lo[4 * c + 2] = __float_as_uint(tf32_rna(v.z - h2)); lo[4 * c + 3] = __float_as_uint(tf32_rna(v.w - h3));
+        // lo = x - trunc_tf32(x): what the hi MMA (which ignores the low 13 mantissa bits of the raw tile) leaves out
+        lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+        lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+        lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+        lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
       }
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(x_empty + xs);        // tile is in registers: the stage can be refilled
-      tc::mbar_wait(a_empty + ab, ((kb >> 1) & 1) ^ 1);    // previous MMAs on this A buffer retired
+      if (lane == 0) tc::mbar_arrive(x_empty + xs);        // tile is in registers (the hi MMAs release it as well)
+      tc::mbar_wait(a_empty + ab, ((kb / kAB) & 1) ^ 1);   // previous MMAs on this lo buffer retired
       tc::fence_after_sync();
-      tmem_st_32x32(tmem_a0 + lane_addr + ab * 64, hi);
-      tmem_st_32x32(tmem_a0 + lane_addr + ab * 64 + 32, lo);
+      tmem_st_32x32(tmem_a0 + lane_addr + ab * 32, lo);
       tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
