@@ -341,6 +341,24 @@ int dggb_allpairs_pair_bwd(const float* z, int32_t n, int32_t d, int32_t row_beg
                            const int32_t* idx, const float* gy /* [row_count,kc] */, int32_t kc,
                            const float* t, float* dz, float* dt, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * One-shot all-reduce (sum) of a flat fp32 buffer over NVLink peer memory, for use INSIDE a captured step: the
+ * data-parallel drivers sum the replicated DGG / conv weight gradients after every backward; as an NCCL
+ * call that is a fixed 20-35 us launch behind a ~110 us step.
+ *   bufs_dev  [world] device array: pointer to every rank's symmetric buffer (peer-mapped; index = rank)
+ *   pads_dev  [world] device array: pointer to every rank's signal pad (uint32 slots, zero on first use); slots
+ *             [pad_slot_base, pad_slot_base + 2 world) are used
+ *   out       [count] local result (may not alias the symmetric buffer: peers read it until the end barrier)
+ *   state     [2] uint32, zero on first use: sequence number + block counter (device-resident: graph replays
+ *             cannot change kernel arguments)
+ *   multicast_ptr: NULL, or the NVSwitch multicast address of the same buffers -- then ONE multimem.ld_reduce per
+ *             16 bytes replaces the `world` peer loads (the switch does the sum)
+ * Every rank must call it the same number of times; count % 4 == 0; world <= 16.
+ * ---------------------------------------------------------------------------------- */
+int dggb_allreduce_oneshot(void* const* bufs_dev, void* const* pads_dev, int32_t rank, int32_t world, int64_t count,
+                           float* out, uint32_t* state, const void* multicast_ptr, int32_t pad_slot_base,
+                           int32_t blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

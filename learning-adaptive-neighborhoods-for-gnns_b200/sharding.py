@@ -75,11 +75,15 @@ def all_reduce_grads(params, group=None):
         off += g.numel()
 
 
-def flatten_grads(params):
+def flatten_grads(params, flat=None):
     """Back every ``p.grad`` by a view into ONE flat buffer, so a single all-reduce of that buffer (no
-    concatenation, capturable in a CUDA graph) sums all replicated-parameter gradients.  Returns the buffer."""
+    concatenation, capturable in a CUDA graph) sums all replicated-parameter gradients.  Returns the buffer
+    (``flat``: use this preallocated buffer, e.g. ``PeerAllReduce.buffer``, instead of a new one)."""
     params = [p for p in params if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype, device=params[0].device)
+    total = sum(p.numel() for p in params)
+    if flat is None:
+        flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+    assert flat.numel() >= total
     off = 0
     for p in params:
         p.grad = flat[off:off + p.numel()].view_as(p)
@@ -107,3 +111,140 @@ def sharded_spmm(vals_local, x_local, graph_local, n, group=None, row_scale=None
 
     x_all = all_gather_rows(x_local, n, group)
     return K.spmm(vals_local, x_all, graph_local, row_scale)
+
+
+class PeerAllReduce:
+    """Sum of a flat fp32 buffer over the ranks by ONE kernel over NVLink peer memory (``dggb_allreduce_oneshot``),
+    launched on the caller's stream: it can be captured into the CUDA graph of the training step, unlike a
+    library collective issued after the replay.
+
+        ar = PeerAllReduce(numel)            # collective: every rank constructs it
+        flatten_grads(params, ar.buffer)     # gradients accumulate straight into symmetric memory
+        ... backward ...
+        total = ar()                         # -> ar.out [numel]: the sum over ranks, identical bits on every rank
+
+    The buffer lives in ``torch.distributed._symmetric_memory`` (peer-mapped; bound to an NVSwitch multicast
+    object when the fabric supports it, in which case the switch performs the reduction: multimem.ld_reduce).
+    ``PeerAllReduce.available()`` is False where symmetric memory cannot be set up (then use ``dist.all_reduce``)."""
+
+    PAD_SLOT_BASE = 1024      # uint32 slots of the signal pad this kernel owns (torch's own barriers use low slots)
+
+    def __init__(self, numel, group=None, use_multicast=True, blocks=8):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import lib
+
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.numel = int(numel)
+        padded = (self.numel + 3) // 4 * 4
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._sym = symm_mem.empty(padded, dtype=torch.float32, device=dev)
+        self._sym.zero_()
+        self._hdl = symm_mem.rendezvous(self._sym, self.group.group_name)
+        assert self._hdl.signal_pad_size >= 4 * (self.PAD_SLOT_BASE + 2 * self.world)
+        self.buffer = self._sym[:self.numel]
+        self._out = torch.zeros(padded, dtype=torch.float32, device=dev)
+        self.out = self._out[:self.numel]
+        self._state = torch.zeros(2, dtype=torch.int32, device=dev)
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        self.multicast = mc != 0
+        self._mc = mc
+        self._blocks = int(blocks)
+        self._lib = lib()
+        torch.cuda.synchronize()
+        dist.barrier(self.group)            # every rank's pad and state are zeroed before the first call
+
+    @staticmethod
+    def available():
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+
+            return torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+        except Exception:
+            return False
+
+    def __call__(self):
+        from ._lib import check, stream
+
+        check(self._lib.dggb_allreduce_oneshot(int(self._hdl.buffer_ptrs_dev), int(self._hdl.signal_pad_ptrs_dev),
+                                               self.rank, self.world, self._sym.numel(), self._out.data_ptr(),
+                                               self._state.data_ptr(), self._mc or None, self.PAD_SLOT_BASE,
+                                               self._blocks, stream()), "allreduce_oneshot")
+        return self.out
+
+
+class RowShardedSAGE_DGG(torch.nn.Module):
+    """``SAGE_DGG``-style model (reference model.py:122-193) for graphs too large for one GPU, with the all-pairs DGG
+    of the north star instead of an input edge list (BASELINE.json configs[3]; the reference's own answer,
+    train_reddit.py:340-369, feeds the 233 k-node graph to a dense N x N pipeline and cannot run).
+
+    Rank r owns the contiguous node block [r ceil(N/R), ...): rows of the scores, of the learned adjacency, of X.
+      z = softmax(LeakyReLU(x Wz + bz))                      local rows        (dgm.py:217-221)
+      all_gather(z) -> y_ij = -t |z_i - z_j| + G_ij, top-Kc of every local row (tcgen05 score GEMM + streaming
+                        top-K, Philox Gumbel noise keyed on (row, col): no exchange)            (dgm.py:275-301)
+      a_ij = exp(y_ij) * (1 - 0.5 (1 + tanh(rank_ij - k_i)))   (the live pipeline of SURVEY A.2 on P = exp(-t D))
+      s_i = sum_j a_ij;  all_gather(s^-1/2)  ->  ahat_ij = a_ij s_i^-1/2 s_j^-1/2            (model.py:146-149)
+      per conv layer (PyG DenseGraphConv, aggr = mean; model.py:128-129):
+          p = h W_rel^T (local, narrow);  all_gather(p);  agg = (ahat p_all) / clamp(rowsum(ahat), 1)
+          h' = agg + b_rel + h W_root^T
+    Backward: the autograd of ``all_gather_rows`` is the matching reduce-scatter (column-side gradients of p, z and
+    s^-1/2 travel back to the owners); replicated-parameter gradients are summed by the caller."""
+
+    def __init__(self, nfeat, nhidden, nclass, d=64, kc=32, k_init=9.0, t_init=4.0):
+        super().__init__()
+        nn = torch.nn
+        self.input_project = nn.Sequential(nn.Linear(nfeat, d), nn.LeakyReLU(), nn.Softmax(dim=-1))
+        self.t = nn.Parameter(torch.full((1,), float(t_init)))
+        self.k_net = nn.Linear(nfeat, 1)
+        self.lin_rel1, self.lin_root1 = nn.Linear(nfeat, nhidden), nn.Linear(nfeat, nhidden, bias=False)
+        self.lin_rel2, self.lin_root2 = nn.Linear(nhidden, nclass), nn.Linear(nhidden, nclass, bias=False)
+        with torch.no_grad():
+            self.k_net.weight.mul_(0.1)
+            self.k_net.bias.fill_(k_init)
+        self.kc = int(kc)
+
+    def adjacency(self, x_local, n, group, seed):
+        """-> (idx [cnt, kc] global columns, ahat [cnt, kc], row scale [cnt] = 1 / clamp(rowsum(ahat), 1))"""
+        from . import functional as K
+
+        z = self.input_project(x_local)
+        k = torch.relu(self.k_net(x_local)) + 1.0                                  # [cnt, 1], >= 1 (dgm.py:1580-1584)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            idx, y = sharded_allpairs_topk(z, self.t, n, self.kc, group, seed=seed, noise_scale=1.0)
+        else:
+            idx, y = K.allpairs_topk(z, self.t, None, self.kc, 3, seed=seed, noise_scale=1.0)
+        r = torch.arange(self.kc, device=x_local.device, dtype=torch.float32).reshape(1, -1)
+        a = torch.exp(y) * (1 - 0.5 * (1 + torch.tanh(r - k)))                     # dgm.py:1213-1229, 1410-1417
+        dinv = a.sum(-1).clamp_min(1e-30) ** -0.5                                  # [cnt]
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dinv_all = all_gather_rows(dinv.unsqueeze(-1), n, group).squeeze(-1)
+        else:
+            dinv_all = dinv
+        ahat = a * dinv.unsqueeze(-1) * dinv_all[idx.long()]
+        scale = 1.0 / ahat.sum(-1).clamp(min=1)
+        return idx, ahat, scale
+
+    def forward(self, x_local, n, group=None, seed=0):
+        from . import functional as K
+        from .graph import CSRGraph
+
+        group = dist.group.WORLD if (group is None and dist.is_initialized()) else group
+        sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+        cnt = x_local.shape[0]
+        idx, ahat, scale = self.adjacency(x_local, n, group, seed)
+        rowptr = torch.arange(0, (cnt + 1) * self.kc, self.kc, dtype=torch.int32, device=x_local.device)
+        g = CSRGraph(cnt, rowptr, idx.reshape(-1).contiguous())          # local rows, GLOBAL column ids
+        g._max_row_nnz = self.kc
+        vals = ahat.reshape(-1)
+        h = x_local
+        for lin_rel, lin_root, last in ((self.lin_rel1, self.lin_root1, False), (self.lin_rel2, self.lin_root2, True)):
+            p = torch.nn.functional.linear(h, lin_rel.weight)            # aggregate in the narrow space
+            fo = p.shape[1]
+            if fo % 4:                                                   # 128-bit gathers: pad 41 classes to 44
+                p = torch.nn.functional.pad(p, (0, 4 - fo % 4))
+            p_all = all_gather_rows(p, n, group) if sharded else p
+            agg = K.spmm(vals, p_all, g, scale)[:, :fo]
+            h_new = agg + lin_rel.bias + lin_root(h)
+            h = h_new if last else torch.nn.functional.dropout(torch.relu(h_new), 0.5, self.training)
+        return torch.log_softmax(h, dim=-1), idx, ahat
