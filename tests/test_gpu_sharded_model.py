@@ -38,25 +38,32 @@ def test_row_sharded_sage_dgg_matches_dense_restatement():
 
     from dgg_b200 import sharding as S
 
-    n, f, hdim, c, kc, seed = 700, 40, 16, 5, 32, 11
+    n, f, hdim, c, kc = 300, 40, 16, 5, 16
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(n, f, generator=gen)
     labels = torch.randint(0, c, (n,), generator=gen)
     torch.manual_seed(1)
-    m = S.RowShardedSAGE_DGG(f, hdim, c, d=32, kc=kc, k_init=6.0, t_init=3.0).eval()
+    m = S.RowShardedSAGE_DGG(f, hdim, c, d=32, kc=kc, k_init=4.0, t_init=3.0).eval()
+    # a swap of two near-tied scores inside a row's window moves weight between two columns, i.e. it changes the
+    # output and every gradient: pick (deterministically) a noise seed whose selected scores are all > 5e-5 apart,
+    # an order of magnitude above the 3xTF32-vs-fp64 distance error, so that EVERYTHING can be asserted tightly
+    for seed in range(1, 200):
+        with torch.no_grad():
+            _, y = _dense_forward(m, x, seed, kc)
+            srt = torch.sort(y, -1, descending=True).values[:, :kc + 1]
+        if float((srt[:, :-1] - srt[:, 1:]).min()) > 5e-5:
+            break
+    else:
+        pytest.fail("no tie-free noise seed found")
     ref = copy.deepcopy(m)
-    want, y = _dense_forward(ref, x, seed, kc)
+    want, _ = _dense_forward(ref, x, seed, kc)
     F.nll_loss(want, labels).backward()
     m = m.cuda()
     got, idx, ahat = m(x.cuda(), n, seed=seed)
-    # rows whose selected scores are well separated must agree everywhere (3xTF32 distances differ by ~1e-6)
-    srt = torch.sort(y.detach(), -1, descending=True).values[:, :kc + 1]
-    ok = ((srt[:, :-1] - srt[:, 1:]) > 1e-4).all(-1)
-    assert ok.float().mean() > 0.8
-    torch.testing.assert_close(got.detach().cpu()[ok], want.detach()[ok], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-4, atol=1e-4)
     F.nll_loss(got, labels.cuda()).backward()
     for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
-        assert_grad_close(p.grad.cpu(), q.grad, rtol=2e-2, atol_rel=2e-3, what=name)
+        assert_grad_close(p.grad.cpu(), q.grad, rtol=5e-3, atol_rel=1e-3, what=name)
 
 
 def test_row_blocks_reproduce_the_unsharded_adjacency():
