@@ -417,8 +417,7 @@ def run_ours(args, rank, local_rank, world):
             reddit = dict(error=repr(e)[:300])
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     roofline = kernel_roofline(m, dsets, shape)
@@ -448,8 +447,19 @@ def run_ours(args, rank, local_rank, world):
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, parity=parity, clocks=clocks, epoch=epoch,
                 reddit=reddit)
     print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Every rank leaves together and without the process-group / symmetric-memory teardown (which can block when
+    the peers are already gone): rank 0 still runs the single-GPU legs (roofline, parity) after the others are done."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def reddit_record(rank, world, dev, steps=4, warmup=2):

@@ -64,16 +64,41 @@ __global__ void __launch_bounds__(kPeerThreads)
   // ---- 2. sum
   const long long n4 = count >> 2;
   const long long tid = (long long)blockIdx.x * kPeerThreads + threadIdx.x, nth = (long long)gridDim.x * kPeerThreads;
-  if (mc != nullptr) {
-    for (long long i = tid; i < n4; i += nth) st4(out + 4 * i, multimem_sum4(mc + 4 * i));
-  } else {
-    for (long long i = tid; i < n4; i += nth) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int p = 0; p < world; ++p) {            // same order on every rank: bit-identical sums everywhere
-        const float4 v = ld_volatile4(bufs[p] + 4 * i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  // (loads are issued in batches of four before any of them is consumed: a load -> store -> load chain would cost one
+  //  NVLink round trip per element)
+  constexpr int kB = 4;
+  for (long long i0 = tid; i0 < n4; i0 += nth * kB) {
+    float4 acc[kB];
+    if (mc != nullptr) {
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const long long i = i0 + b * nth;
+        acc[b] = i < n4 ? multimem_sum4(mc + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      st4(out + 4 * i, acc);
+    } else {
+#pragma unroll
+      for (int b = 0; b < kB; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p0 = 0; p0 < world; p0 += 4) {        // same order on every rank: bit-identical sums everywhere
+        float4 v[kB][4];
+#pragma unroll
+        for (int b = 0; b < kB; ++b)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const long long i = i0 + b * nth;
+            v[b][pp] = (i < n4 && p0 + pp < world) ? ld_volatile4(bufs[p0 + pp] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int b = 0; b < kB; ++b)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            acc[b].x += v[b][pp].x; acc[b].y += v[b][pp].y; acc[b].z += v[b][pp].z; acc[b].w += v[b][pp].w;
+          }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kB; ++b) {
+      const long long i = i0 + b * nth;
+      if (i < n4) st4(out + 4 * i, acc[b]);
     }
   }
   // ---- 3. everybody is done reading (the last block of this rank speaks for it)

