@@ -313,10 +313,11 @@ def run_ours(args, rank, local_rank, world):
 
         if world > 1 and PeerAllReduce.available() and not os.environ.get("DGGB_NO_PEER_AR"):
             try:    # gradients accumulate straight into symmetric (peer-mapped) memory; the sum is a captured kernel
-                peer_ar = PeerAllReduce(sum(p.numel() for p in params))
-                flat_grads = flatten_grads(params, peer_ar.buffer)
-                grad_sync = ("in-graph one-shot all-reduce kernel over NVLink peer memory"
-                             + (" (NVSwitch multicast reduction)" if peer_ar.multicast else " (P2P loads)"))
+                n_par = sum(p.numel() for p in params)      # two buffers, alternated by the graphs: no end barrier
+                peer_ar = [PeerAllReduce(n_par, end_barrier=False) for _ in range(2)]
+                flat_grads = flatten_grads(params, peer_ar[0].buffer)
+                grad_sync = ("in-graph one-shot all-reduce kernel over NVLink peer memory, double-buffered"
+                             + (" (NVSwitch multicast reduction)" if peer_ar[0].multicast else " (P2P loads)"))
             except Exception as e:   # symmetric memory not available on this fabric: captured NCCL all-reduce
                 peer_ar = None
                 grad_sync = f"NCCL all_reduce captured in the step graph (symmetric memory unavailable: {repr(e)[:80]})"
@@ -325,20 +326,27 @@ def run_ours(args, rank, local_rank, world):
             if world > 1 and grad_sync.startswith("none"):
                 grad_sync = "NCCL all_reduce captured in the step graph"
 
-        def graph_body(s):
+        def graph_body(s, j):
             out = eager_step(s, True)
             if world > 1:
                 if peer_ar is not None:
-                    peer_ar()
+                    peer_ar[j % 2]()
                 else:
                     dist.all_reduce(flat_grads)
             return out
 
-        graphed = [dgg_b200.GraphedStep(lambda s=s: graph_body(s)) for s in dsets]
+        graphed = []
+        for j, s in enumerate(dsets):       # N_SETS is even: consecutive replays alternate between the two buffers
+            if peer_ar is not None:
+                flat_grads = flatten_grads(params, peer_ar[j % 2].buffer)    # this graph's static .grad views
+            graphed.append(dgg_b200.GraphedStep(lambda s=s, j=j: graph_body(s, j)))
+
+    replay_no = [0]     # a running index (not the caller's): consecutive replays must alternate the gradient buffers
 
     def step_resident(i):
         if graphed is not None:
-            graphed[i % N_SETS]()
+            graphed[replay_no[0] % N_SETS]()
+            replay_no[0] += 1
         else:
             eager_step(dsets[i % N_SETS])
             if world > 1:
@@ -399,6 +407,7 @@ def run_ours(args, rank, local_rank, world):
     launches = int(L.dggb_kernel_launches() - l0)
     if graphed is not None:   # replayed graphs launch the kernels recorded at capture time
         launches = sum(graphed[i % N_SETS].dggb_launches_per_replay for i in range(args.steps))
+        assert N_SETS % 2 == 0
     for i in range(max(3, args.warmup)):
         step_e2e(i)
     staged.clear()          # the timed region starts with nothing prefetched
@@ -422,6 +431,8 @@ def run_ours(args, rank, local_rank, world):
 
     roofline = kernel_roofline(m, dsets, shape)
     epoch = full_model_epoch(dsets, shape, dev) if world == 1 else None
+    if epoch is not None and not os.environ.get("DGGB_BENCH_NO_CONFIGS"):
+        epoch["configs"] = config_epochs(dev, dsets)
     cpu, parity = None, None
     if world == 1:
         torch.set_num_threads(os.cpu_count())
@@ -651,6 +662,163 @@ def full_model_epoch(dsets, shape, dev, iters=20):
     return res
 
 
+def _step_timer(fn, iters=10, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def _sparse_features(n, f, density, seed):
+    """Bag-of-words style features (Cora 1.3 % / Citeseer 0.9 % dense), row-normalised like T.NormalizeFeatures."""
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(n, f, generator=g) < density).float()
+    x[torch.arange(n), torch.randint(0, f, (n,), generator=g)] = 1.0
+    return x / x.sum(-1, keepdim=True)
+
+
+def config_epochs(dev, pubmed_sets):
+    """BASELINE.json configs[0..2] as training steps (forward, nll loss, backward, the script's Adam groups) on
+    synthetic graphs of the named shapes, eager and as a CUDA-graph replay, next to the CPU oracle's fwd+bwd of the
+    same model (dense reference algorithm, this box's host cores):
+      Cora-shape  GCN_DGG   (DGG_LearnableK_debug: u-v-deg, k-net x, k_times_edge_prob)   N = 2 708, F = 1 433
+      Citeseer-shape GCNII_DGG, 64 layers, 2 DGG layers                                  N = 3 327, F = 3 703
+      Pubmed-shape GAT_DGG_00, 8 heads + 1 (GPU only: the dense reference needs ~40 GB per backward)"""
+    import torch.nn.functional as F
+
+    import dgg_b200
+    import model as models
+    from oracle import dgg_oracle as O
+
+    out = []
+    lk = dict(extra_edge_dim=2, extra_k_dim=1, dgg_hard=False, deg_mean=3.899, deg_std=5.288,
+              dgg_mode_edge_net="u-v-deg", dgg_mode_k_net="x", dgg_mode_k_select="k_times_edge_prob", debug_step=3,
+              perturb_edge_prob=False, symmetric_noise=True, stochastic_k=False, dgg_adj_input="input_adj",
+              n_dgg_layers=2)
+
+    def build_graph(n, mean_deg, seed):
+        idx, val = chung_lu_graph(n, mean_deg, 60, seed)
+        keep = idx[0] != idx[1]                     # the scripts pass the graph WITHOUT self loops
+        return idx[:, keep].contiguous(), val[keep]
+
+    def run(name, cls, n, f, c, density, mean_deg, layers, args, hidden=64, lr=0.01, cpu=None):
+        idx, val = build_graph(n, mean_deg, 7)
+        x = _sparse_features(n, f, density, 8)
+        g = torch.Generator().manual_seed(9)
+        labels = torch.randint(0, c, (n,), generator=g)
+        train_idx = torch.arange(140)
+        torch.manual_seed(0)
+        net = models.__dict__[cls](nfeat=f, nlayers=layers, nhidden=hidden, nclass=c, dropout=0.6, lamda=0.5,
+                                   alpha=0.1, variant=False, args=argparse.Namespace(**args))
+        state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        net = net.to(dev)
+        adj = torch.sparse_coo_tensor(idx.to(dev), val.to(dev), (n, n)).coalesce()
+        dgg_b200.CSRGraph.from_coo(adj)
+        xd, yd, ti = x.to(dev), labels.to(dev), train_idx.to(dev)
+        groups = ([dict(params=net.params1, weight_decay=0.01), dict(params=net.params2, weight_decay=5e-4)]
+                  if "II" in cls else [dict(params=net.params1, weight_decay=5e-4), dict(params=net.params2, weight_decay=0)])
+        rec = dict(model=cls, shape=name, n=n, f=f, layers=layers, edges=int(idx.shape[1]))
+
+        def make_step(opt):
+            def step(_i=0):
+                net.train()
+                opt.zero_grad(set_to_none=True)
+                res = net(xd, adj)
+                logp = res[0] if isinstance(res, tuple) else res
+                loss = F.nll_loss(logp[ti], yd[ti])
+                loss.backward()
+                opt.step()
+                return loss
+            return step
+
+        rec["train_step_ms"] = _step_timer(make_step(torch.optim.Adam(groups, lr=lr, fused=True)))
+        try:
+            gs = dgg_b200.GraphedStep(make_step(torch.optim.Adam(groups, lr=lr, capturable=True, fused=True)))
+            rec["train_step_graph_ms"] = _step_timer(lambda i: gs(), iters=20)
+        except Exception as e:
+            rec["train_step_graph_ms"], rec["train_step_graph_error"] = None, repr(e)[:200]
+        if cpu is not None:
+            torch.set_num_threads(os.cpu_count())
+            cpu(x, idx, val, n, state, labels, train_idx)                       # warm the thread pool
+            t0 = time.perf_counter()
+            cpu(x, idx, val, n, state, labels, train_idx)
+            rec["cpu_oracle_fwd_bwd_ms"] = (time.perf_counter() - t0) * 1e3
+            rec["cpu_cores"] = os.cpu_count()
+        out.append(rec)
+
+    def cpu_gcn_dgg(x, idx, val, n, state, labels, ti):
+        p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+        a = O.add_self_loops_dense(idx, val, n).to_sparse().coalesce()
+        d = O.learnable_k_forward(x, a.indices(), a.values(), n, {k[7:]: v for k, v in p.items() if k.startswith("dggs.0.")},
+                                  "u-v-deg", "x", "k_times_edge_prob")
+        na = O.normalize_adj(d["out"])
+        hh = O.gcn_conv(O.gcn_conv(x, na, p["conv1.W"]), na, p["conv2.W"])
+        F.nll_loss(F.log_softmax(hh, -1)[ti], labels[ti]).backward()
+
+    def cpu_gcnii_dgg(x, idx, val, n, state, labels, ti):
+        p = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+        a = O.add_self_loops_dense(idx, val, n).to_sparse().coalesce()
+        h0 = torch.relu(F.linear(x, p["fcs.0.weight"], p["fcs.0.bias"]))
+        hh, na = h0, None
+        n_layers = sum(1 for k in p if k.startswith("convs.") and k.endswith(".weight"))
+        for i in range(n_layers):
+            if i < 2:
+                d = O.learnable_k_forward(x, a.indices(), a.values(), n,
+                                          {k[len(f"dggs.{i}."):]: v for k, v in p.items() if k.startswith(f"dggs.{i}.")},
+                                          "u-v-deg", "x", "k_times_edge_prob")
+                na = O.normalize_adj(d["out"])
+            hh = torch.relu(O.gcnii_conv(hh, na, h0, p[f"convs.{i}.weight"], 0.5, 0.1, i + 1))
+        logits = F.linear(hh, p["fcs.1.weight"], p["fcs.1.bias"])
+        F.nll_loss(F.log_softmax(logits, 1)[ti], labels[ti]).backward()
+
+    for spec in (dict(name="cora", cls="GCN_DGG", n=2708, f=1433, c=7, density=0.013, mean_deg=3.9, layers=2, args=lk,
+                      cpu=cpu_gcn_dgg),
+                 dict(name="citeseer", cls="GCNII_DGG", n=3327, f=3703, c=6, density=0.009, mean_deg=2.8, layers=64,
+                      args=lk, cpu=cpu_gcnii_dgg)):
+        try:
+            run(**spec)
+        except Exception as e:
+            out.append(dict(model=spec["cls"], shape=spec["name"], error=repr(e)[:300]))
+    # ---- config 3 as literally written: Pubmed-shape GAT_DGG_00 (class DGG + 8 attention heads + 1)
+    try:
+        shape = PUBMED
+        n = shape["n"]
+        torch.manual_seed(0)
+        net = models.GAT_DGG_00(nfeat=shape["f"], nlayers=2, nhidden=shape["h"], nclass=3,
+                                args=argparse.Namespace(extra_edge_dim=0, dgg_adj_input="input_adj")).to(dev)
+        opt = torch.optim.Adam(net.parameters(), lr=0.005, weight_decay=5e-4, fused=True)      # train_small_graphs.py:417
+        labels = torch.randint(0, 3, (n,), device=dev)
+        ti = torch.arange(60, device=dev)
+        sets = []
+        for s_ in pubmed_sets:
+            ii = s_["adj"].indices()
+            nl = ii[:, ii[0] != ii[1]].contiguous()
+            a_ = torch.sparse_coo_tensor(nl, torch.ones(nl.shape[1], device=dev), (n, n)).coalesce()
+            sets.append((s_["x"], a_, nl))
+
+        def gat_step(i):
+            xg, ag, eg = sets[i % len(sets)]
+            net.train()
+            opt.zero_grad(set_to_none=True)
+            logp, _, _ = net(xg, ag, edge_index=eg)
+            F.nll_loss(logp[ti], labels[ti]).backward()
+            opt.step()
+
+        out.append(dict(model="GAT_DGG_00", shape="pubmed", n=n, f=shape["f"], heads="8 + 1",
+                        train_step_ms=_step_timer(gat_step, iters=10),
+                        reference_cpu="not runnable: 9 heads x dense [N, N] fp32 attention = 1.55 GB each, ~40 GB live in "
+                                      "the backward (SURVEY 3.3)"))
+    except Exception as e:
+        out.append(dict(model="GAT_DGG_00", shape="pubmed", error=repr(e)[:300]))
+    return out
+
+
 def kernel_roofline(m, dsets, shape, iters=30):
     """Time each hand-written kernel of the step alone (CUDA events on the launch stream, rotating
     input sets) and report the dominant one against the measured HBM peak."""
@@ -769,10 +937,56 @@ def kernel_roofline(m, dsets, shape, iters=30):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get(name)
+    others = {c[0]: dict(us=c[1] * 1e6, algorithmic_bytes=int(c[2]), gbps=c[2] / c[1] / 1e9,
+                         frac=c[2] / c[1] / 1e9 / peak) for c in cands}
+    # the gathered rows of the edge kernels are L2-resident at this size (y is 5 MB): next to the un-cached
+    # algorithmic bytes above, the fraction against the COMPULSORY bytes (every array touched once)
+    comp_fwd = E * 8 + n * h * 4 + E * 12 + n * 12
+    comp_bwd = E * 8 + n * h * 4 + E * 16 + n * h * 4 + n * 12
+    for key, tt, cb in ((cands[2][0], t_fwd, comp_fwd), (cands[3][0], t_bwd, comp_bwd)):
+        others[key].update(compulsory_bytes=int(cb), frac_compulsory=cb / tt / 1e9 / peak)
+
+    # ---- selection and aggregation kernels the conv layers / DGG_LearnableK_debug / GAT use (north_star: "achieved HBM
+    # GB/s against B200 peak for selection and SpMM"), same graphs, F = h
+    from dgg_b200 import functional as K
+
+    feats = [torch.randn(n, h, device=dev) for _ in range(N_SETS)]
+    gys = torch.randn(n, h, device=dev)
+    vals = [torch.rand(g.nnz, device=dev) + 0.1 for g, _, _ in prepared]
+    ks = torch.rand(n, device=dev) * 8 + 1
+    w64 = torch.randn(h, h, device=dev) / 8
+    heads = 8
+    hd = torch.randn(n, heads * h, device=dev)
+    pq = torch.randn(n, heads, 2, device=dev)
+    gat_out = torch.empty(n, heads * h, device=dev)
+    mz = torch.empty(2, n, heads, device=dev)
+    y_sp, dval, dx = torch.empty(n, h, device=dev), torch.empty(E + 64, device=dev), torch.zeros(n, h, device=dev)
+    rk, fo = torch.empty(E + 64, dtype=torch.int32, device=dev), torch.empty(E + 64, device=dev)
+    dsc, dk = torch.empty(E + 64, device=dev), torch.empty(n, device=dev)
+    s_out = torch.empty(n, h, device=dev)
+
+    def G(i):
+        return prepared[i % N_SETS][0]
+
+    extra = [
+        ("spmm_fwd_kernel (F=64)", lambda i: check(L.dggb_spmm_csr_fwd(p(G(i).rowptr), p(G(i).col), p(vals[i % N_SETS]), n, p(feats[i % N_SETS]), h, None, p(y_sp), stream()), "spmm"),
+         E * (8 + h * 4) + n * h * 4 + n * 4),
+        ("spmm_bwd_kernel (F=64, dA + dX)", lambda i: check(L.dggb_spmm_csr_bwd(p(G(i).rowptr), p(G(i).col), p(vals[i % N_SETS]), n, p(feats[i % N_SETS]), h, None, p(gys), p(dval), p(dx), stream()), "spmm_bwd"),
+         E * (8 + h * 4) + n * h * 4 + E * (h * 4 + 4) + n * 4),
+        ("spmm_gemm_fwd_kernel (SpMM + W 64x64 + ReLU)", lambda i: check(L.dggb_spmm_gemm_fwd(p(G(i).rowptr), p(G(i).col), p(vals[i % N_SETS]), n, p(feats[i % N_SETS]), h, None, None, 1.0, 0.0, p(w64), h, 1.0, 0.0, None, 1, p(y_sp), p(s_out), stream()), "spmm_gemm"),
+         E * (8 + h * 4) + 2 * n * h * 4 + n * 4 + h * h * 4),
+        ("row_firstk_fwd_kernel (in-row rank + soft first-k)", lambda i: check(L.dggb_row_firstk_fwd(p(G(i).rowptr), n, p(vals[i % N_SETS]), p(ks), 0, p(rk), p(fo), None, stream()), "firstk"),
+         E * 12 + n * 8),
+        ("row_firstk_bwd_kernel", lambda i: check(L.dggb_row_firstk_bwd(p(G(i).rowptr), n, p(vals[i % N_SETS]), p(ks), 0, p(rk), p(fo), p(dsc), p(dk), stream()), "firstk_bwd"),
+         E * 20 + n * 12),
+        ("gat_fwd_kernel (8 heads x F=64, dense-background softmax)", lambda i: check(L.dggb_gat_aggregate_fwd(p(G(i).rowptr), p(G(i).col), n, G(i).nnz, heads, h, p(hd), heads * h, p(pq), p(vals[i % N_SETS]), None, p(hd[0]), None, 0.2, float(n), p(gat_out), heads * h, p(mz[0]), p(mz[1]), stream()), "gat"),
+         heads * (E * (h * 4 + 8) + 2 * n * h * 4 + n * 16) + E * 8),
+    ]
+    for nm, fn, nbytes in extra:
+        tt = timed(fn)
+        others[nm] = dict(us=tt * 1e6, algorithmic_bytes=int(nbytes), gbps=nbytes / tt / 1e9, frac=nbytes / tt / 1e9 / peak)
     return dict(bound="hbm", kernel=name, achieved=b / t / 1e9, peak=peak, unit="GB/s", frac=b / t / 1e9 / peak,
-                traffic=traffic, peak_source=peak_src, algorithmic_bytes=int(b), kernel_us=t * 1e6,
-                others={c[0]: dict(us=c[1] * 1e6, algorithmic_bytes=int(c[2]), gbps=c[2] / c[1] / 1e9,
-                                  frac=c[2] / c[1] / 1e9 / peak) for c in cands})
+                traffic=traffic, peak_source=peak_src, algorithmic_bytes=int(b), kernel_us=t * 1e6, others=others)
 
 
 # --------------------------------------------------------------------------- Reddit-shape all-pairs arm

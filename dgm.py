@@ -508,10 +508,12 @@ class DGG_LearnableK_debug(nn.Module):
             d = self.k_net(self.input_degree_project((in_deg - mu) / (var + 1e-5)))
             return F.relu(d * var + mu) + 1.0
         if mode in ("gcn-x-deg", "x"):
-            xe = self.node_encode_for_k(x)
+            enc = self.node_encode_for_k
+            xe = K.encoder_linear(x, enc[0].weight, enc[0].bias, enc[1].negative_slope)   # tensor cores, x padded once
             if mode == "gcn-x-deg":
                 nv = K.sym_normalize(vals, graph)
-                xe = torch.relu(K.spmm(nv, xe, graph) @ self.k_W)
+                fused = K.spmm_gemm(nv, xe, self.k_W, graph, relu=True)                    # relu((A x) k_W), one launch
+                xe = fused if fused is not None else torch.relu(K.spmm(nv, xe, graph) @ self.k_W)
             mu, var = in_deg.mean(), in_deg.std()
             feats = torch.cat([xe, (in_deg - mu) / (var + 1e-5)], dim=-1)
             d = self.k_net(self.k_embed(feats))

@@ -357,7 +357,8 @@ int dggb_allpairs_pair_bwd(const float* z, int32_t n, int32_t d, int32_t row_beg
  * ---------------------------------------------------------------------------------- */
 int dggb_allreduce_oneshot(void* const* bufs_dev, void* const* pads_dev, int32_t rank, int32_t world, int64_t count,
                            float* out, uint32_t* state, const void* multicast_ptr, int32_t pad_slot_base,
-                           int32_t blocks, void* stream);
+                           int32_t blocks, int32_t end_barrier /* 0: the caller alternates two buffers */,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,10 @@
 //   1. tells every peer "my buffer is complete" (st.release.sys into the peer's signal pad) and waits for theirs,
 //   2. reads all `world` buffers and sums them (128-bit volatile loads over NVLink; or ONE multimem.ld_reduce per
 //      16 bytes when the buffers are bound to an NVSwitch multicast object: the switch does the sum),
-//   3. tells every peer "I am done reading" and waits for theirs, so that the next step may overwrite the buffers.
+//   3. tells every peer "I am done reading" and waits for theirs, so that the next step may overwrite the buffers
+//      (skipped with end_barrier = 0: callers that ALTERNATE between two symmetric buffers do not need it -- a peer
+//      can only signal step i + 1 after its step-i kernel, i.e. its reads of buffer i % 2, has completed, and nobody
+//      overwrites buffer i % 2 before its own step i + 1 kernel has passed that barrier).
 // No host involvement, no stream switch, capturable in a CUDA graph; sequence numbers live in device memory because a
 // replayed graph cannot change kernel arguments.
 #include "common.cuh"
@@ -42,7 +45,8 @@ constexpr int kPeerThreads = 256;
 // base + 2 world) = "done reading".  state[0] = last completed sequence number, state[1] = finished-block counter.
 __global__ void __launch_bounds__(kPeerThreads)
     allreduce_oneshot_kernel(float* const* __restrict__ bufs, uint32_t* const* __restrict__ pads, int rank, int world,
-                             long long count, float* __restrict__ out, uint32_t* state, const float* mc, int base) {
+                             long long count, float* __restrict__ out, uint32_t* state, const float* mc, int base,
+                             int end_barrier) {
   pdl_trigger();
   pdl_wait();
   __shared__ uint32_t seq_s;
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kPeerThreads)
   }
   __syncthreads();
   if (last_s) {
-    if (threadIdx.x < world) {
+    if (end_barrier && threadIdx.x < world) {
       st_release_sys(pads[threadIdx.x] + base + world + rank, seq);
       const uint32_t* mine = pads[rank] + base + world + threadIdx.x;
       while (ld_acquire_sys(mine) != seq) {
@@ -128,7 +132,7 @@ using namespace dggb;
 
 extern "C" int dggb_allreduce_oneshot(void* const* bufs_dev, void* const* pads_dev, int32_t rank, int32_t world,
                                       int64_t count, float* out, uint32_t* state, const void* multicast_ptr,
-                                      int32_t pad_slot_base, int32_t blocks, void* stream) {
+                                      int32_t pad_slot_base, int32_t blocks, int32_t end_barrier, void* stream) {
   if (!bufs_dev || !pads_dev || !out || !state || rank < 0 || world < 1 || rank >= world || count < 0 ||
       pad_slot_base < 0 || blocks < 1)
     return DGGB_ERR_BAD_ARG;
@@ -137,6 +141,6 @@ extern "C" int dggb_allreduce_oneshot(void* const* bufs_dev, void* const* pads_d
   launch_pdl(allreduce_oneshot_kernel, dim3(blocks), dim3(kPeerThreads), 0, as_stream(stream),
              reinterpret_cast<float* const*>(bufs_dev), reinterpret_cast<uint32_t* const*>(pads_dev), (int)rank,
              (int)world, (long long)count, out, state, reinterpret_cast<const float*>(multicast_ptr),
-             (int)pad_slot_base);
+             (int)pad_slot_base, (int)end_barrier);
   return launch_status();
 }

@@ -408,13 +408,17 @@ def pad_features(x):
     return xp
 
 
-def encoder_linear(x, w, b, slope):
-    """LeakyReLU_slope(x W^T + b) for the tall node encoders: on tcgen05 also when F % 4 != 0 (features padded once,
-    weight padded per call -- it is [h, F], tiny)."""
+def encoder_linear(x, w, b, slope, dropout=0.0, training=False):
+    """LeakyReLU_slope(dropout(x) W^T + b) for the tall node encoders (slope = 0: ReLU, 1: plain Linear): on tcgen05
+    also when F % 4 != 0 (features padded ONCE -- before the dropout, so the cached padded copy is reused every
+    epoch -- and the [h, F] weight padded per call, it is tiny)."""
     f = x.shape[1]
     if f % 4 != 0 and x.is_cuda and not x.requires_grad:
         x = pad_features(x)
-        w = torch.nn.functional.pad(w, (0, x.shape[1] - f))
+    if x.shape[1] > w.shape[1]:       # x padded here or by the caller (``pad_features``): zero weight columns for it
+        w = torch.nn.functional.pad(w, (0, x.shape[1] - w.shape[1]))
+    if dropout > 0.0 and training:
+        x = torch.nn.functional.dropout(x, dropout, training=True)
     return tall_linear(x, w, b, slope)
 
 

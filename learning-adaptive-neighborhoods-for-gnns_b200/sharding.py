@@ -127,11 +127,13 @@ class PeerAllReduce:
 
     The buffer lives in ``torch.distributed._symmetric_memory`` (peer-mapped; bound to an NVSwitch multicast
     object when the fabric supports it, in which case the switch performs the reduction: multimem.ld_reduce).
+    ``end_barrier=False``: for callers that alternate between TWO instances from step to step (the closing "done
+    reading" round trip is then implied by the next step's opening barrier; see csrc/peer.cu).
     ``PeerAllReduce.available()`` is False where symmetric memory cannot be set up (then use ``dist.all_reduce``)."""
 
     PAD_SLOT_BASE = 1024      # uint32 slots of the signal pad this kernel owns (torch's own barriers use low slots)
 
-    def __init__(self, numel, group=None, use_multicast=True, blocks=None):
+    def __init__(self, numel, group=None, use_multicast=True, blocks=None, end_barrier=True):
         import torch.distributed._symmetric_memory as symm_mem
 
         from ._lib import lib
@@ -157,6 +159,7 @@ class PeerAllReduce:
         # one 16-byte element per thread where possible: every load of the sum is in flight at once
         self._blocks = int(blocks) if blocks else max(1, min(148, (padded // 4 + 255) // 256))
         self._lib = lib()
+        self._end_barrier = 1 if end_barrier else 0
         torch.cuda.synchronize()
         dist.barrier(self.group)            # every rank's pad and state are zeroed before the first call
 
@@ -175,7 +178,7 @@ class PeerAllReduce:
         check(self._lib.dggb_allreduce_oneshot(int(self._hdl.buffer_ptrs_dev), int(self._hdl.signal_pad_ptrs_dev),
                                                self.rank, self.world, self._sym.numel(), self._out.data_ptr(),
                                                self._state.data_ptr(), self._mc or None, self.PAD_SLOT_BASE,
-                                               self._blocks, stream()), "allreduce_oneshot")
+                                               self._blocks, self._end_barrier, stream()), "allreduce_oneshot")
         return self.out
 
 

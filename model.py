@@ -254,8 +254,16 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
 
     def forward(self, x, in_adj, epoch=None, writer=None):
         _layers = []
+        if x.is_cuda:
+            # raw features are [N, 3703] at Citeseer: pad to a multiple of 4 columns ONCE (cached across epochs) so
+            # that fcs[0] and the DGG node encoders run on the TMA-fed tensor-core kernel; the dropout mask is drawn
+            # on the padded tensor and shared by fcs[0] and the DGG layers, like the reference (model.py:705, 720)
+            x = K.pad_features(x)
         x = F.dropout(x, self.dropout, training=self.training)
-        layer_inner = self.act_fn(self.fcs[0](x))
+        if x.is_cuda and self.fcs[0].out_features in (16, 32, 64, 128) and x.shape[0] >= 512:
+            layer_inner = K.encoder_linear(x, self.fcs[0].weight, self.fcs[0].bias, 0.0)       # slope 0: ReLU
+        else:
+            layer_inner = self.act_fn(F.linear(x[:, :self.fcs[0].in_features], self.fcs[0].weight, self.fcs[0].bias))
         _layers.append(layer_inner)
         in_adj = add_self_loops_coo(in_adj)
         unnorm_adj = in_adj
