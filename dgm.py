@@ -54,7 +54,7 @@ class _EdgeRankerBase(nn.Module):
                                     self.node_encoder[1].negative_slope)                       # dgm.py:1778, 1784
         dd = self.degree_decoder[0]
         out_vals, k, R, rank = K.dgg_edge(y, lin.bias, dd.weight, dd.bias, graph, noise, hard_k)
-        self.last_k, self.last_rank = k, rank
+        self.last_k, self.last_rank = k.detach(), rank
         return graph, out_vals, x_enc
 
 
@@ -358,7 +358,9 @@ class DGG_LearnableK_debug(nn.Module):
             graph, vals, out = self._k_only_spill(graph, vals, out, k, n)
         if writer is not None:
             self.get_adj_diff_stats(graph, vals, out, k, writer=writer, epoch=epoch)
-        self.last_k = k
+        # (detached: a module attribute that carries a grad_fn would keep the whole step's autograd graph -- and the
+        # AccumulateGrad nodes of the stream it ran on -- alive into the next step, which breaks CUDA-graph capture)
+        self.last_k = None if k is None else k.detach()
         return self.return_hard_or_soft(graph, out)
 
     # ------------------------------------------------------------------ Gumbel perturbation (dgm.py:1211-1229)

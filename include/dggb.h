@@ -229,6 +229,15 @@ int dggb_gat_aggregate_bwd(const int32_t* rowptr, const int32_t* col, int32_t n,
                            const float* g_out, int32_t ldo, const float* m_in, const float* z_in, float* d_hd,
                            float* d_pq, float* d_adj_val, float* d_htot, void* stream);
 
+/* Edge-parallel variants of the two calls above for short-row graphs (citation graphs: ~5 entries per row): groups of
+ * lanes walk runs of 8 consecutive entries instead of one warp per row -- ~10x fewer instructions at Pubmed shape and
+ * perfectly balanced under power-law degrees.  y MUST BE ZEROED by the caller (rows cut by a run boundary are combined
+ * with vector reductions); erow = row of every entry (dggb_csr_expand_rows).  F % 4 == 0, F <= 512. */
+int dggb_spmm_edge_fwd(const int32_t* rowptr, const int32_t* erow, const int32_t* col, const float* val, int32_t n,
+                       int64_t nnz, const float* x, int32_t f, const float* row_scale, float* y, void* stream);
+int dggb_spmm_edge_bwd(const int32_t* erow, const int32_t* col, const float* val, int64_t nnz, const float* x,
+                       int32_t f, const float* row_scale, const float* dy, float* dval, float* dx, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * SpMM with the conv layer's dense part folded in -- GCNConv relu((A x) W) (model.py:594-598) and the GCNII layer
  * theta * (s W) + (1 - theta) * s, s = (1 - alpha) A h + alpha h0 (model.py:32-44, 65-77) -- one launch per

@@ -25,6 +25,21 @@ with torch.no_grad():
     print("spmm fwd F=64          : %.1f us" % timed(lambda i: K.spmm(vs[i % 3], xs[i % 3], gs[i % 3])))
     print("spmm_gemm fwd 64->64   : %.1f us" % timed(lambda i: K.spmm_gemm(vs[i % 3], xs[i % 3], w, gs[i % 3], relu=True)))
     print("mm N x 64 x 64         : %.1f us" % timed(lambda i: torch.mm(xs[i % 3], w)))
+from dgg_b200._lib import lib, check, p as P, stream
+L = lib()
+ye = torch.zeros(n, 64, device="cuda"); dv = torch.empty(E, device="cuda"); dxe = torch.zeros(n, 64, device="cuda")
+def efwd(i):
+    g = gs[i % 3]; ye.zero_()
+    check(L.dggb_spmm_edge_fwd(P(g.rowptr), P(g.erow), P(g.col), P(vs[i % 3]), n, g.nnz, P(xs[i % 3]), 64, None, P(ye), stream()), "e")
+def ebwd(i):
+    g = gs[i % 3]
+    check(L.dggb_spmm_edge_bwd(P(g.erow), P(g.col), P(vs[i % 3]), g.nnz, P(xs[i % 3]), 64, None, P(gy), P(dv), P(dxe), stream()), "e")
+def rbwd(i):
+    g = gs[i % 3]
+    check(L.dggb_spmm_csr_bwd(P(g.rowptr), P(g.col), P(vs[i % 3]), n, P(xs[i % 3]), 64, None, P(gy), P(dv), P(dxe), stream()), "e")
+print("spmm EDGE fwd (+zero)  : %.1f us" % timed(efwd))
+print("spmm EDGE bwd          : %.1f us" % timed(ebwd))
+print("spmm row  bwd          : %.1f us" % timed(rbwd))
 def fb(fused):
     def f(i):
         v = vs[i % 3].clone().requires_grad_(True); x = xs[i % 3].clone().requires_grad_(True); ww = w.clone().requires_grad_(True)
