@@ -252,7 +252,7 @@ class RowShardedSAGE_DGG(torch.nn.Module):
             if fo % 4:                                                   # 128-bit gathers: pad 41 classes to 44
                 p = torch.nn.functional.pad(p, (0, 4 - fo % 4))
             p_all = all_gather_rows(p, n, group) if sharded else p
-            agg = K.spmm(vals, p_all, g, scale)[:, :fo]
+            agg = K.spmm(vals, p_all, g)[:, :fo] * scale.unsqueeze(-1)     # (scale carries gradient: not the kernel's constant row_scale)
             h_new = agg + lin_rel.bias + lin_root(h)
             h = h_new if last else torch.nn.functional.dropout(torch.relu(h_new), 0.5, self.training)
         return torch.log_softmax(h, dim=-1), idx, ahat

@@ -68,9 +68,9 @@ def test_row_sharded_sage_dgg_matches_dense_restatement():
     F.nll_loss(got, labels.cuda()).backward()
     for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         if name == "t":
-            assert abs(float(p.grad) - float(q.grad)) <= 1e-4 * t_scale, (float(p.grad), float(q.grad), t_scale)
+            assert abs(float(p.grad) - float(q.grad)) <= 2e-4 * t_scale, (float(p.grad), float(q.grad), t_scale)
         else:
-            assert_grad_close(p.grad.cpu(), q.grad, rtol=5e-3, atol_rel=1e-3, what=name)
+            assert_grad_close(p.grad.cpu(), q.grad, rtol=2e-3, atol_rel=2e-4, what=name)
 
 
 def test_row_blocks_reproduce_the_unsharded_adjacency():
