@@ -721,8 +721,10 @@ def config_epochs(dev, pubmed_sets):
         adj = torch.sparse_coo_tensor(idx.to(dev), val.to(dev), (n, n)).coalesce()
         dgg_b200.CSRGraph.from_coo(adj)
         xd, yd, ti = x.to(dev), labels.to(dev), train_idx.to(dev)
-        groups = ([dict(params=net.params1, weight_decay=0.01), dict(params=net.params2, weight_decay=5e-4)]
-                  if "II" in cls else [dict(params=net.params1, weight_decay=5e-4), dict(params=net.params2, weight_decay=0)])
+        def groups():      # fresh dicts per optimiser (Adam writes its defaults, incl. capturable, into them)
+            return ([dict(params=net.params1, weight_decay=0.01), dict(params=net.params2, weight_decay=5e-4)]
+                    if "II" in cls else
+                    [dict(params=net.params1, weight_decay=5e-4), dict(params=net.params2, weight_decay=0)])
         rec = dict(model=cls, shape=name, n=n, f=f, layers=layers, edges=int(idx.shape[1]))
 
         def make_step(opt):
@@ -737,9 +739,9 @@ def config_epochs(dev, pubmed_sets):
                 return loss
             return step
 
-        rec["train_step_ms"] = _step_timer(make_step(torch.optim.Adam(groups, lr=lr, fused=True)))
+        rec["train_step_ms"] = _step_timer(make_step(torch.optim.Adam(groups(), lr=lr, fused=True)))
         try:
-            gs = dgg_b200.GraphedStep(make_step(torch.optim.Adam(groups, lr=lr, capturable=True, fused=True)))
+            gs = dgg_b200.GraphedStep(make_step(torch.optim.Adam(groups(), lr=lr, capturable=True, fused=True)))
             rec["train_step_graph_ms"] = _step_timer(lambda i: gs(), iters=20)
         except Exception as e:
             rec["train_step_graph_ms"], rec["train_step_graph_error"] = None, repr(e)[:200]
