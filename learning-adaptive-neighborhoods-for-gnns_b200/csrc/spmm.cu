@@ -328,21 +328,23 @@ struct SpmmGemmArgs {
   int relu;
 };
 
-constexpr int kRB = 4;   // rows per warp iteration: the W tile is read from shared memory once per kRB rows
+// RB = rows per warp iteration: the W tile is read from shared memory once per RB rows (RB = 4: large graphs, the
+// dense part dominates; RB = 1: small graphs -- every row gets its own warp, the dependent-load latency of the
+// aggregation is what a 3 k-node layer costs, measured 25.7 -> see DESIGN.md)
 
-// dense part for kRB rows at once: out[r][c] = sum_f S[r][f] * M[f][c];  lane owns columns c = lane + 32 q (q < 4).
-// S rows are read as broadcast float4, M as conflict-free scalars: 3 LDS per 8 (kRB * 2) FMAs at 64 columns.
-template <int Q>
+// dense part for RB rows at once: out[r][c] = sum_f S[r][f] * M[f][c];  lane owns columns c = lane + 32 q (q < 4).
+// S rows are read as broadcast float4, M as conflict-free scalars: 3 LDS per 8 (RB * 2) FMAs at 64 columns.
+template <int Q, int RB>
 __device__ __forceinline__ void dense_rows(const float* __restrict__ S, int ld_s, const float* __restrict__ M, int k_dim,
-                                           int n_cols, int lane, float (&acc)[kRB][Q]) {
+                                           int n_cols, int lane, float (&acc)[RB][Q]) {
 #pragma unroll
-  for (int r = 0; r < kRB; ++r)
+  for (int r = 0; r < RB; ++r)
 #pragma unroll
     for (int q = 0; q < Q; ++q) acc[r][q] = 0.f;
   for (int f = 0; f < k_dim; f += 4) {
-    float4 sv[kRB];
+    float4 sv[RB];
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) sv[r] = *reinterpret_cast<const float4*>(S + r * ld_s + f);
+    for (int r = 0; r < RB; ++r) sv[r] = *reinterpret_cast<const float4*>(S + r * ld_s + f);
 #pragma unroll
     for (int ff = 0; ff < 4; ++ff) {
       float mv[Q];
@@ -352,7 +354,7 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ S, int ld_s
         mv[q] = (c < n_cols) ? M[(f + ff) * n_cols + c] : 0.f;
       }
 #pragma unroll
-      for (int r = 0; r < kRB; ++r) {
+      for (int r = 0; r < RB; ++r) {
         const float sf = ff == 0 ? sv[r].x : (ff == 1 ? sv[r].y : (ff == 2 ? sv[r].z : sv[r].w));
 #pragma unroll
         for (int q = 0; q < Q; ++q) acc[r][q] = fmaf(sf, mv[q], acc[r][q]);
@@ -362,11 +364,11 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ S, int ld_s
 }
 
 // same with a reduction length that need not be a multiple of 4 (the S rows are zero-padded to ld_s)
-template <int Q>
+template <int Q, int RB>
 __device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld_s, const float* __restrict__ M,
-                                             int k_dim, int n_cols, int lane, float (&acc)[kRB][Q]) {
+                                             int k_dim, int n_cols, int lane, float (&acc)[RB][Q]) {
 #pragma unroll
-  for (int r = 0; r < kRB; ++r)
+  for (int r = 0; r < RB; ++r)
 #pragma unroll
     for (int q = 0; q < Q; ++q) acc[r][q] = 0.f;
   for (int f = 0; f < k_dim; ++f) {
@@ -377,7 +379,7 @@ __device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld
       mv[q] = (c < n_cols) ? M[f * n_cols + c] : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       const float sf = S[r * ld_s + f];
 #pragma unroll
       for (int q = 0; q < Q; ++q) acc[r][q] = fmaf(sf, mv[q], acc[r][q]);
@@ -385,21 +387,21 @@ __device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld
   }
 }
 
-template <int T, int Q>
+template <int T, int Q, int RB>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_fwd_kernel(SpmmGemmArgs A, float* __restrict__ y, float* __restrict__ s_out) {
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                                                     // [fin][fout]
-  float* srows = sm + A.fin * A.fout + (threadIdx.x >> 5) * kRB * A.fin;   // this warp's kRB rows of s
+  float* srows = sm + A.fin * A.fout + (threadIdx.x >> 5) * RB * A.fin;   // this warp's RB rows of s
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) Ws[c] = __ldg(A.w + c);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * kRB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * kRB) {
+  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * RB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * RB) {
     __syncwarp();
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       const int i = i0 + r;
       float* srow = srows + r * A.fin;
       if (i >= A.n) {                                                 // ragged last block: zero rows
@@ -453,10 +455,10 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       }
     }
     __syncwarp();
-    float d[kRB][Q];
-    dense_rows<Q>(srows, A.fin, Ws, A.fin, A.fout, lane, d);
+    float d[RB][Q];
+    dense_rows<Q, RB>(srows, A.fin, Ws, A.fin, A.fout, lane, d);
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       const int i = i0 + r;
       if (i >= A.n) break;
 #pragma unroll
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   }
 }
 
-template <int T, int Q>
+template <int T, int Q, int RB>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_bwd_kernel(SpmmGemmArgs A, const float* __restrict__ gy, float* __restrict__ dval,
                          float* __restrict__ dx, float* __restrict__ ds_out) {
@@ -482,8 +484,8 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   extern __shared__ __align__(16) float sm[];
   float* Wt = sm;                                           // [fout][fin] (transposed copy)
   const int fo4 = (A.fout + 3) & ~3;                        // 16-byte aligned rows for the float4 reads below
-  float* grows = sm + ((A.fin * A.fout + 3) & ~3) + (threadIdx.x >> 5) * kRB * (A.fin + fo4);   // kRB rows of g ...
-  float* dsrows = grows + kRB * fo4;                        // ... and of ds
+  float* grows = sm + ((A.fin * A.fout + 3) & ~3) + (threadIdx.x >> 5) * RB * (A.fin + fo4);   // RB rows of g ...
+  float* dsrows = grows + RB * fo4;                        // ... and of ds
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
     const int f = c / A.fout, o = c % A.fout;
@@ -492,19 +494,19 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * kRB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * kRB) {
+  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * RB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * RB) {
     __syncwarp();
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       const int i = i0 + r;
       for (int c = lane; c < fo4; c += kWarp)
         grows[r * fo4 + c] = (i < A.n && c < A.fout) ? __ldg(gy + (size_t)i * A.fout + c) : 0.f;
     }
     __syncwarp();
     // ds[r][f] = theta * sum_c g[r][c] Wt[c][f] + beta * g[r][f]
-    float d[kRB][Q];
-    dense_rows_k<Q>(grows, fo4, Wt, A.fout, A.fin, lane, d);
+    float d[RB][Q];
+    dense_rows_k<Q, RB>(grows, fo4, Wt, A.fout, A.fin, lane, d);
 #pragma unroll
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       const int i = i0 + r;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       }
     }
     __syncwarp();
-    for (int r = 0; r < kRB; ++r) {
+    for (int r = 0; r < RB; ++r) {
       const int i = i0 + r;
       if (i >= A.n) break;
       const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
@@ -568,6 +570,9 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     }
   }
 }
+
+// graphs below this many rows: one row per warp (every row of the layer in flight at once)
+constexpr int kSmallGraphRows = 8 * kNumSMs * kSpmmWarps;
 
 static int spmm_gemm_lanes(int fin, int* t_out) {
   const int chunks = fin / 4;
@@ -653,18 +658,21 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
   if (n == 0) return DGGB_OK;
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
-  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * kRB * fin) * sizeof(float);
+  const int rb = n >= kSmallGraphRows ? 4 : 1;
+  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * rb * fin) * sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = rows_grid((n + kRB - 1) / kRB, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    const int grid = rows_grid((n + rb - 1) / rb, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, y, s_out);
     return launch_status();
   };
   const int Q = fout <= 32 ? 1 : (fout <= 64 ? 2 : 4);
-#define DGGB_SG_F(T_) (Q == 1 ? go(spmm_gemm_fwd_kernel<T_, 1>) : (Q == 2 ? go(spmm_gemm_fwd_kernel<T_, 2>) : go(spmm_gemm_fwd_kernel<T_, 4>)))
+#define DGGB_SG_Q(T_, R_) (Q == 1 ? go(spmm_gemm_fwd_kernel<T_, 1, R_>) : (Q == 2 ? go(spmm_gemm_fwd_kernel<T_, 2, R_>) : go(spmm_gemm_fwd_kernel<T_, 4, R_>)))
+#define DGGB_SG_F(T_) (rb == 4 ? DGGB_SG_Q(T_, 4) : DGGB_SG_Q(T_, 1))
   return T == 1 ? DGGB_SG_F(1) : (T == 2 ? DGGB_SG_F(2) : DGGB_SG_F(4));
 #undef DGGB_SG_F
+#undef DGGB_SG_Q
 }
 
 extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
@@ -678,19 +686,22 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
   if (n == 0) return DGGB_OK;
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
+  const int rb = n >= kSmallGraphRows ? 4 : 1;
   const size_t smem =
-      ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * kRB * (fin + ((fout + 3) & ~3))) * sizeof(float);
+      ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * rb * (fin + ((fout + 3) & ~3))) * sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = rows_grid((n + kRB - 1) / kRB, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    const int grid = rows_grid((n + rb - 1) / rb, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out);
     return launch_status();
   };
   const int Q = fin <= 32 ? 1 : (fin <= 64 ? 2 : 4);
-#define DGGB_SG_B(T_) (Q == 1 ? go(spmm_gemm_bwd_kernel<T_, 1>) : (Q == 2 ? go(spmm_gemm_bwd_kernel<T_, 2>) : go(spmm_gemm_bwd_kernel<T_, 4>)))
+#define DGGB_SG_Q(T_, R_) (Q == 1 ? go(spmm_gemm_bwd_kernel<T_, 1, R_>) : (Q == 2 ? go(spmm_gemm_bwd_kernel<T_, 2, R_>) : go(spmm_gemm_bwd_kernel<T_, 4, R_>)))
+#define DGGB_SG_B(T_) (rb == 4 ? DGGB_SG_Q(T_, 4) : DGGB_SG_Q(T_, 1))
   return T == 1 ? DGGB_SG_B(1) : (T == 2 ? DGGB_SG_B(2) : DGGB_SG_B(4));
 #undef DGGB_SG_B
+#undef DGGB_SG_Q
 }
 
 // Edge-parallel variants (F % 4 == 0, F <= 512): y must be zeroed by the caller (rows cut by a run boundary are
