@@ -26,8 +26,11 @@ using tc::tf32_rna;
 __global__ void split_w_kernel(const float* __restrict__ w, int count, int h, int f, int transposed,
                                float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w2, int count2,
                                float* __restrict__ hi2, float* __restrict__ lo2, float* zero_ws, long long zero_count) {
-  pdl_trigger();
+  // wait FIRST, then let the dependent grid go: when the GEMM kernel's CTAs start, everything before this launch has
+  // completed, so the GEMM may stream its x tiles (never written by this kernel) without waiting for the split --
+  // only its W loads wait.  The x ring fills while W is being split.
   pdl_wait();
+  pdl_trigger();
   zero_fill(zero_ws, zero_count);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count + count2; i += gridDim.x * blockDim.x) {
     if (i < count) {
@@ -150,9 +153,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tc::mbar_init(a2_full, 4);
     tc::mbar_init(acc2_full, 1);
     tc::fence_barrier_init();
-    pdl_wait();   // x / W may come from the preceding kernel; everything above overlapped its tail
-    // the first round of both rings needs no "empty" wait: put it in flight before the TMEM allocation / CTA sync
+    // The preceding grid is split_w_kernel of the same call, which triggers this launch only AFTER its own
+    // dependency wait: x (and everything else older than the split) is complete and visible, only the split W is not.
+    // The first round of both rings needs no "empty" wait: x goes in flight right away, W after the wait.
     for (int kb = 0; kb < XS && kb < num_kb; ++kb) load_x(kb);
+    pdl_wait();
     for (int kb = 0; kb < WS && kb < num_kb; ++kb) load_w(kb);
   }
   if (warp == 1) {

@@ -143,13 +143,18 @@ class _Spmm(torch.autograd.Function):
         _require_cuda(vals, x)
         vals, x = _f32c(vals), _f32c(x)
         n, f = graph.n, x.shape[1]
-        # short rows (citation graphs, learned top-K adjacencies): the BACKWARD runs entry-parallel (measured at
-        # Pubmed shape, F = 64: 18.1 vs 32.1 us); the forward stays warp-per-row (20.9 us entry-parallel incl. the
-        # zero fill it needs vs 21.3 us: no gain)
+        # short rows (citation graphs, learned top-K adjacencies): entry-parallel kernels in both directions
+        # (Pubmed shape, F = 64, inside a CUDA graph: forward 9.7 us incl. the zero fill vs 15.2 warp-per-row,
+        # backward 7.7 vs 21.7 us)
         ctx.edge = (not _NO_EDGE_SPMM) and f % 4 == 0 and f <= 512 and graph.nnz > 0 and graph.nnz <= 64 * n
-        y = torch.empty(n, f, dtype=torch.float32, device=x.device)
-        check(lib().dggb_spmm_csr_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(n), p(x), i32(f), p(row_scale),
-                                      p(y), stream()), "spmm_csr_fwd")
+        if ctx.edge:
+            y = torch.zeros(n, f, dtype=torch.float32, device=x.device)
+            check(lib().dggb_spmm_edge_fwd(p(graph.rowptr), p(graph.erow), p(graph.col), p(vals), i32(n),
+                                           i64(graph.nnz), p(x), i32(f), p(row_scale), p(y), stream()), "spmm_edge_fwd")
+        else:
+            y = torch.empty(n, f, dtype=torch.float32, device=x.device)
+            check(lib().dggb_spmm_csr_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(n), p(x), i32(f), p(row_scale),
+                                          p(y), stream()), "spmm_csr_fwd")
         ctx.graph = graph
         ctx.save_for_backward(vals, x, row_scale)
         return y
