@@ -133,7 +133,8 @@ def test_gat_general_edge_list(golden):
     torch.testing.assert_close(got.cpu(), want, **FWD)
 
 
-@pytest.mark.parametrize("heads,f_out,background", [(8, 16, True), (1, 7, True), (4, 8, False), (2, 64, True)])
+@pytest.mark.parametrize("heads,f_out,background", [(8, 16, True), (1, 7, True), (4, 8, False), (2, 64, True), (8, 64, True),
+                                                    (3, 32, False), (8, 128, True)])
 def test_gat_heads_fused_fwd_bwd_vs_dense_formula(heads, f_out, background):
     """The fused all-heads kernel (edge list == adjacency support) against the dense masked-by-multiplication
     formula of model.py:556-577 (oracle.gat_conv_dgg) / the plain masked softmax of model.py:510-531, forward and
