@@ -399,90 +399,115 @@ __device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld
   }
 }
 
+// Block b owns the kSpmmWarps * RB consecutive rows [r0, r1) and therefore the contiguous entry range
+// [rowptr[r0], rowptr[r1]).  Phase 1 (aggregation) is ENTRY-parallel inside the block: groups of L lanes walk runs of
+// consecutive entries, keep the running row sum in registers and add it to the row's accumulator in shared memory
+// when the row changes (shared-memory atomics: rows are only ever touched by their own block) -- balanced under any
+// degree distribution inside the block, no per-row shuffle reduction.  Phase 2 (dense part) is row-parallel: each warp
+// takes RB rows out of shared memory.  (r02 measurements of the first version, warp-per-row aggregation: 32 us at
+// Pubmed shape against 9.7 + 3.7 us for the entry-parallel SpMM + a library GEMM.)
+__device__ __forceinline__ int row_of_entry(const int32_t* __restrict__ rowptr, int r0, int r1, int e) {
+  int lo = r0, hi = r1 - 1;                         // last row r in [r0, r1) with rowptr[r] <= e
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(rowptr + mid) <= e) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 template <int T, int Q, int RB>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_fwd_kernel(SpmmGemmArgs A, float* __restrict__ y, float* __restrict__ s_out) {
+  constexpr int R = kSpmmWarps * RB;
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
-  float* Ws = sm;                                                     // [fin][fout]
-  float* srows = sm + A.fin * A.fout + (threadIdx.x >> 5) * RB * A.fin;   // this warp's RB rows of s
+  float* Ws = sm;                                   // [fin][fout]
+  float* S = sm + A.fin * A.fout;                   // [R][fin] row accumulators, then s
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
+  const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R);
+  for (int c = threadIdx.x; c < R * A.fin; c += blockDim.x) S[c] = 0.f;
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) Ws[c] = __ldg(A.w + c);
+  const int eb0 = __ldg(A.rowptr + r0), eb1 = __ldg(A.rowptr + r1);
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * RB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * RB) {
-    __syncwarp();
-    for (int r = 0; r < RB; ++r) {
-      const int i = i0 + r;
-      float* srow = srows + r * A.fin;
-      if (i >= A.n) {                                                 // ragged last block: zero rows
-        for (int c = lane; c < A.fin; c += kWarp) srow[c] = 0.f;
-        continue;
-      }
-      const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
-      const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
+  // ---- phase 1: entry-parallel aggregation into S ----
+  {
+    const int nE = eb1 - eb0, groups = kSpmmWarps * G;
+    const int per = (nE + groups - 1) / groups;
+    const int e_beg = eb0 + (warp * G + grp) * per, e_end = min(eb1, e_beg + per);
+    if (e_beg < e_end) {
+      int cur = row_of_entry(A.rowptr, r0, r1, e_beg);
+      int next_start = __ldg(A.rowptr + cur + 1);
       Vec<4> acc[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) acc[t].zero();
-      for (int w0 = beg; w0 < end; w0 += kWarp) {
-        const int e_l = w0 + lane;
-        const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
-        const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
-        const int cnt = min(kWarp, end - w0);
-#pragma unroll 4
-        for (int j0 = 0; j0 < cnt; j0 += G) {
-          const int j = j0 + grp;
-          const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
-          float a = __shfl_sync(0xffffffffu, a_l, j & 31);
-          if (j >= cnt) a = 0.f;
-          const float* xr = A.x + (size_t)v * A.fin;
+      auto flush = [&]() {
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const int c = 4 * (lg + L * t);
-            if (c < A.fin) {
-              Vec<4> xv;
-              xv.load(xr + c);
-              acc[t].fma(a, xv);
-            }
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < A.fin) {
+            float* d = S + (cur - r0) * A.fin + c;
+            atomicAdd(d + 0, acc[t].v.x); atomicAdd(d + 1, acc[t].v.y);
+            atomicAdd(d + 2, acc[t].v.z); atomicAdd(d + 3, acc[t].v.w);
+          }
+          acc[t].zero();
+        }
+      };
+#pragma unroll 2
+      for (int e = e_beg; e < e_end; ++e) {
+        while (e >= next_start) {                   // group-uniform: the run crossed into the next (non-empty) row
+          flush();
+          ++cur;
+          next_start = __ldg(A.rowptr + cur + 1);
+        }
+        const int v = __ldg(A.col + e);
+        const float a = __ldg(A.val + e);
+        const float* xr = A.x + (size_t)v * A.fin;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < A.fin) {
+            Vec<4> xv;
+            xv.load(xr + c);
+            acc[t].fma(a, xv);
           }
         }
       }
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        for (int o = L; o < kWarp; o <<= 1) acc[t].xor_add(o);
-        const int c = 4 * (lg + L * t);
-        if (grp == 0 && c < A.fin) {
-          float4 sv = acc[t].v;
-          const float k1 = A.c1 * rs;
-          sv.x *= k1; sv.y *= k1; sv.z *= k1; sv.w *= k1;
-          if (A.h0) {
-            const float4 h = ldg4(A.h0 + (size_t)i * A.fin + c);
-            sv.x = fmaf(A.c2, h.x, sv.x); sv.y = fmaf(A.c2, h.y, sv.y);
-            sv.z = fmaf(A.c2, h.z, sv.z); sv.w = fmaf(A.c2, h.w, sv.w);
-          }
-          *reinterpret_cast<float4*>(srow + c) = sv;
-          if (s_out) st4(s_out + (size_t)i * A.fin + c, sv);
-        }
-      }
+      flush();
     }
-    __syncwarp();
-    float d[RB][Q];
-    dense_rows<Q, RB>(srows, A.fin, Ws, A.fin, A.fout, lane, d);
+  }
+  __syncthreads();
+  // ---- phase 2: s = c1 rs agg + c2 h0 (in place), y = act(theta s W + beta s + resid), RB rows per warp ----
+  float* srows = S + warp * RB * A.fin;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int i = i0 + r;
-      if (i >= A.n) break;
+  for (int r = 0; r < RB; ++r) {
+    const int i = r0 + warp * RB + r;
+    if (i >= A.n) break;
+    const float k1 = A.c1 * (A.row_scale ? __ldg(A.row_scale + i) : 1.f);
+    for (int c = lane; c < A.fin; c += kWarp) {
+      float v = k1 * srows[r * A.fin + c];
+      if (A.h0) v = fmaf(A.c2, __ldg(A.h0 + (size_t)i * A.fin + c), v);
+      srows[r * A.fin + c] = v;
+      if (s_out) s_out[(size_t)i * A.fin + c] = v;
+    }
+  }
+  __syncwarp();
+  float d[RB][Q];
+  dense_rows<Q, RB>(srows, A.fin, Ws, A.fin, A.fout, lane, d);
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const int c = lane + 32 * q;
-        if (c < A.fout) {
-          float v = A.theta * d[r][q];
-          if (A.beta != 0.f) v = fmaf(A.beta, srows[r * A.fin + c], v);      // fout == fin (checked on the host)
-          if (A.resid) v += __ldg(A.resid + (size_t)i * A.fout + c);
-          if (A.relu) v = fmaxf(v, 0.f);
-          y[(size_t)i * A.fout + c] = v;
-        }
+  for (int r = 0; r < RB; ++r) {
+    const int i = r0 + warp * RB + r;
+    if (i >= A.n) break;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int c = lane + 32 * q;
+      if (c < A.fout) {
+        float v = A.theta * d[r][q];
+        if (A.beta != 0.f) v = fmaf(A.beta, srows[r * A.fin + c], v);      // fout == fin (checked on the host)
+        if (A.resid) v += __ldg(A.resid + (size_t)i * A.fout + c);
+        if (A.relu) v = fmaxf(v, 0.f);
+        y[(size_t)i * A.fout + c] = v;
       }
     }
   }
@@ -492,92 +517,93 @@ template <int T, int Q, int RB>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_bwd_kernel(SpmmGemmArgs A, const float* __restrict__ gy, float* __restrict__ dval,
                          float* __restrict__ dx, float* __restrict__ ds_out) {
+  constexpr int R = kSpmmWarps * RB;
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* Wt = sm;                                           // [fout][fin] (transposed copy)
-  const int fo4 = (A.fout + 3) & ~3;                        // 16-byte aligned rows for the float4 reads below
-  float* grows = sm + ((A.fin * A.fout + 3) & ~3) + (threadIdx.x >> 5) * RB * (A.fin + fo4);   // RB rows of g ...
-  float* dsrows = grows + RB * fo4;                        // ... and of ds
+  const int fo4 = (A.fout + 3) & ~3;                        // 16-byte aligned rows
+  float* Gs = sm + ((A.fin * A.fout + 3) & ~3);             // [R][fo4] rows of gy
+  float* DS = Gs + R * fo4;                                 // [R][fin]  ds rows (scaled by c1 rs for phase B)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
+  const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R);
   pdl_wait();
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
     const int f = c / A.fout, o = c % A.fout;
     Wt[o * A.fin + f] = __ldg(A.w + c);
   }
+  for (int c = threadIdx.x; c < R * fo4; c += blockDim.x) {
+    const int r = c / fo4, o = c % fo4, i = r0 + r;
+    Gs[c] = (i < A.n && o < A.fout) ? __ldg(gy + (size_t)i * A.fout + o) : 0.f;
+  }
+  const int eb0 = __ldg(A.rowptr + r0), eb1 = __ldg(A.rowptr + r1);
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  for (int i0 = (blockIdx.x * kSpmmWarps + (threadIdx.x >> 5)) * RB; i0 < A.n; i0 += gridDim.x * kSpmmWarps * RB) {
-    __syncwarp();
-    for (int r = 0; r < RB; ++r) {
-      const int i = i0 + r;
-      for (int c = lane; c < fo4; c += kWarp)
-        grows[r * fo4 + c] = (i < A.n && c < A.fout) ? __ldg(gy + (size_t)i * A.fout + c) : 0.f;
-    }
-    __syncwarp();
-    // ds[r][f] = theta * sum_c g[r][c] Wt[c][f] + beta * g[r][f]
+  // ---- phase A: ds[r][f] = theta * sum_c g[r][c] Wt[c][f] + beta * g[r][f], RB rows per warp ----
+  {
+    float* grows = Gs + warp * RB * fo4;
     float d[RB][Q];
     dense_rows_k<Q, RB>(grows, fo4, Wt, A.fout, A.fin, lane, d);
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const int i = i0 + r;
+      const int i = r0 + warp * RB + r;
+      const float k1 = (i < A.n) ? A.c1 * (A.row_scale ? __ldg(A.row_scale + i) : 1.f) : 0.f;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const int f = lane + 32 * q;
         if (f < A.fin) {
           float v = A.theta * d[r][q];
           if (A.beta != 0.f) v = fmaf(A.beta, grows[r * fo4 + f], v);
-          dsrows[r * A.fin + f] = v;
           if (ds_out && i < A.n) ds_out[(size_t)i * A.fin + f] = v;
+          DS[(warp * RB + r) * A.fin + f] = k1 * v;
         }
       }
     }
-    __syncwarp();
-    for (int r = 0; r < RB; ++r) {
-      const int i = i0 + r;
-      if (i >= A.n) break;
-      const int beg = __ldg(A.rowptr + i), end = __ldg(A.rowptr + i + 1);
-      const float rs = A.row_scale ? __ldg(A.row_scale + i) : 1.f;
-      Vec<4> g[T];
-      const float k1 = A.c1 * rs;
+  }
+  __syncthreads();
+  // ---- phase B: entry-parallel  dval_e = <c1 rs ds_u, x_v>,  dx_v += a_e c1 rs ds_u ----
+  const int nE = eb1 - eb0, groups = kSpmmWarps * G;
+  const int per = (nE + groups - 1) / groups;
+  const int e_beg = eb0 + (warp * G + grp) * per, e_end = min(eb1, e_beg + per);
+  if (e_beg < e_end) {
+    int cur = row_of_entry(A.rowptr, r0, r1, e_beg);
+    int next_start = __ldg(A.rowptr + cur + 1);
+    Vec<4> g[T];
+    auto load_row = [&]() {
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int c = 4 * (lg + L * t);
+        if (c < A.fin) g[t].v = *reinterpret_cast<const float4*>(DS + (cur - r0) * A.fin + c);
+        else g[t].zero();
+      }
+    };
+    load_row();
+#pragma unroll 2
+    for (int e = e_beg; e < e_end; ++e) {
+      if (e >= next_start) {
+        while (e >= next_start) {
+          ++cur;
+          next_start = __ldg(A.rowptr + cur + 1);
+        }
+        load_row();
+      }
+      const int v = __ldg(A.col + e);
+      const float a = __ldg(A.val + e);
+      float dot = 0.f;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         const int c = 4 * (lg + L * t);
         if (c < A.fin) {
-          g[t].v = *reinterpret_cast<const float4*>(dsrows + r * A.fin + c);
-          g[t].scale(k1);
-        } else {
-          g[t].zero();
+          if (dval) {
+            Vec<4> xv;
+            xv.load(A.x + (size_t)v * A.fin + c);
+            dot += g[t].dot(xv);
+          }
+          if (dx) g[t].red(dx + (size_t)v * A.fin + c, a);
         }
       }
-      for (int w0 = beg; w0 < end; w0 += kWarp) {
-        const int e_l = w0 + lane;
-        const int c_l = (e_l < end) ? __ldg(A.col + e_l) : 0;
-        const float a_l = (e_l < end) ? __ldg(A.val + e_l) : 0.f;
-        const int cnt = min(kWarp, end - w0);
-#pragma unroll 2
-        for (int j0 = 0; j0 < cnt; j0 += G) {
-          const int j = j0 + grp;
-          const bool valid = j < cnt;
-          const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
-          const float a = __shfl_sync(0xffffffffu, a_l, j & 31);
-          float dot = 0.f;
-#pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const int c = 4 * (lg + L * t);
-            if (c < A.fin && valid) {
-              if (dval) {
-                Vec<4> xv;
-                xv.load(A.x + (size_t)v * A.fin + c);
-                dot += g[t].dot(xv);
-              }
-              if (dx) g[t].red(dx + (size_t)v * A.fin + c, a);
-            }
-          }
-          if (dval) {
-            dot = group_sum(dot, L);
-            if (lg == 0 && valid) dval[w0 + j] = dot;
-          }
-        }
+      if (dval) {
+        dot = group_sum(dot, L);
+        if (lg == 0) dval[e] = dot;
       }
     }
   }
@@ -675,7 +701,7 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = rows_grid((n + rb - 1) / rb, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    const int grid = (n + kSpmmWarps * rb - 1) / (kSpmmWarps * rb);        // one block per kSpmmWarps * rb rows
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, y, s_out);
     return launch_status();
   };
@@ -704,7 +730,7 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = rows_grid((n + rb - 1) / rb, kSpmmWarps, resident_blocks(kern, kSpmmWarps * kWarp, smem));
+    const int grid = (n + kSpmmWarps * rb - 1) / (kSpmmWarps * rb);
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out);
     return launch_status();
   };
