@@ -296,13 +296,15 @@ def run_ours(args, rank, local_rank, world):
     flat_grads = None
 
     def eager_step(s, static_grads=False):
-        if static_grads:
-            flat_grads.zero_()      # graphs share ONE flat static .grad buffer, accumulated in place
+        if static_grads and world > 1:
+            flat_grads.zero_()      # ranks sum ONE flat static .grad buffer, accumulated in place
         else:
-            for p in params:
-                p.grad = None
+            for p in params:        # zero_grad(set_to_none=True): the backward's own buffers become the .grad tensors
+                p.grad = None       # (no fill, no accumulation kernels); a captured graph returns them as outputs
         out, x_enc = m(s["x"], s["adj"])
         torch.autograd.backward([out._dgg_vals, x_enc], [s["g_vals"], s["g_xenc"]])
+        if static_grads and world == 1:
+            return out._dgg_vals, [p.grad for p in params]
         return out._dgg_vals
 
     # one captured CUDA graph per resident input set (a training loop that holds its mini-batches on the
@@ -321,9 +323,9 @@ def run_ours(args, rank, local_rank, world):
             except Exception as e:   # symmetric memory not available on this fabric: captured NCCL all-reduce
                 peer_ar = None
                 grad_sync = f"NCCL all_reduce captured in the step graph (symmetric memory unavailable: {repr(e)[:80]})"
-        if flat_grads is None:
+        if flat_grads is None and world > 1:
             flat_grads = flatten_grads(params)
-            if world > 1 and grad_sync.startswith("none"):
+            if grad_sync.startswith("none"):
                 grad_sync = "NCCL all_reduce captured in the step graph"
 
         def graph_body(s, j):

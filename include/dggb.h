@@ -285,6 +285,23 @@ int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, cons
 int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
                         int32_t f, int32_t h, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);
+/* The node encoder + edge-encoder projection of class DGG as the training step runs them (dgm.py:1778, 1784 and
+ * their autograd):
+ *   dggb_encoder_fwd:  x_enc = LeakyReLU_slope(x Wn^T + bn),  y = x_enc We^T  (H in {32, 64}; == dggb_linear_fused with
+ *     w2 = We).  Its weight-split launch additionally writes we_t_split [2H, H] = [We^T_hi ; We^T_lo] (or NULL) -- the
+ *     pre-split B operand of the backward's d pre GEMM -- and clears zero_ws (the backward's accumulators), so the
+ *     backward needs no split / fill launches of its own.
+ *   dggb_encoder_bwd_dpre:  d pre = LeakyReLU'_slope(x_enc) * (g_y We + g_xenc)  (g_xenc may be NULL) in ONE launch.
+ *     dpre [N,H] may be NULL when the caller only needs the weight gradients; dpre_t_hi / dpre_t_lo [H, npad]
+ *     (npad >= n, npad % 4 == 0; both or neither) receive the TRANSPOSED TF32 hi/lo split of d pre, zero padded, and
+ *     colsum[H] (or NULL) += its column sums (the bias gradient): the operands of dggb_gemm_tn_tc_presplit. */
+int dggb_encoder_fwd(const float* x, const float* wn, const float* bn, float slope, int32_t n, int32_t f,
+                     int32_t h, float* x_enc, const float* we, float* y, void* workspace,
+                     int64_t workspace_bytes, float* we_t_split, float* zero_ws, int64_t zero_count,
+                     void* stream);
+int dggb_encoder_bwd_dpre(const float* g_y, const float* we_t_split, const float* g_xenc, const float* x_enc,
+                          float slope, int32_t n, int32_t h, float* dpre, float* dpre_t_hi, float* dpre_t_lo,
+                          int32_t npad, float* colsum, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Weight gradients of the tall node encoders (nn.Linear of dgm.py:1741-1744 / 1097-1100 /
@@ -300,6 +317,10 @@ int dggb_gemm_tn_splitk(const float* a /* [N,P] */, const float* b /* [N,Q] */, 
 int64_t dggb_gemm_tn_tc_workspace_bytes(int32_t n, int32_t p);
 int dggb_gemm_tn_tc(const float* a, const float* b, int32_t n, int32_t p, int32_t q, float* out,
                     float* colsum_a, void* workspace, int64_t workspace_bytes, void* stream);
+/* Same product from an operand that is already transposed and split (a_t_hi / a_t_lo [P, npad], zero padded for
+ * nodes >= n; written by dggb_encoder_bwd_dpre): no transpose pass, no workspace. */
+int dggb_gemm_tn_tc_presplit(const float* a_t_hi, const float* a_t_lo, int32_t npad, const float* b, int32_t n,
+                             int32_t p, int32_t q, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * All-pairs scoring + per-row streaming top-K (legacy all-pairs DGG, dgm.py:271-301; a15):

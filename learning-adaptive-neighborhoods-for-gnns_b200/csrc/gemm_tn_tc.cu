@@ -216,24 +216,19 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   }
 }
 
+// a_hi / a_lo: a^T split, [P, npad] (npad % 4 == 0, zero padded beyond n)
 template <int P>
-static int launch_tn(const float* a, const float* b, int n, int q, float* out, float* colsum, float* ws,
-                     cudaStream_t st) {
-  const int npad = (n + 31) / 32 * 32;
-  float* a_hi = ws;
-  float* a_lo = ws + (size_t)P * npad;
-  launch_pdl(transpose_split_kernel, dim3(dim3(npad / 32, (P + 31) / 32)), dim3(256), 0, st, a, n, npad, P, a_hi, a_lo, colsum);
-  int rc = launch_status();
-  if (rc != DGGB_OK) return rc;
+static int launch_tn_gemm(const float* a_hi, const float* a_lo, int npad, const float* b, int n, int q, float* out,
+                          cudaStream_t st) {
   CUtensorMap tm_b, tm_ahi, tm_alo;
-  rc = make_tmap_2d_f32(&tm_b, b, (uint64_t)n, (uint64_t)q, 32, 32);
+  int rc = make_tmap_2d_f32(&tm_b, b, (uint64_t)n, (uint64_t)q, 32, 32);
   if (rc != DGGB_OK) return rc;
   rc = make_tmap_2d_f32(&tm_ahi, a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
   if (rc != DGGB_OK) return rc;
   rc = make_tmap_2d_f32(&tm_alo, a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
   if (rc != DGGB_OK) return rc;
   const int m_tiles = (q + kTcM - 1) / kTcM;
-  const int kb_total = npad / 32;
+  const int kb_total = (n + 31) / 32;
   int splits = (2 * kNumSMs + m_tiles - 1) / m_tiles;
   if (splits > kb_total) splits = kb_total;
   const int kb_per_split = (kb_total + splits - 1) / splits;
@@ -244,6 +239,18 @@ static int launch_tn(const float* a, const float* b, int n, int q, float* out, f
   launch_pdl(gemm_tn_tf32x3_kernel<P>, dim3(m_tiles, splits), dim3(kTcThreads), smem, st, tm_b, tm_ahi, tm_alo, n, q,
              kb_per_split, out);
   return launch_status();
+}
+
+template <int P>
+static int launch_tn(const float* a, const float* b, int n, int q, float* out, float* colsum, float* ws,
+                     cudaStream_t st) {
+  const int npad = (n + 31) / 32 * 32;
+  float* a_hi = ws;
+  float* a_lo = ws + (size_t)P * npad;
+  launch_pdl(transpose_split_kernel, dim3(dim3(npad / 32, (P + 31) / 32)), dim3(256), 0, st, a, n, npad, P, a_hi, a_lo, colsum);
+  int rc = launch_status();
+  if (rc != DGGB_OK) return rc;
+  return launch_tn_gemm<P>(a_hi, a_lo, npad, b, n, q, out, st);
 }
 
 }  // namespace dggb
@@ -267,6 +274,24 @@ extern "C" int dggb_gemm_tn_tc(const float* a, const float* b, int32_t n, int32_
     case 32: return launch_tn<32>(a, b, n, q, out, colsum_a, ws, st);
     case 64: return launch_tn<64>(a, b, n, q, out, colsum_a, ws, st);
     case 128: return launch_tn<128>(a, b, n, q, out, colsum_a, ws, st);
+    default: return DGGB_ERR_BAD_SHAPE;
+  }
+}
+
+// out[P,Q] += a^T b with a^T already split (a_t_hi / a_t_lo [P, npad], zero padded for nodes >= n): the operand
+// dggb_encoder_bwd_dpre leaves behind -- no transpose pass
+extern "C" int dggb_gemm_tn_tc_presplit(const float* a_t_hi, const float* a_t_lo, int32_t npad, const float* b,
+                                        int32_t n, int32_t p, int32_t q, float* out, void* stream) {
+  if (!a_t_hi || !a_t_lo || !b || !out || n < 0 || p <= 0 || q <= 0 || npad < n) return DGGB_ERR_BAD_ARG;
+  if (q % 4 != 0 || npad % 4 != 0 || ((uintptr_t)b % 16) || ((uintptr_t)a_t_hi % 16) || ((uintptr_t)a_t_lo % 16))
+    return DGGB_ERR_BAD_SHAPE;
+  if (n == 0) return DGGB_OK;
+  cudaStream_t st = as_stream(stream);
+  switch (p) {
+    case 16: return launch_tn_gemm<16>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
+    case 32: return launch_tn_gemm<32>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
+    case 64: return launch_tn_gemm<64>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
+    case 128: return launch_tn_gemm<128>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
     default: return DGGB_ERR_BAD_SHAPE;
   }
 }

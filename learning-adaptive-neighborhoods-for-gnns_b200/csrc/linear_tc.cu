@@ -25,15 +25,23 @@ using tc::tf32_rna;
 // (transposed: w is given as [F, H] and the kernel needs W_eff[h][f] = w[f][h])
 __global__ void split_w_kernel(const float* __restrict__ w, int count, int h, int f, int transposed,
                                float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ w2, int count2,
-                               float* __restrict__ hi2, float* __restrict__ lo2, float* zero_ws, long long zero_count) {
+                               float* __restrict__ hi2, float* __restrict__ lo2, float* __restrict__ t2,
+                               int h2, float* zero_ws, long long zero_count) {
   // wait FIRST, then let the dependent grid go: when the GEMM kernel's CTAs start, everything before this launch has
   // completed, so the GEMM may stream its x tiles (never written by this kernel) without waiting for the split --
   // only its W loads wait.  The x ring fills while W is being split.
   pdl_wait();
   pdl_trigger();
   zero_fill(zero_ws, zero_count);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count + count2; i += gridDim.x * blockDim.x) {
-    if (i < count) {
+  const int count3 = t2 != nullptr ? count2 : 0;   // [W2^T_hi ; W2^T_lo] stacked ([2 h2, h2]): the backward's B operand
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count + count2 + count3; i += gridDim.x * blockDim.x) {
+    if (i >= count + count2) {
+      const int k = i - count - count2;                          // k = r * h2 + c  ->  W2^T[r][c] = w2[c][r]
+      const float v = __ldg(w2 + (size_t)(k % h2) * h2 + (k / h2));
+      const float hh = tf32_rna(v);
+      t2[k] = hh;
+      t2[count2 + k] = tf32_rna(v - hh);
+    } else if (i < count) {
       const float v = transposed ? __ldg(w + (size_t)(i % f) * h + (i / f)) : __ldg(w + i);
       const float hh = tf32_rna(v);
       hi[i] = hh;
@@ -89,7 +97,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                          const __grid_constant__ CUtensorMap tm_w2hi, const __grid_constant__ CUtensorMap tm_w2lo,
                          const float* __restrict__ bias, const float* __restrict__ addend,
                          const float* __restrict__ act_src, float slope, int n, int f, float* __restrict__ out,
-                         float* __restrict__ out2) {
+                         float* __restrict__ out2, int wait_first, float* __restrict__ outT_hi,
+                         float* __restrict__ outT_lo, int npad, float* __restrict__ colsum) {
   static_assert(!FUSE2 || H == 32 || H == 64, "fused second GEMM: K = H must be one or two 32-float k-blocks");
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
@@ -156,8 +165,11 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     // The preceding grid is split_w_kernel of the same call, which triggers this launch only AFTER its own
     // dependency wait: x (and everything else older than the split) is complete and visible, only the split W is not.
     // The first round of both rings needs no "empty" wait: x goes in flight right away, W after the wait.
+    // (wait_first: W arrives pre-split and no split kernel precedes this launch -- the preceding grid may be the
+    // producer of x, so nothing is loaded before the dependency wait.)
+    if (wait_first) pdl_wait();
     for (int kb = 0; kb < XS && kb < num_kb; ++kb) load_x(kb);
-    pdl_wait();
+    if (!wait_first) pdl_wait();
     for (int kb = 0; kb < WS && kb < num_kb; ++kb) load_w(kb);
   }
   if (warp == 1) {
@@ -345,13 +357,47 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           v.x = v.x > 0.f ? v.x : slope * v.x; v.y = v.y > 0.f ? v.y : slope * v.y;
           v.z = v.z > 0.f ? v.z : slope * v.z; v.w = v.w > 0.f ? v.w : slope * v.w;
         }
-        if (row < n) *reinterpret_cast<float4*>(out + (size_t)row * H + ec) = v;
-        else v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (FUSE2) *reinterpret_cast<float4*>(stg + lr * kPitch + ec) = v;   // activated tile for the chained GEMM
+        if (row >= n) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (out != nullptr) *reinterpret_cast<float4*>(out + (size_t)row * H + ec) = v;
+        // the finished tile goes back to the staging slice for the chained GEMM / the transposed copy
+        if (FUSE2 || outT_hi != nullptr) *reinterpret_cast<float4*>(stg + lr * kPitch + ec) = v;
       }
       if (it0 == 0 && threadIdx.x == 64) LTRACE(7);
     }
     if (threadIdx.x == 64) LTRACE(3);
+    if (!FUSE2 && outT_hi != nullptr) {
+      // ---- transposed TF32 hi/lo copy of the tile, outT[p][node] ([H, npad], zero padded), and its column sums:
+      // what the weight-gradient GEMM dW = out^T x (gemm_tn_tc.cu) takes as its K-major B operand and the bias
+      // gradient -- written here instead of by a transpose pass that re-reads `out` (one launch and 2 N H 4 bytes
+      // less per backward).  lane == row of this warp's 32-row slice: 128-byte coalesced stores per p.
+      __syncwarp();
+      const int node = row0 + q * 32 + lane;
+      if (node < npad) {
+#pragma unroll 4
+        for (int c = 0; c < H; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(stg + lane * kPitch + c);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float hh = tf32_rna(vv[j]);
+            outT_hi[(size_t)(c + j) * npad + node] = hh;
+            outT_lo[(size_t)(c + j) * npad + node] = tf32_rna(vv[j] - hh);
+          }
+        }
+      }
+      if (colsum != nullptr) {
+#pragma unroll
+        for (int c0 = 0; c0 < H; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < H) {
+            float t = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) t += stg[r * kPitch + c];     // rows >= n hold zeros
+            if (t != 0.f) atomicAdd(colsum + c, t);
+          }
+        }
+      }
+    }
     if (FUSE2) {
       // ---- chained GEMM: this thread's activated row -> TF32 hi/lo -> TMEM (A operand, K = H) ----
       __syncwarp();
@@ -397,25 +443,44 @@ __global__ void __launch_bounds__(kLinThreads, 1)
   }
 }
 
+// Optional pieces of one call (all pointers may be NULL):
+//   w_presplit : `w` is the stacked [W_hi ; W_lo] ([2H, F]) written by an earlier launch; no split kernel runs
+//   w2t_split  : out, [2H, H]: stacked split of W2^T (the B operand of the backward's d pre GEMM)
+//   outT_hi/lo : out, [H, npad] transposed TF32 split of `out` + colsum[H] += column sums (see the kernel epilogue)
+struct LinearExtra {
+  bool w_presplit = false;
+  float* w2t_split = nullptr;
+  float* outT_hi = nullptr;
+  float* outT_lo = nullptr;
+  int npad = 0;
+  float* colsum = nullptr;
+};
+
 template <int H>
 static int launch_linear(const float* x, const float* w, int w_transposed, const float* b, const float* addend,
                          const float* act_src, float slope, int n, int f, float* out, float* ws, const float* w2,
-                         float* out2, float* zero_ws, long long zero_count, cudaStream_t st) {
+                         float* out2, float* zero_ws, long long zero_count, cudaStream_t st,
+                         const LinearExtra& ex = LinearExtra()) {
 #ifndef DGGB_LIN_XS
 #define DGGB_LIN_XS 4
 #define DGGB_LIN_WS 3
 #endif
   constexpr int XS = DGGB_LIN_XS, WS = DGGB_LIN_WS;   // H <= 64: 64 KB + 3 x 2H x 128 B <= 112 KB so that two CTAs share an SM
-  float* w_hi = ws;               // [W_hi ; W_lo] stacked: one [2H, F] matrix, one tensor map
-  float* w_lo = ws + (size_t)H * f;
+  float* w_hi = ex.w_presplit ? const_cast<float*>(w) : ws;   // [W_hi ; W_lo] stacked: one [2H, F] matrix, one tensor map
   const bool chained = (H == 32 || H == 64) && w2 != nullptr;
-  float* w2_hi = ws + (size_t)2 * H * f;
-  float* w2_lo = w2_hi + (size_t)H * H;
-  const int n_split = H * f + (chained ? H * H : 0);
-  launch_pdl(split_w_kernel, dim3((n_split + 255) / 256), dim3(256), 0, st, w, H * f, H, f, w_transposed, w_hi, w_lo,
-             chained ? w2 : static_cast<const float*>(nullptr), chained ? H * H : 0, w2_hi, w2_lo, zero_ws, zero_count);
-  int rc = launch_status();
-  if (rc != DGGB_OK) return rc;
+  float* w2_hi = ex.w_presplit ? nullptr : ws + (size_t)2 * H * f;
+  float* w2_lo = ex.w_presplit ? nullptr : w2_hi + (size_t)H * H;
+  int rc;
+  if (!ex.w_presplit) {
+    float* w_lo = ws + (size_t)H * f;
+    const int n_split = H * f + (chained ? H * H * (ex.w2t_split ? 2 : 1) : 0);
+    launch_pdl(split_w_kernel, dim3((n_split + 255) / 256), dim3(256), 0, st, w, H * f, H, f, w_transposed, w_hi, w_lo,
+               chained ? w2 : static_cast<const float*>(nullptr), chained ? H * H : 0, w2_hi, w2_lo,
+               chained ? ex.w2t_split : static_cast<float*>(nullptr), H, zero_ws, zero_count);
+    rc = launch_status();
+    if (rc != DGGB_OK) return rc;
+  }
+  const int wait_first = ex.w_presplit ? 1 : 0;
   CUtensorMap tm_x, tm_w, tm_w2hi, tm_w2lo;
   rc = make_tmap_2d_f32(&tm_x, x, (uint64_t)n, (uint64_t)f, kLinBM, 32);
   if (rc != DGGB_OK) return rc;
@@ -425,6 +490,7 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   const int grid = (n + kLinBM - 1) / kLinBM;
   if constexpr (H == 32 || H == 64) {
     if (w2 != nullptr) {
+      if (ex.w_presplit || ex.outT_hi) return DGGB_ERR_BAD_ARG;
       rc = make_tmap_2d_f32(&tm_w2hi, w2_hi, (uint64_t)H, (uint64_t)H, H, 32);
       if (rc != DGGB_OK) return rc;
       rc = make_tmap_2d_f32(&tm_w2lo, w2_lo, (uint64_t)H, (uint64_t)H, H, 32);
@@ -433,7 +499,8 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return cuda_status(e);
       launch_pdl((linear_tf32x3_kernel<H, XS, WS, true>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w,
-                 tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2);
+                 tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2, 0, static_cast<float*>(nullptr),
+                 static_cast<float*>(nullptr), 0, static_cast<float*>(nullptr));
       return launch_status();
     }
   }
@@ -442,8 +509,20 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
   launch_pdl((linear_tf32x3_kernel<H, XS, WS, false>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w, tm_w, tm_w,
-             b, addend, act_src, slope, n, f, out, static_cast<float*>(nullptr));
+             b, addend, act_src, slope, n, f, out, static_cast<float*>(nullptr), wait_first, ex.outT_hi, ex.outT_lo,
+             ex.npad, ex.colsum);
   return launch_status();
+}
+
+template <typename... A>
+static int dispatch_linear(int h, A... a) {
+  switch (h) {
+    case 16: return launch_linear<16>(a...);
+    case 32: return launch_linear<32>(a...);
+    case 64: return launch_linear<64>(a...);
+    case 128: return launch_linear<128>(a...);
+    default: return DGGB_ERR_BAD_SHAPE;
+  }
 }
 
 }  // namespace dggb
@@ -453,6 +532,8 @@ extern "C" int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h) {
   if (f <= 0 || h <= 0) return DGGB_ERR_BAD_ARG;
   return ((int64_t)2 * h * f + (int64_t)2 * h * h) * 4;   // W hi/lo (+ W2 hi/lo of the chained GEMM)
 }
+
+static bool misaligned(const void* p) { return p != nullptr && ((uintptr_t)p % 16) != 0; }
 
 extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
                                  const float* addend, const float* act_src, float slope, int32_t n, int32_t f,
@@ -465,25 +546,62 @@ extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_trans
   if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
   float* ws = reinterpret_cast<float*>(workspace);
   // TMA needs 16-byte row pitches and base addresses; the supported widths are the hidden sizes of the path
-  if (f % 4 != 0 || ((uintptr_t)x % 16) || ((uintptr_t)w % 16) || ((uintptr_t)out % 16) || (w2 && (h > 64 || h % 32)) ||
-      (addend && ((uintptr_t)addend % 16)) || (act_src && ((uintptr_t)act_src % 16)) ||
-      (b && ((uintptr_t)b % 16)) || (out2 && ((uintptr_t)out2 % 16)))
+  if (f % 4 != 0 || misaligned(x) || misaligned(w) || misaligned(out) || (w2 && (h > 64 || h % 32)) ||
+      misaligned(addend) || misaligned(act_src) || misaligned(b) || misaligned(out2))
     return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
-  cudaStream_t st = as_stream(stream);
-  switch (h) {
-    case 16: return launch_linear<16>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
-    case 32: return launch_linear<32>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
-    case 64: return launch_linear<64>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
-    case 128: return launch_linear<128>(x, w, w_transposed, b, addend, act_src, slope, n, f, out, ws, w2, out2, zero_ws, (long long)zero_count, st);
-    default: return DGGB_ERR_BAD_SHAPE;
-  }
+  return dispatch_linear(h, x, w, (int)w_transposed, b, addend, act_src, slope, (int)n, (int)f, out, ws, w2, out2,
+                         zero_ws, (long long)zero_count, as_stream(stream), LinearExtra());
 }
 
 extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
                                    int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, nullptr, nullptr, workspace,
                            workspace_bytes, nullptr, 0, stream);
+}
+
+// (x_enc, y) = (LeakyReLU_slope(x Wn^T + bn), x_enc We^T) in one launch (+ the weight-split launch), see dggb.h
+extern "C" int dggb_encoder_fwd(const float* x, const float* wn, const float* bn, float slope, int32_t n, int32_t f,
+                                int32_t h, float* x_enc, const float* we, float* y, void* workspace,
+                                int64_t workspace_bytes, float* we_t_split, float* zero_ws, int64_t zero_count,
+                                void* stream) {
+  if (!x || !wn || !x_enc || !we || !y || !workspace || n < 0 || f <= 0 || zero_count < 0) return DGGB_ERR_BAD_ARG;
+  if (h != 32 && h != 64) return DGGB_ERR_BAD_SHAPE;
+  if (workspace_bytes < dggb_linear_act_workspace_bytes(f, h)) return DGGB_ERR_WORKSPACE;
+  if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
+  if (f % 4 != 0 || misaligned(x) || misaligned(wn) || misaligned(x_enc) || misaligned(bn) || misaligned(y) ||
+      misaligned(we_t_split))
+    return DGGB_ERR_BAD_SHAPE;
+  if (n == 0) return DGGB_OK;
+  LinearExtra ex;
+  ex.w2t_split = we_t_split;
+  return dispatch_linear(h, x, wn, 0, bn, static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+                         slope, (int)n, (int)f, x_enc, reinterpret_cast<float*>(workspace), we, y, zero_ws,
+                         (long long)zero_count, as_stream(stream), ex);
+}
+
+// d pre = LeakyReLU'_slope(x_enc) * (g_y We + g_xenc) from the PRE-SPLIT We^T of dggb_encoder_fwd: one launch; the tile
+// also leaves as the transposed TF32 split + column sums that dggb_gemm_tn_tc_presplit consumes
+extern "C" int dggb_encoder_bwd_dpre(const float* g_y, const float* we_t_split, const float* g_xenc,
+                                     const float* x_enc, float slope, int32_t n, int32_t h, float* dpre,
+                                     float* dpre_t_hi, float* dpre_t_lo, int32_t npad, float* colsum, void* stream) {
+  if (!g_y || !we_t_split || !x_enc || n < 0 || (dpre_t_hi == nullptr) != (dpre_t_lo == nullptr) ||
+      (!dpre && !dpre_t_hi))
+    return DGGB_ERR_BAD_ARG;
+  if (h != 16 && h != 32 && h != 64 && h != 128) return DGGB_ERR_BAD_SHAPE;
+  if (dpre_t_hi && (npad < n || npad % 4 != 0)) return DGGB_ERR_BAD_ARG;
+  if (misaligned(g_y) || misaligned(we_t_split) || misaligned(g_xenc) || misaligned(x_enc) || misaligned(dpre))
+    return DGGB_ERR_BAD_SHAPE;
+  if (n == 0) return DGGB_OK;
+  LinearExtra ex;
+  ex.w_presplit = true;
+  ex.outT_hi = dpre_t_hi;
+  ex.outT_lo = dpre_t_lo;
+  ex.npad = npad;
+  ex.colsum = colsum;
+  return dispatch_linear(h, g_y, we_t_split, 0, static_cast<const float*>(nullptr), g_xenc, x_enc, slope, (int)n,
+                         (int)h, dpre, static_cast<float*>(nullptr), static_cast<const float*>(nullptr),
+                         static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0LL, as_stream(stream), ex);
 }
 
 #ifdef DGGB_LIN_TRACE

@@ -539,15 +539,46 @@ def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None
     return out if w2 is None else (out, out2)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for the independent branch of the encoder backward (dWe next to d pre -> dWn);
+    inside a CUDA-graph capture the fork / join become parallel branches of the graph."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
 class _EncodeProject(torch.autograd.Function):
     """(x_enc, y) = (LeakyReLU(x Wn^T + bn), x_enc We^T): the node encoder and the edge-encoder projection of
-    ``DGG`` (dgm.py:1778, 1784) as ONE autograd node, so the backward is three kernels:
-        dpre = LeakyReLU'(x_enc) * (g_y We + g_xenc)   (dggb_linear_fused)
-        dWe  = g_y^T x_enc ;  (dWn, dbn) = dpre^T x     (dggb_gemm_tn_tc)"""
+    ``DGG`` (dgm.py:1778, 1784) as ONE autograd node.  Forward: two launches (weight split, GEMM with the chained
+    second GEMM); the split launch also leaves the pre-split We^T and the cleared accumulators for the backward, which
+    is then three launches and no fills:
+        dpre = LeakyReLU'(x_enc) * (g_y We + g_xenc), leaving as a transposed TF32 split + column sums (= dbn)
+        dWn  = dpre^T x   (dggb_gemm_tn_tc_presplit)         |  on a second stream:  dWe = g_y^T x_enc"""
 
     @staticmethod
     def forward(ctx, x, wn, bn, we, slope: float):
-        if wn.shape[0] in (32, 64):     # one launch: y chained in the encoder kernel's epilogue
+        h, f_in = wn.shape
+        n = x.shape[0]
+        ctx.fast = h in (32, 64) and n >= 4096 and f_in >= 256      # the tensor-core weight-gradient GEMM's domain
+        wet = zbuf = None
+        if ctx.fast:
+            x, wn, bn, we = x.contiguous(), wn.contiguous(), bn.contiguous(), we.contiguous()
+            dev = x.device
+            x_enc = torch.empty(n, h, dtype=torch.float32, device=dev)
+            y = torch.empty(n, h, dtype=torch.float32, device=dev)
+            ws = torch.empty(2 * h * f_in + 2 * h * h, dtype=torch.float32, device=dev)
+            if any(ctx.needs_input_grad[:4]):
+                wet = torch.empty(2 * h * h, dtype=torch.float32, device=dev)
+                zbuf = torch.empty(h * h + h * f_in + h, dtype=torch.float32, device=dev)   # dWe | dWn | dbn
+            check(lib().dggb_encoder_fwd(p(x), p(wn), p(bn), float(slope), i32(n), i32(f_in), i32(h), p(x_enc), p(we),
+                                         p(y), p(ws), i64(ws.numel() * 4), p(wet), p(zbuf),
+                                         i64(0 if zbuf is None else zbuf.numel()), stream()), "encoder_fwd")
+        elif h in (32, 64):     # one launch: y chained in the encoder kernel's epilogue
             res = _linear_act_tc(x, wn, bn, slope, w2=we)
             x_enc, y = res if res is not None else (None, None)
         else:
@@ -556,6 +587,7 @@ class _EncodeProject(torch.autograd.Function):
         if y is None:
             raise RuntimeError("encode_project: shape not supported by the tensor-core kernels")
         ctx.slope = slope
+        ctx.wet, ctx.zbuf = wet, zbuf
         ctx.save_for_backward(x, wn, we, x_enc)
         ctx.set_materialize_grads(False)   # an unused output must not cost an [N, h] zero fill
         return x_enc, y
@@ -568,6 +600,31 @@ class _EncodeProject(torch.autograd.Function):
         g_y = torch.zeros_like(x_enc) if g_y is None else _f32c(g_y)
         g_xenc = None if g_xenc is None else _f32c(g_xenc)
         h, f_in = wn.shape
+        n = x.shape[0]
+        if ctx.fast and ctx.wet is not None:
+            dev = x.device
+            zbuf, ctx.zbuf = ctx.zbuf, None       # cleared by the forward's split launch; a second backward: fresh zeros
+            if zbuf is None:
+                zbuf = torch.zeros(h * h + h * f_in + h, dtype=torch.float32, device=dev)
+            dwe, dwn, dbn = zbuf[:h * h].view(h, h), zbuf[h * h:h * h + h * f_in].view(h, f_in), zbuf[h * h + h * f_in:]
+            npad = (n + 31) // 32 * 32
+            want_dx = ctx.needs_input_grad[0]
+            dpre = torch.empty(n, h, dtype=torch.float32, device=dev) if want_dx else None
+            dpt = torch.empty(2, h, npad, dtype=torch.float32, device=dev)
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(main)                                  # fork: g_y and the cleared accumulators are ready
+            with torch.cuda.stream(side):
+                check(lib().dggb_gemm_tn_splitk(p(g_y), p(x_enc), i32(n), i32(h), i32(h), p(dwe), None, stream()),
+                      "gemm_tn_splitk")
+            check(lib().dggb_encoder_bwd_dpre(p(g_y), p(ctx.wet), p(g_xenc), p(x_enc), float(ctx.slope), i32(n), i32(h),
+                                              p(dpre), p(dpt[0]), p(dpt[1]), i32(npad), p(dbn), stream()),
+                  "encoder_bwd_dpre")
+            check(lib().dggb_gemm_tn_tc_presplit(p(dpt[0]), p(dpt[1]), i32(npad), p(x), i32(n), i32(h), i32(f_in),
+                                                 p(dwn), stream()), "gemm_tn_tc_presplit")
+            main.wait_stream(side)                                  # join
+            dx = dpre @ wn if want_dx else None
+            return dx, dwn, dbn, dwe, None
         # split-K accumulators of both weight-gradient GEMMs: cleared by the dpre launch (its weight-split kernel)
         zbuf = torch.empty(h * h + h * f_in + h, dtype=torch.float32, device=x.device)
         dpre = _linear_act_tc(g_y, we, None, ctx.slope, w_transposed=True, addend=g_xenc, act_src=x_enc, zero=zbuf)
