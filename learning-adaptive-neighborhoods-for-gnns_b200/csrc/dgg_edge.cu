@@ -752,6 +752,284 @@ __global__ void __launch_bounds__(kFusedThreads)
   for (int c = threadIdx.x; c < h; c += kFusedThreads) atomicAdd(dbe + c, dbe_s[c]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second generation of the fused kernels (same contract, same results up to the summation order of the row sums).
+// What the ncu source view of the first generation showed at Pubmed shape (profiles/r02_fused_edge_v2.md): a third
+// of the stall samples sat at block barriers (rows dealt to 8-lane groups finish at very different times, and rows
+// longer than 32 entries were ranked by the whole block after yet another barrier), a quarter behind the per-edge
+// dependent chain "index load -> gather" that every group repeated `per` times back to back.  Here
+//   * phase 1 walks the block's entries INTERLEAVED over the groups (coalesced index loads) and loads the indices of
+//     the next entry while the current entry's rows are in flight: one memory round trip per entry instead of two;
+//   * phase 2 is ENTRY-parallel: thread == entry; it sweeps its own row in shared memory, which yields the rank (a
+//     count), the row sum s and therefore k in the same loop -- no per-row pass, no long-row pass, one barrier.  The
+//     compare work is the same sum of deg^2, but spread evenly (a 171-entry row occupies 171 threads for 171
+//     iterations instead of one 8-lane group for 3 600);
+//   * backward: entry-parallel as well -- per-entry d out / d k terms into shared memory, each entry's thread sums its
+//     row (= dk_i), forms ds_i and its own d R_e; then the gather / scatter phase with prefetched indices.
+// ------------------------------------------------------------------------------------------------
+template <int T, int LC>
+__global__ void __launch_bounds__(kFusedThreads)
+    dgg_fwd_fused2_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
+                          const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb, int cap,
+                          const float* __restrict__ y, const float* __restrict__ be,
+                          const float* __restrict__ abl_noise, const float* __restrict__ deg_w,
+                          const float* __restrict__ deg_b, int hard_k, float* R, int32_t* __restrict__ rank,
+                          float* __restrict__ s_out, float* __restrict__ k_out, float* __restrict__ out,
+                          float* zero_ws, long long zero_count) {
+  pdl_trigger();
+  if constexpr (LC > 0) {
+    L = LC;
+    h = 16 * LC;
+  }
+  extern __shared__ float sR[];          // [cap] scores of this block's entry range
+  __shared__ int rng[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  pdl_wait();
+  zero_fill(zero_ws, zero_count);   // the backward's accumulation buffers (dy | dbe | ddeg | ds)
+  fused_row_range(rowptr, erow, n, nnz, epb, rng);
+  const int r0 = rng[0], r1 = rng[1], eb0 = rng[2], eb1 = rng[3];
+  const int nE = eb1 - eb0;
+  // ---- phase 1: scores.  entry idx = it * groups + gid ----
+  {
+    RowSlice<T> bias;
+    load_slice<T>(bias, be, h, lg, L);
+    const int groups = (kFusedThreads / kWarp) * G;
+    const int per = (nE + groups - 1) / groups;
+    int idx = warp * G + grp;
+    int u_n = 0, v_n = 0;
+    if (idx < nE) {
+      u_n = __ldg(erow + eb0 + idx);
+      v_n = __ldg(col + eb0 + idx);
+    }
+    for (int it = 0; it < per; ++it, idx += groups) {
+      const bool valid = idx < nE;
+      const int u = u_n, v = v_n;
+      if (idx + groups < nE) {            // next entry's indices travel while this entry's rows do
+        u_n = __ldg(erow + eb0 + idx + groups);
+        v_n = __ldg(col + eb0 + idx + groups);
+      }
+      RowSlice<T> yu, yv;
+      load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
+      load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+      const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
+      if (valid && lg == 0) {
+        const int e = eb0 + idx;
+        float r = sigmoidf_(z);
+        if (abl_noise != nullptr) r = sigmoidf_(r + __ldg(abl_noise + e));  // dgm.py:1933-1935
+        R[e] = r;
+        if (idx < cap) sR[idx] = r;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: thread == entry ----
+  const float w = __ldg(deg_w), b = __ldg(deg_b);
+  for (int idx = threadIdx.x; idx < nE; idx += kFusedThreads) {
+    const int e = eb0 + idx;
+    const int u = __ldg(erow + e);
+    const int jb = __ldg(rowptr + u) - eb0, je = __ldg(rowptr + u + 1) - eb0;   // the row inside the block's window
+    float mine, s = 0.f;
+    int cnt = 0;
+    if (je <= cap) {
+      mine = sR[idx];
+#pragma unroll 4
+      for (int j = jb; j < je; ++j) {
+        const float rj = sR[j];
+        s += rj;
+        cnt += (rj > mine) || (rj == mine && j < idx);
+      }
+    } else {                              // beyond the shared-memory window (very large bounded-degree graphs)
+      mine = __ldcg(R + e);
+#pragma unroll 4
+      for (int j = jb; j < je; ++j) {
+        const float rj = __ldcg(R + eb0 + j);
+        s += rj;
+        cnt += (rj > mine) || (rj == mine && j < idx);
+      }
+    }
+    const float k = leaky(w * s + b);  // dgm.py:1791-1792
+    rank[e] = cnt;
+    out[e] = (hard_k >= 0) ? (cnt < hard_k ? mine : 0.f) : mine * first_k_plus_one((float)cnt, k);
+    if (idx == jb) {
+      s_out[u] = s;
+      k_out[u] = k;
+    }
+  }
+  for (int i = r0 + threadIdx.x; i < r1; i += kFusedThreads) {   // empty rows: s = 0
+    if (__ldg(rowptr + i) == __ldg(rowptr + i + 1)) {
+      s_out[i] = 0.f;
+      k_out[i] = leaky(b);
+    }
+  }
+}
+
+template <int T, int LC>
+__global__ void __launch_bounds__(kFusedThreads)
+    dgg_bwd_fused2_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
+                          const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb, int cap,
+                          const float* __restrict__ y, const float* __restrict__ be,
+                          const float* __restrict__ abl_noise, int hard_k, const float* __restrict__ R,
+                          const int32_t* __restrict__ rank, const float* __restrict__ s_in,
+                          const float* __restrict__ k_in, const float* __restrict__ g_out,
+                          const float* __restrict__ deg_w, const float* __restrict__ deg_b, float* ds_ws,
+                          float* __restrict__ dy, float* __restrict__ dbe, float* __restrict__ ddeg) {
+  pdl_trigger();
+  if constexpr (LC > 0) {
+    L = LC;
+    h = 16 * LC;
+  }
+  extern __shared__ float sm2[];         // sT[cap]: d out / d k terms, sDr[cap]: d loss / d R_e   (nE <= cap, host)
+  float* sT = sm2;
+  float* sDr = sm2 + cap;
+  __shared__ float dbe_s[512];           // block-level bias-gradient accumulator (h <= 512)
+  __shared__ float red[2][kFusedThreads / kWarp];
+  __shared__ int rng[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int G = kWarp / L, lg = lane % L, grp = lane / L;
+  for (int c = threadIdx.x; c < h; c += kFusedThreads) dbe_s[c] = 0.f;
+  pdl_wait();
+  fused_row_range(rowptr, erow, n, nnz, epb, rng);
+  const int eb0 = rng[2], eb1 = rng[3];
+  const int nE = eb1 - eb0;
+  // ---- phase A: thread == entry.  d out / d k_i = 0.5 sum_e g_e R_e sech^2(r_e - k_i), chained through the degree
+  // decoder: ds_i = dk_i LeakyReLU'(w s_i + b) w;  d R_e = g_e (first_k + 1) + ds_i ----
+  if (hard_k < 0) {
+    for (int idx = threadIdx.x; idx < nE; idx += kFusedThreads) {
+      const int e = eb0 + idx;
+      const float th = tanhf((float)__ldg(rank + e) - __ldg(k_in + __ldg(erow + e)));
+      sT[idx] = __ldg(g_out + e) * __ldg(R + e) * 0.5f * (1.f - th * th);
+    }
+  }
+  __syncthreads();
+  {
+    const float w = __ldg(deg_w), b = __ldg(deg_b);
+    float dw_acc = 0.f, db_acc = 0.f;
+    for (int idx = threadIdx.x; idx < nE; idx += kFusedThreads) {
+      const int e = eb0 + idx;
+      const float g = __ldg(g_out + e);
+      float dr;
+      if (hard_k >= 0) {
+        dr = (__ldg(rank + e) < hard_k) ? g : 0.f;
+      } else {
+        const int u = __ldg(erow + e);
+        const int jb = __ldg(rowptr + u) - eb0, je = __ldg(rowptr + u + 1) - eb0;
+        float dk = 0.f;
+#pragma unroll 4
+        for (int j = jb; j < je; ++j) dk += sT[j];
+        const float s = __ldg(s_in + u), k = __ldg(k_in + u);
+        const float lr = leaky_grad(w * s + b);
+        const float dsi = dk * lr * w;
+        if (idx == jb) {                   // once per row
+          ds_ws[u] = dsi;
+          dw_acc += dk * lr * s;
+          db_acc += dk * lr;
+        }
+        dr = g * first_k_plus_one((float)__ldg(rank + e), k) + dsi;
+      }
+      if (abl_noise != nullptr) {
+        const float r2 = __ldg(R + e);
+        dr *= r2 * (1.f - r2);  // through the second sigmoid
+      }
+      sDr[idx] = dr;
+    }
+    dw_acc = warp_sum(dw_acc);
+    db_acc = warp_sum(db_acc);
+    if (lane == 0) {
+      red[0][warp] = dw_acc;
+      red[1][warp] = db_acc;
+    }
+  }
+  __syncthreads();
+  if (hard_k < 0 && threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kFusedThreads / kWarp; ++wv) t += red[threadIdx.x][wv];
+    if (t != 0.f) atomicAdd(ddeg + threadIdx.x, t);
+  }
+  // ---- phase B: per entry, recompute z and scatter d pre; every group walks a contiguous run (one flush of the
+  // source-row accumulator per row change), indices of the next entry prefetched ----
+  RowSlice<T> bias, dbe_acc, acc;
+  load_slice<T>(bias, be, h, lg, L);
+#pragma unroll
+  for (int t = 0; t < T; ++t) dbe_acc.v[t] = acc.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int groups = (kFusedThreads / kWarp) * G;
+  const int per = (nE + groups - 1) / groups;
+  const int g0 = (warp * G + grp) * per;
+  int cur_u = -1;
+  int u_n = 0, v_n = 0;
+  if (g0 < nE) {
+    u_n = __ldg(erow + eb0 + g0);
+    v_n = __ldg(col + eb0 + g0);
+  }
+  for (int it = 0; it < per; ++it) {
+    const int idx = g0 + it;
+    const bool valid = idx < nE;
+    const int u = u_n, v = v_n;
+    if (it + 1 < per && idx + 1 < nE) {
+      u_n = __ldg(erow + eb0 + idx + 1);
+      v_n = __ldg(col + eb0 + idx + 1);
+    }
+    const float dr = valid ? sDr[idx] : 0.f;
+    RowSlice<T> yu, yv;
+    load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
+    load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+    const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
+    const float r1s = sigmoidf_(z);
+    const float dz = valid ? dr * r1s * (1.f - r1s) : 0.f;
+    if (valid && u != cur_u) {  // group-uniform branch: flush the finished source row
+      if (cur_u >= 0) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int c = 4 * (lg + L * t);
+          if (c < h) red_add4(dy + (size_t)cur_u * h + c, acc.v[t]);
+          acc.v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      cur_u = u;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int c = 4 * (lg + L * t);
+      float4 d;
+      d.x = dz * leaky_grad(yu.v[t].x - yv.v[t].x + bias.v[t].x);
+      d.y = dz * leaky_grad(yu.v[t].y - yv.v[t].y + bias.v[t].y);
+      d.z = dz * leaky_grad(yu.v[t].z - yv.v[t].z + bias.v[t].z);
+      d.w = dz * leaky_grad(yu.v[t].w - yv.v[t].w + bias.v[t].w);
+      dbe_acc.v[t].x += d.x; dbe_acc.v[t].y += d.y; dbe_acc.v[t].z += d.z; dbe_acc.v[t].w += d.w;
+      if (valid && u != v) {  // a self loop adds +d and -d to the same row: skip both (it still counts for dbe)
+        acc.v[t].x += d.x; acc.v[t].y += d.y; acc.v[t].z += d.z; acc.v[t].w += d.w;
+        if (c < h) red_add4(dy + (size_t)v * h + c, make_float4(-d.x, -d.y, -d.z, -d.w));
+      }
+    }
+  }
+  if (cur_u >= 0) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int c = 4 * (lg + L * t);
+      if (c < h) red_add4(dy + (size_t)cur_u * h + c, acc.v[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    for (int o = L; o < kWarp; o <<= 1) {
+      dbe_acc.v[t].x += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].x, o);
+      dbe_acc.v[t].y += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].y, o);
+      dbe_acc.v[t].z += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].z, o);
+      dbe_acc.v[t].w += __shfl_xor_sync(0xffffffffu, dbe_acc.v[t].w, o);
+    }
+    const int c = 4 * (lg + L * t);
+    if (grp == 0 && c < h) {
+      atomicAdd(&dbe_s[c + 0], dbe_acc.v[t].x);
+      atomicAdd(&dbe_s[c + 1], dbe_acc.v[t].y);
+      atomicAdd(&dbe_s[c + 2], dbe_acc.v[t].z);
+      atomicAdd(&dbe_s[c + 3], dbe_acc.v[t].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < h; c += kFusedThreads) atomicAdd(dbe + c, dbe_s[c]);
+}
+
 // grid of the fused kernels: at most one wave (blocks_per_sm from the occupancy calculator), >= 128 edges per block (measured 256 / 128 / 64: forward 16.8 / 14.1 / 14.1 us at Pubmed shape; DGGB_FUSED_EPB overrides)
 static void fused_grid(int nnz, int blocks_per_sm, int* blocks, int* epb) {
   static const int min_epb = getenv("DGGB_FUSED_EPB") ? atoi(getenv("DGGB_FUSED_EPB")) : 128;
@@ -761,6 +1039,12 @@ static void fused_grid(int nnz, int blocks_per_sm, int* blocks, int* epb) {
   if (b < 1) b = 1;
   *epb = (int)((nnz + b - 1) / b);
   *blocks = (nnz + *epb - 1) / *epb;
+}
+
+// DGGB_FUSED_V1=1: first-generation fused kernels (A/B measurements)
+static bool fused_v1() {
+  static const bool v1 = getenv("DGGB_FUSED_V1") != nullptr;
+  return v1;
 }
 
 static int edges_grid(long long nnz, int blocks_per_sm = 8) {
@@ -878,17 +1162,30 @@ extern "C" int dggb_dgg_edge_fwd_fused(const int32_t* rowptr, const int32_t* ero
                (long long)zero_count);
     return launch_status();
   };
-  if (h == 16 * L) {   // the usual hidden widths: fully specialised kernels
+  if (fused_v1()) {
+    if (h == 16 * L) {   // the usual hidden widths: fully specialised kernels
+      switch (L) {
+        case 1: return go(dgg_fwd_fused_kernel<4, 1>);
+        case 2: return go(dgg_fwd_fused_kernel<4, 2>);
+        case 4: return go(dgg_fwd_fused_kernel<4, 4>);
+        case 8: return go(dgg_fwd_fused_kernel<4, 8>);
+        case 16: return go(dgg_fwd_fused_kernel<4, 16>);
+        default: return go(dgg_fwd_fused_kernel<4, 32>);
+      }
+    }
+    return dispatch_T(h, L, [&](auto tc) { return go(dgg_fwd_fused_kernel<decltype(tc)::value, 0>); });
+  }
+  if (h == 16 * L) {
     switch (L) {
-      case 1: return go(dgg_fwd_fused_kernel<4, 1>);
-      case 2: return go(dgg_fwd_fused_kernel<4, 2>);
-      case 4: return go(dgg_fwd_fused_kernel<4, 4>);
-      case 8: return go(dgg_fwd_fused_kernel<4, 8>);
-      case 16: return go(dgg_fwd_fused_kernel<4, 16>);
-      default: return go(dgg_fwd_fused_kernel<4, 32>);
+      case 1: return go(dgg_fwd_fused2_kernel<4, 1>);
+      case 2: return go(dgg_fwd_fused2_kernel<4, 2>);
+      case 4: return go(dgg_fwd_fused2_kernel<4, 4>);
+      case 8: return go(dgg_fwd_fused2_kernel<4, 8>);
+      case 16: return go(dgg_fwd_fused2_kernel<4, 16>);
+      default: return go(dgg_fwd_fused2_kernel<4, 32>);
     }
   }
-  return dispatch_T(h, L, [&](auto tc) { return go(dgg_fwd_fused_kernel<decltype(tc)::value, 0>); });
+  return dispatch_T(h, L, [&](auto tc) { return go(dgg_fwd_fused2_kernel<decltype(tc)::value, 0>); });
 }
 
 extern "C" int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* erow, const int32_t* col, int32_t n,
@@ -912,6 +1209,37 @@ extern "C" int dggb_dgg_edge_bwd_fused(const int32_t* rowptr, const int32_t* ero
                be, ablation_noise, hard_k, R, rank, s, k, g_out, deg_w, deg_b, ds_ws, dy, dbe, ddeg);
     return launch_status();
   };
+  // second generation: two shared-memory floats per entry of the block's window (epb + max_row_nnz entries); graphs
+  // whose one-wave grid makes that window larger than 48 KB stay on the first generation
+  auto go2 = [&](auto kern, int* fits) {
+    int occ = 0, blocks, epb;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kFusedThreads,
+                                                  (size_t)(128 + max_row_nnz) * 2 * sizeof(float));
+    fused_grid(nnz, occ, &blocks, &epb);
+    const int cap = epb + max_row_nnz;
+    *fits = cap <= 6144;
+    if (!*fits) return (int)DGGB_OK;
+    launch_pdl(kern, dim3(blocks), dim3(kFusedThreads), (size_t)cap * 2 * sizeof(float), as_stream(stream), rowptr,
+               erow, col, n, nnz, h, L, epb, cap, y, be, ablation_noise, hard_k, R, rank, s, k, g_out, deg_w, deg_b,
+               ds_ws, dy, dbe, ddeg);
+    return launch_status();
+  };
+  if (!fused_v1()) {
+    int fits = 0, rc;
+    if (h == 16 * L) {
+      switch (L) {
+        case 1: rc = go2(dgg_bwd_fused2_kernel<4, 1>, &fits); break;
+        case 2: rc = go2(dgg_bwd_fused2_kernel<4, 2>, &fits); break;
+        case 4: rc = go2(dgg_bwd_fused2_kernel<4, 4>, &fits); break;
+        case 8: rc = go2(dgg_bwd_fused2_kernel<4, 8>, &fits); break;
+        case 16: rc = go2(dgg_bwd_fused2_kernel<4, 16>, &fits); break;
+        default: rc = go2(dgg_bwd_fused2_kernel<4, 32>, &fits); break;
+      }
+    } else {
+      rc = dispatch_T(h, L, [&](auto tc) { return go2(dgg_bwd_fused2_kernel<decltype(tc)::value, 0>, &fits); });
+    }
+    if (fits || rc != DGGB_OK) return rc;
+  }
   if (h == 16 * L) {
     switch (L) {
       case 1: return go(dgg_bwd_fused_kernel<4, 1>);

@@ -386,6 +386,9 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         }
       }
       if (colsum != nullptr) {
+        // per-warp column sums -> shared memory -> ONE atomic per column and CTA (every CTA of the grid reaches this
+        // point at about the same time and targets the same H addresses)
+        float* cs = reinterpret_cast<float*>(smem) + (size_t)kLinBM * kPitch;    // [4][H], behind the staging tile
 #pragma unroll
         for (int c0 = 0; c0 < H; c0 += 32) {
           const int c = c0 + lane;
@@ -393,7 +396,18 @@ __global__ void __launch_bounds__(kLinThreads, 1)
             float t = 0.f;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) t += stg[r * kPitch + c];     // rows >= n hold zeros
-            if (t != 0.f) atomicAdd(colsum + c, t);
+            cs[q * H + c] = t;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");                  // the four epilogue warps
+        if (q == 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < H; c0 += 32) {
+            const int c = c0 + lane;
+            if (c < H) {
+              const float t = cs[c] + cs[H + c] + cs[2 * H + c] + cs[3 * H + c];
+              if (t != 0.f) atomicAdd(colsum + c, t);
+            }
           }
         }
       }
