@@ -294,14 +294,16 @@ int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float sl
  *   dggb_encoder_bwd_dpre:  d pre = LeakyReLU'_slope(x_enc) * (g_y We + g_xenc)  (g_xenc may be NULL) in ONE launch.
  *     dpre [N,H] may be NULL when the caller only needs the weight gradients; dpre_t_hi / dpre_t_lo [H, npad]
  *     (npad >= n, npad % 4 == 0; both or neither) receive the TRANSPOSED TF32 hi/lo split of d pre, zero padded, and
- *     colsum[H] (or NULL) += its column sums (the bias gradient): the operands of dggb_gemm_tn_tc_presplit. */
+ *     colsum[H] (or NULL) += its column sums (the bias gradient): the operands of dggb_gemm_tn_tc_presplit.
+ *     gy_t_hi / gy_t_lo [H, npad] (both or neither): the same transposed split of the INPUT g_y, for the
+ *     dWe = g_y^T x_enc product that dggb_gemm_tn_tc_presplit computes in the same launch as dWn = d pre^T x. */
 int dggb_encoder_fwd(const float* x, const float* wn, const float* bn, float slope, int32_t n, int32_t f,
                      int32_t h, float* x_enc, const float* we, float* y, void* workspace,
                      int64_t workspace_bytes, float* we_t_split, float* zero_ws, int64_t zero_count,
                      void* stream);
 int dggb_encoder_bwd_dpre(const float* g_y, const float* we_t_split, const float* g_xenc, const float* x_enc,
                           float slope, int32_t n, int32_t h, float* dpre, float* dpre_t_hi, float* dpre_t_lo,
-                          int32_t npad, float* colsum, void* stream);
+                          int32_t npad, float* colsum, float* gy_t_hi, float* gy_t_lo, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Weight gradients of the tall node encoders (nn.Linear of dgm.py:1741-1744 / 1097-1100 /
@@ -318,9 +320,12 @@ int64_t dggb_gemm_tn_tc_workspace_bytes(int32_t n, int32_t p);
 int dggb_gemm_tn_tc(const float* a, const float* b, int32_t n, int32_t p, int32_t q, float* out,
                     float* colsum_a, void* workspace, int64_t workspace_bytes, void* stream);
 /* Same product from an operand that is already transposed and split (a_t_hi / a_t_lo [P, npad], zero padded for
- * nodes >= n; written by dggb_encoder_bwd_dpre): no transpose pass, no workspace. */
+ * nodes >= n; written by dggb_encoder_bwd_dpre): no transpose pass, no workspace.  a2_t_hi / a2_t_lo / b2 [N, q2] /
+ * out2 [P, q2] (all or none; q2 <= 128): a second, narrow product out2 += a2^T b2 over the same nodes computed by
+ * extra CTAs of the same launch (dWe = g_y^T x_enc next to dWn = d pre^T x). */
 int dggb_gemm_tn_tc_presplit(const float* a_t_hi, const float* a_t_lo, int32_t npad, const float* b, int32_t n,
-                             int32_t p, int32_t q, float* out, void* stream);
+                             int32_t p, int32_t q, float* out, const float* a2_t_hi, const float* a2_t_lo,
+                             const float* b2, int32_t q2, float* out2, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * All-pairs scoring + per-row streaming top-K (legacy all-pairs DGG, dgm.py:271-301; a15):

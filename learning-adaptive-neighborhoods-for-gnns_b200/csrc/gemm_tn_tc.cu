@@ -63,9 +63,19 @@ __global__ void __launch_bounds__(256)
 
 template <int P>
 __global__ void __launch_bounds__(kTcThreads, 2)
-    gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_ahi,
-                          const __grid_constant__ CUtensorMap tm_alo, int n, int q, int kb_per_split,
-                          float* __restrict__ out) {
+    gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_ahi1,
+                          const __grid_constant__ CUtensorMap tm_alo1, int n, int q1, int kb_per_split,
+                          float* __restrict__ out1, int m_tiles1, const __grid_constant__ CUtensorMap tm_b2,
+                          const __grid_constant__ CUtensorMap tm_ahi2, const __grid_constant__ CUtensorMap tm_alo2,
+                          int q2, float* __restrict__ out2) {
+  // CTAs with blockIdx.x >= m_tiles1 work on the second (narrow) product of the same launch: other operands, same
+  // node split
+  const bool second = (int)blockIdx.x >= m_tiles1;
+  const CUtensorMap& tm_b = second ? tm_b2 : tm_b1;
+  const CUtensorMap& tm_ahi = second ? tm_ahi2 : tm_ahi1;
+  const CUtensorMap& tm_alo = second ? tm_alo2 : tm_alo1;
+  const int q = second ? q2 : q1;
+  float* __restrict__ out = second ? out2 : out1;
   constexpr uint32_t kXBytes = 4 * 32 * 128;       // four [32 nodes][32 feats] boxes = 128 features x 32 nodes
   constexpr uint32_t kWBytes = P * 128;            // a^T hi (or lo): [P rows][32 nodes]
   constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTcM;                              // first feature of this CTA
+  const int m0 = (second ? (int)blockIdx.x - m_tiles1 : (int)blockIdx.x) * kTcM;   // first feature of this CTA
   const int kb_begin = blockIdx.y * kb_per_split;
   const int kb_total = (n + 31) / 32;
   const int num_kb = max(0, min(kb_per_split, kb_total - kb_begin));
@@ -217,17 +227,37 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 }
 
 // a_hi / a_lo: a^T split, [P, npad] (npad % 4 == 0, zero padded beyond n)
+struct TnSecond {     // optional second product of the launch (see the kernel)
+  const float* a_hi = nullptr;
+  const float* a_lo = nullptr;
+  const float* b = nullptr;
+  int q = 0;
+  float* out = nullptr;
+};
+
 template <int P>
 static int launch_tn_gemm(const float* a_hi, const float* a_lo, int npad, const float* b, int n, int q, float* out,
-                          cudaStream_t st) {
-  CUtensorMap tm_b, tm_ahi, tm_alo;
+                          cudaStream_t st, const TnSecond& s2 = TnSecond()) {
+  CUtensorMap tm_b, tm_ahi, tm_alo, tm_b2, tm_ahi2, tm_alo2;
   int rc = make_tmap_2d_f32(&tm_b, b, (uint64_t)n, (uint64_t)q, 32, 32);
   if (rc != DGGB_OK) return rc;
   rc = make_tmap_2d_f32(&tm_ahi, a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
   if (rc != DGGB_OK) return rc;
   rc = make_tmap_2d_f32(&tm_alo, a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
   if (rc != DGGB_OK) return rc;
-  const int m_tiles = (q + kTcM - 1) / kTcM;
+  tm_b2 = tm_b, tm_ahi2 = tm_ahi, tm_alo2 = tm_alo;
+  int m_tiles2 = 0;
+  if (s2.b != nullptr) {
+    rc = make_tmap_2d_f32(&tm_b2, s2.b, (uint64_t)n, (uint64_t)s2.q, 32, 32);
+    if (rc != DGGB_OK) return rc;
+    rc = make_tmap_2d_f32(&tm_ahi2, s2.a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
+    if (rc != DGGB_OK) return rc;
+    rc = make_tmap_2d_f32(&tm_alo2, s2.a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
+    if (rc != DGGB_OK) return rc;
+    m_tiles2 = (s2.q + kTcM - 1) / kTcM;
+  }
+  const int m_tiles1 = (q + kTcM - 1) / kTcM;
+  const int m_tiles = m_tiles1 + m_tiles2;
   const int kb_total = (n + 31) / 32;
   int splits = (2 * kNumSMs + m_tiles - 1) / m_tiles;
   if (splits > kb_total) splits = kb_total;
@@ -237,7 +267,7 @@ static int launch_tn_gemm(const float* a_hi, const float* a_lo, int npad, const 
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
   launch_pdl(gemm_tn_tf32x3_kernel<P>, dim3(m_tiles, splits), dim3(kTcThreads), smem, st, tm_b, tm_ahi, tm_alo, n, q,
-             kb_per_split, out);
+             kb_per_split, out, m_tiles1, tm_b2, tm_ahi2, tm_alo2, s2.q, s2.out);
   return launch_status();
 }
 
@@ -281,17 +311,25 @@ extern "C" int dggb_gemm_tn_tc(const float* a, const float* b, int32_t n, int32_
 // out[P,Q] += a^T b with a^T already split (a_t_hi / a_t_lo [P, npad], zero padded for nodes >= n): the operand
 // dggb_encoder_bwd_dpre leaves behind -- no transpose pass
 extern "C" int dggb_gemm_tn_tc_presplit(const float* a_t_hi, const float* a_t_lo, int32_t npad, const float* b,
-                                        int32_t n, int32_t p, int32_t q, float* out, void* stream) {
+                                        int32_t n, int32_t p, int32_t q, float* out, const float* a2_t_hi,
+                                        const float* a2_t_lo, const float* b2, int32_t q2, float* out2,
+                                        void* stream) {
   if (!a_t_hi || !a_t_lo || !b || !out || n < 0 || p <= 0 || q <= 0 || npad < n) return DGGB_ERR_BAD_ARG;
+  const int n2 = (a2_t_hi != nullptr) + (a2_t_lo != nullptr) + (b2 != nullptr) + (out2 != nullptr);
+  if (n2 != 0 && n2 != 4) return DGGB_ERR_BAD_ARG;
   if (q % 4 != 0 || npad % 4 != 0 || ((uintptr_t)b % 16) || ((uintptr_t)a_t_hi % 16) || ((uintptr_t)a_t_lo % 16))
+    return DGGB_ERR_BAD_SHAPE;
+  if (n2 && (q2 <= 0 || q2 % 4 != 0 || ((uintptr_t)b2 % 16) || ((uintptr_t)a2_t_hi % 16) || ((uintptr_t)a2_t_lo % 16)))
     return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
   cudaStream_t st = as_stream(stream);
+  TnSecond s2;
+  if (n2) s2.a_hi = a2_t_hi, s2.a_lo = a2_t_lo, s2.b = b2, s2.q = q2, s2.out = out2;
   switch (p) {
-    case 16: return launch_tn_gemm<16>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
-    case 32: return launch_tn_gemm<32>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
-    case 64: return launch_tn_gemm<64>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
-    case 128: return launch_tn_gemm<128>(a_t_hi, a_t_lo, npad, b, n, q, out, st);
+    case 16: return launch_tn_gemm<16>(a_t_hi, a_t_lo, npad, b, n, q, out, st, s2);
+    case 32: return launch_tn_gemm<32>(a_t_hi, a_t_lo, npad, b, n, q, out, st, s2);
+    case 64: return launch_tn_gemm<64>(a_t_hi, a_t_lo, npad, b, n, q, out, st, s2);
+    case 128: return launch_tn_gemm<128>(a_t_hi, a_t_lo, npad, b, n, q, out, st, s2);
     default: return DGGB_ERR_BAD_SHAPE;
   }
 }

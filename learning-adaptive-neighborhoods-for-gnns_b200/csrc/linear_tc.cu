@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                          const float* __restrict__ bias, const float* __restrict__ addend,
                          const float* __restrict__ act_src, float slope, int n, int f, float* __restrict__ out,
                          float* __restrict__ out2, int wait_first, float* __restrict__ outT_hi,
-                         float* __restrict__ outT_lo, int npad, float* __restrict__ colsum) {
+                         float* __restrict__ outT_lo, int npad, float* __restrict__ colsum,
+                         float* __restrict__ xT_hi, float* __restrict__ xT_lo) {
   static_assert(!FUSE2 || H == 32 || H == 64, "fused second GEMM: K = H must be one or two 32-float k-blocks");
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
@@ -288,6 +289,28 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
         lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
       }
+      if (xT_hi != nullptr) {
+        // transposed TF32 split of the INPUT tile, xT[col][node] ([F, npad]): the d pre launch leaves g_y^T behind for
+        // the dWe = g_y^T x_enc product that rides along in the weight-gradient GEMM launch.  hi = trunc_tf32(x)
+        // (what the tensor core sees of the raw tile), lo = x - hi; lane == row: coalesced 128-byte stores.
+        const int node = row0 + r_in_tile;
+        if (node < npad) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (r_in_tile & 7)) << 4));
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int colx = kb * 32 + 4 * c + j;
+              if (colx < f) {
+                const size_t o = (size_t)colx * npad + node;
+                xT_hi[o] = __uint_as_float(__float_as_uint(vv[j]) & 0xffffe000u);
+                xT_lo[o] = __uint_as_float(lo[4 * c + j]);
+              }
+            }
+          }
+        }
+      }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(x_empty + xs);        // tile is in registers (the hi MMAs release it as well)
       tc::mbar_wait(a_empty + ab, ((kb / kAB) & 1) ^ 1);   // previous MMAs on this lo buffer retired
@@ -468,6 +491,8 @@ struct LinearExtra {
   float* outT_lo = nullptr;
   int npad = 0;
   float* colsum = nullptr;
+  float* xT_hi = nullptr;       // out, [F, npad]: transposed TF32 split of x (see the converter loop)
+  float* xT_lo = nullptr;
 };
 
 template <int H>
@@ -504,7 +529,7 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   const int grid = (n + kLinBM - 1) / kLinBM;
   if constexpr (H == 32 || H == 64) {
     if (w2 != nullptr) {
-      if (ex.w_presplit || ex.outT_hi) return DGGB_ERR_BAD_ARG;
+      if (ex.w_presplit || ex.outT_hi || ex.xT_hi) return DGGB_ERR_BAD_ARG;
       rc = make_tmap_2d_f32(&tm_w2hi, w2_hi, (uint64_t)H, (uint64_t)H, H, 32);
       if (rc != DGGB_OK) return rc;
       rc = make_tmap_2d_f32(&tm_w2lo, w2_lo, (uint64_t)H, (uint64_t)H, H, 32);
@@ -514,7 +539,8 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
       if (e != cudaSuccess) return cuda_status(e);
       launch_pdl((linear_tf32x3_kernel<H, XS, WS, true>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w,
                  tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2, 0, static_cast<float*>(nullptr),
-                 static_cast<float*>(nullptr), 0, static_cast<float*>(nullptr));
+                 static_cast<float*>(nullptr), 0, static_cast<float*>(nullptr), static_cast<float*>(nullptr),
+                 static_cast<float*>(nullptr));
       return launch_status();
     }
   }
@@ -524,7 +550,7 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   if (e != cudaSuccess) return cuda_status(e);
   launch_pdl((linear_tf32x3_kernel<H, XS, WS, false>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w, tm_w, tm_w,
              b, addend, act_src, slope, n, f, out, static_cast<float*>(nullptr), wait_first, ex.outT_hi, ex.outT_lo,
-             ex.npad, ex.colsum);
+             ex.npad, ex.colsum, ex.xT_hi, ex.xT_lo);
   return launch_status();
 }
 
@@ -598,12 +624,13 @@ extern "C" int dggb_encoder_fwd(const float* x, const float* wn, const float* bn
 // also leaves as the transposed TF32 split + column sums that dggb_gemm_tn_tc_presplit consumes
 extern "C" int dggb_encoder_bwd_dpre(const float* g_y, const float* we_t_split, const float* g_xenc,
                                      const float* x_enc, float slope, int32_t n, int32_t h, float* dpre,
-                                     float* dpre_t_hi, float* dpre_t_lo, int32_t npad, float* colsum, void* stream) {
+                                     float* dpre_t_hi, float* dpre_t_lo, int32_t npad, float* colsum,
+                                     float* gy_t_hi, float* gy_t_lo, void* stream) {
   if (!g_y || !we_t_split || !x_enc || n < 0 || (dpre_t_hi == nullptr) != (dpre_t_lo == nullptr) ||
-      (!dpre && !dpre_t_hi))
+      (gy_t_hi == nullptr) != (gy_t_lo == nullptr) || (!dpre && !dpre_t_hi))
     return DGGB_ERR_BAD_ARG;
   if (h != 16 && h != 32 && h != 64 && h != 128) return DGGB_ERR_BAD_SHAPE;
-  if (dpre_t_hi && (npad < n || npad % 4 != 0)) return DGGB_ERR_BAD_ARG;
+  if ((dpre_t_hi || gy_t_hi) && (npad < n || npad % 4 != 0)) return DGGB_ERR_BAD_ARG;
   if (misaligned(g_y) || misaligned(we_t_split) || misaligned(g_xenc) || misaligned(x_enc) || misaligned(dpre))
     return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
@@ -613,6 +640,8 @@ extern "C" int dggb_encoder_bwd_dpre(const float* g_y, const float* we_t_split, 
   ex.outT_lo = dpre_t_lo;
   ex.npad = npad;
   ex.colsum = colsum;
+  ex.xT_hi = gy_t_hi;
+  ex.xT_lo = gy_t_lo;
   return dispatch_linear(h, g_y, we_t_split, 0, static_cast<const float*>(nullptr), g_xenc, x_enc, slope, (int)n,
                          (int)h, dpre, static_cast<float*>(nullptr), static_cast<const float*>(nullptr),
                          static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0LL, as_stream(stream), ex);

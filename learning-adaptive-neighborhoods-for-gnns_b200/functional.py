@@ -539,26 +539,14 @@ def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None
     return out if w2 is None else (out, out2)
 
 
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    """One extra stream per device for the independent branch of the encoder backward (dWe next to d pre -> dWn);
-    inside a CUDA-graph capture the fork / join become parallel branches of the graph."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    st = _SIDE_STREAMS.get(key)
-    if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
-    return st
-
-
 class _EncodeProject(torch.autograd.Function):
     """(x_enc, y) = (LeakyReLU(x Wn^T + bn), x_enc We^T): the node encoder and the edge-encoder projection of
     ``DGG`` (dgm.py:1778, 1784) as ONE autograd node.  Forward: two launches (weight split, GEMM with the chained
     second GEMM); the split launch also leaves the pre-split We^T and the cleared accumulators for the backward, which
-    is then three launches and no fills:
-        dpre = LeakyReLU'(x_enc) * (g_y We + g_xenc), leaving as a transposed TF32 split + column sums (= dbn)
-        dWn  = dpre^T x   (dggb_gemm_tn_tc_presplit)         |  on a second stream:  dWe = g_y^T x_enc"""
+    is then TWO launches and no fills:
+        dpre = LeakyReLU'(x_enc) * (g_y We + g_xenc), leaving as a transposed TF32 split + column sums (= dbn), next
+               to the same split of its input g_y
+        dWn  = dpre^T x  and  dWe = g_y^T x_enc  in one tensor-core launch (dggb_gemm_tn_tc_presplit)"""
 
     @staticmethod
     def forward(ctx, x, wn, bn, we, slope: float):
@@ -610,19 +598,14 @@ class _EncodeProject(torch.autograd.Function):
             npad = (n + 31) // 32 * 32
             want_dx = ctx.needs_input_grad[0]
             dpre = torch.empty(n, h, dtype=torch.float32, device=dev) if want_dx else None
-            dpt = torch.empty(2, h, npad, dtype=torch.float32, device=dev)
-            main = torch.cuda.current_stream(dev)
-            side = _side_stream(dev)
-            side.wait_stream(main)                                  # fork: g_y and the cleared accumulators are ready
-            with torch.cuda.stream(side):
-                check(lib().dggb_gemm_tn_splitk(p(g_y), p(x_enc), i32(n), i32(h), i32(h), p(dwe), None, stream()),
-                      "gemm_tn_splitk")
+            tsp = torch.empty(4, h, npad, dtype=torch.float32, device=dev)   # dpre^T hi | lo | g_y^T hi | lo
             check(lib().dggb_encoder_bwd_dpre(p(g_y), p(ctx.wet), p(g_xenc), p(x_enc), float(ctx.slope), i32(n), i32(h),
-                                              p(dpre), p(dpt[0]), p(dpt[1]), i32(npad), p(dbn), stream()),
-                  "encoder_bwd_dpre")
-            check(lib().dggb_gemm_tn_tc_presplit(p(dpt[0]), p(dpt[1]), i32(npad), p(x), i32(n), i32(h), i32(f_in),
-                                                 p(dwn), stream()), "gemm_tn_tc_presplit")
-            main.wait_stream(side)                                  # join
+                                              p(dpre), p(tsp[0]), p(tsp[1]), i32(npad), p(dbn), p(tsp[2]), p(tsp[3]),
+                                              stream()), "encoder_bwd_dpre")
+            # dWn = dpre^T x and, from extra CTAs of the same launch, dWe = g_y^T x_enc
+            check(lib().dggb_gemm_tn_tc_presplit(p(tsp[0]), p(tsp[1]), i32(npad), p(x), i32(n), i32(h), i32(f_in),
+                                                 p(dwn), p(tsp[2]), p(tsp[3]), p(x_enc), i32(h), p(dwe), stream()),
+                  "gemm_tn_tc_presplit")
             dx = dpre @ wn if want_dx else None
             return dx, dwn, dbn, dwe, None
         # split-K accumulators of both weight-gradient GEMMs: cleared by the dpre launch (its weight-split kernel)
