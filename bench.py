@@ -917,25 +917,57 @@ def kernel_roofline(m, dsets, shape, iters=30):
     ws_tn_bytes = int(L.dggb_gemm_tn_tc_workspace_bytes(i32(n), i32(h)))
     ws_tn = torch.empty(ws_tn_bytes // 4, device=dev)
 
-    def lin(i):
+    # what one training step launches for the encoder (functional._EncodeProject): forward = weight split + GEMM with
+    # the chained y = x_enc We^T; backward = d pre (leaving its transposed TF32 split and g_y's) + ONE weight-gradient
+    # launch (dWn = dpre^T x, dWe = g_y^T x_enc)
+    we = lin.weight.detach().contiguous()
+    y_out = torch.empty(n, h, device=dev)
+    wet = torch.empty(2 * h * h, device=dev)
+    zb = torch.zeros(h * h + h * f_in + h, device=dev)
+    npad = (n + 31) // 32 * 32
+    tsp = torch.zeros(4, h, npad, device=dev)
+    g_y, g_xe, x_enc_s = torch.randn(n, h, device=dev), torch.randn(n, h, device=dev), torch.randn(n, h, device=dev)
+
+    def lin_plain(i):
         check(L.dggb_linear_act_fwd(p(xs[i % N_SETS]), p(w_enc), p(b_enc), ctypes.c_float(0.01), i32(n), i32(f_in),
                                     i32(h), p(x_out), p(ws_lin), ctypes.c_int64(ws_lin.numel() * 4), stream()), "lin")
 
-    def tn(i):
-        check(L.dggb_gemm_tn_tc(p(dpre), p(xs[i % N_SETS]), i32(n), i32(h), i32(f_in), p(dw_out[:h * f_in]),
-                                p(dw_out[h * f_in:]), p(ws_tn), ctypes.c_int64(ws_tn_bytes), stream()), "tn")
+    def enc_fwd(i):
+        check(L.dggb_encoder_fwd(p(xs[i % N_SETS]), p(w_enc), p(b_enc), ctypes.c_float(0.01), i32(n), i32(f_in), i32(h),
+                                 p(x_out), p(we), p(y_out), p(ws_lin), ctypes.c_int64(ws_lin.numel() * 4), p(wet),
+                                 p(zb), ctypes.c_int64(zb.numel()), stream()), "encoder_fwd")
 
-    t_lin = timed(lin)
+    def enc_dpre(i):
+        check(L.dggb_encoder_bwd_dpre(p(g_y), p(wet), p(g_xe), p(x_enc_s), ctypes.c_float(0.01), i32(n), i32(h), p(None),
+                                      p(tsp[0]), p(tsp[1]), i32(npad), p(zb[h * h + h * f_in:]), p(tsp[2]), p(tsp[3]),
+                                      stream()), "encoder_bwd_dpre")
+
+    def tn(i):
+        check(L.dggb_gemm_tn_tc_presplit(p(tsp[0]), p(tsp[1]), i32(npad), p(xs[i % N_SETS]), i32(n), i32(h), i32(f_in),
+                                         p(zb[h * h:h * h + h * f_in]), p(tsp[2]), p(tsp[3]), p(x_enc_s), i32(h),
+                                         p(zb[:h * h]), stream()), "gemm_tn_tc_presplit")
+
+    enc_fwd(0)          # leaves the pre-split We^T the d pre launch reads
+    t_lin = timed(lin_plain)
+    t_enc = timed(enc_fwd)
+    t_dpre = timed(enc_dpre)
     t_tn = timed(tn)
     # algorithmic bytes (int32 CSR, fp32)
     b_fwd = E * (4 + 4 * h) + n * (4 * h + 12) + E * 12
     b_bwd = E * (4 + 4 * h + 12) + E * 4 * h + n * (4 * h * 2 + 12)
     b_lin = n * f_in * 4 + n * h * 4 + h * f_in * 4
-    b_tn = n * f_in * 4 + n * h * 4 + h * f_in * 4
-    cands = [("linear_tf32x3_kernel (+ split_w)", t_lin, b_lin),
-             ("gemm_tn_tf32x3_kernel (+ transpose_split)", t_tn, b_tn),
-             ("dgg_fwd_fused_kernel" if fused else "dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd),
-             ("dgg_bwd_fused_kernel" if fused else "dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd)]
+    b_enc = n * f_in * 4 + 2 * n * h * 4 + h * f_in * 4 + h * h * 4
+    b_dpre = 3 * n * h * 4 + 4 * h * npad * 4
+    b_tn = n * f_in * 4 + n * h * 4 + 4 * h * npad * 4 + h * f_in * 4
+    v2 = not os.environ.get("DGGB_FUSED_V1")
+    cands = [("linear_tf32x3_kernel<chained y> (+ split_w): encoder forward, x_enc and y", t_enc, b_enc),
+             ("gemm_tn_tf32x3_kernel: dWn = dpre^T x and dWe = g_y^T x_enc in one launch", t_tn, b_tn),
+             ("linear_tf32x3_kernel: d pre + transposed TF32 splits of d pre and g_y + bias gradient", t_dpre, b_dpre),
+             (("dgg_fwd_fused2_kernel" if v2 else "dgg_fwd_fused_kernel") if fused
+              else "dgg_edge_score_kernel + dgg_row_rank_kernel", t_fwd, b_fwd),
+             (("dgg_bwd_fused2_kernel" if v2 else "dgg_bwd_fused_kernel") if fused
+              else "dgg_row_dk_kernel + dgg_edge_grad_kernel", t_bwd, b_bwd),
+             ("linear_tf32x3_kernel (+ split_w): plain node encoder, as in r01", t_lin, b_lin)]
     name, t, b = max(cands, key=lambda c: c[1])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -947,7 +979,7 @@ def kernel_roofline(m, dsets, shape, iters=30):
     # algorithmic bytes above, the fraction against the COMPULSORY bytes (every array touched once)
     comp_fwd = E * 8 + n * h * 4 + E * 12 + n * 12
     comp_bwd = E * 8 + n * h * 4 + E * 16 + n * h * 4 + n * 12
-    for key, tt, cb in ((cands[2][0], t_fwd, comp_fwd), (cands[3][0], t_bwd, comp_bwd)):
+    for key, tt, cb in ((cands[3][0], t_fwd, comp_fwd), (cands[4][0], t_bwd, comp_bwd)):
         others[key].update(compulsory_bytes=int(cb), frac_compulsory=cb / tt / 1e9 / peak)
 
     # ---- selection and aggregation kernels the conv layers / DGG_LearnableK_debug / GAT use (north_star: "achieved HBM

@@ -9,7 +9,7 @@ from dgg_b200._lib import lib
 n, f, h = 19717, 500, 64
 xs = [torch.rand(n, f, device="cuda") for _ in range(6)]
 wn = torch.randn(h, f, device="cuda") / 20; b = torch.randn(h, device="cuda"); we = torch.randn(h, h, device="cuda") / 8
-for fuse in (False,):
+for fuse in (False, True):
     for i in range(6):
         if fuse: K._linear_act_tc(xs[i], wn, b, 0.01, w2=we)
         else: K._linear_act_tc(xs[i], wn, b, 0.01)
