@@ -395,6 +395,27 @@ int dggb_allreduce_oneshot(void* const* bufs_dev, void* const* pads_dev, int32_t
                            int32_t blocks, int32_t end_barrier /* 0: the caller alternates two buffers */,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Sub-graph sampling on the device: what torch_geometric.loader.GraphSAINTRandomWalkSampler does
+ * for train_large_graphs.py:402-413 / train_reddit.py:400-411 (third-party, not in the reference tree: semantics of
+ * torch_sparse random_walk + saint_subgraph restated; parity unpinned).
+ *   dggb_random_walk: walk[w][0] = start[w]; step s moves to entry floor(u * deg) of the current row's CSR range,
+ *     u = (x >> 8) / 2^24 with x = 32-bit lane (s & 3) of Philox4x32-7(counter = (walker_offset + w, s >> 2), key = seed);
+ *     a node without out-edges keeps the walker in place.  walk is [num_walkers, walk_length + 1] int32.
+ *   dggb_induced_subgraph_count / _fill: the sub-graph induced by the SORTED, unique node list nodes[m]:
+ *     count fills relabel[n] (position in nodes, or -1) and counts[m + 1] (kept entries per selected row, counts[m] = 0);
+ *     the caller scans counts into sub_rowptr[m + 1]; fill writes the kept entries in row-major order:
+ *     sub_col (relabelled column) and sub_eid (position of the entry in the parent CSR).
+ * ---------------------------------------------------------------------------------- */
+int dggb_random_walk(const int32_t* rowptr, const int32_t* col, int32_t n, const int32_t* start,
+                     int32_t num_walkers, int32_t walk_length, uint64_t seed, int64_t walker_offset, int32_t* walk,
+                     void* stream);
+int dggb_induced_subgraph_count(const int32_t* rowptr, const int32_t* col, int32_t n, const int32_t* nodes, int32_t m,
+                                int32_t* relabel, int32_t* counts, void* stream);
+int dggb_induced_subgraph_fill(const int32_t* rowptr, const int32_t* col, const int32_t* nodes, int32_t m,
+                               const int32_t* relabel, const int32_t* sub_rowptr, int32_t* sub_col, int32_t* sub_eid,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,5 +11,6 @@ from . import sharding  # noqa: F401
 from .graphed import GraphedStep  # noqa: F401
 from . import checkpoint  # noqa: F401
 from . import losses  # noqa: F401
+from . import samplers  # noqa: F401
 
 __all__ = ["CSRGraph", "functional", "sharding", "GraphedStep", "lib", "build", "DggbError", "declared_symbols"]

@@ -14,6 +14,7 @@
 // (+ TMEM owner), w2..w5 epilogue.
 #include "common.cuh"
 #include "tc05.cuh"
+#include "philox.cuh"
 #include <climits>
 #include <cstdlib>
 
@@ -89,19 +90,6 @@ __global__ void __launch_bounds__(256)
 // noise tensor in HBM) and a host implementation can materialise the same matrix for small N
 // (tests/philox_ref.py).  v = ((x >> 8) + 0.5) * 2^-24 in (0,1);  g = -scale * log(-log1p(-v)).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
-  uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
-#pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-    const uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
-    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return make_uint4(x0, x1, x2, x3);
-}
 // sqrt.approx (MUFU, <= 2 ulp, no slow-path call): the distance already carries ~1e-6 of GEMM rounding
 __device__ __forceinline__ float sqrt_fast(float x) {
   float r;

@@ -22,6 +22,11 @@ import os as _os
 
 _NO_FUSED_CONV = bool(_os.environ.get("DGGB_NO_FUSED_CONV"))
 _NO_EDGE_SPMM = bool(_os.environ.get("DGGB_NO_EDGE_SPMM"))
+# The one-launch conv layer (SpMM + W in shared memory + epilogue) pays off where the step is launch-bound: Cora /
+# Citeseer sized graphs (GCNII-64 Citeseer train step 5.24 vs 5.38 ms, Cora GCN_DGG 0.551 vs 0.553).  At Pubmed size
+# its SIMT dense part (N x 64 x 64 FMAs next to the gathers) loses to the entry-parallel SpMM + a library GEMM:
+# GCN_DGG_00 train step 0.337 vs 0.308 ms (scripts/model_ab.py, DGGB_NO_FUSED_CONV A/B).
+_FUSED_CONV_MAX_N = int(_os.environ.get("DGGB_FUSED_CONV_MAX_N", "8192"))
 _FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu
 _LONG_ROW = 1024       # kRankCap of csrc/dgg_edge.cu: longer rows are ranked by a grid-wide launch
 
@@ -234,6 +239,8 @@ def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2
     if not (x.is_cuda and fin % 4 == 0 and fin <= 128 and fout <= 128 and (beta == 0.0 or fin == fout)):
         return None
     if _NO_FUSED_CONV:      # A/B measurements: DGGB_NO_FUSED_CONV=1 selects SpMM + library GEMM + elementwise ops
+        return None
+    if graph.n >= _FUSED_CONV_MAX_N:
         return None
     return _SpmmGemm.apply(vals, x, w, h0, resid, graph, row_scale, float(c1), float(c2), float(theta), float(beta),
                            bool(relu))
@@ -641,6 +648,12 @@ def gemm_tn(a, b, want_colsum=False, use_tc=None, zeroed=None):
         # padding N x q to N x 4 costs one small copy, the scalar staging path costs 3x the whole GEMM
         out, cs = gemm_tn(a, torch.nn.functional.pad(b, (0, 4 - q % 4)), want_colsum, use_tc)
         return out[:, :q].contiguous(), cs
+    if pp % 4 != 0 and pp < 64 and q % 4 == 0 and zeroed is None:
+        # narrow LEFT operand (dW of a narrowing layer, e.g. 64 -> 3 class logits: a = d logits [N, 3]): the transposed
+        # product b^T a has the narrow operand on the right, where padding it to 4 columns keeps the 16-byte staging
+        # path (measured at Pubmed shape: 20.7 us on the scalar path)
+        out_t, _ = gemm_tn(b, torch.nn.functional.pad(a, (0, 4 - pp % 4)), False, use_tc)
+        return out_t[:, :pp].t().contiguous(), (a.sum(0) if want_colsum else None)
     need = pp * q + (pp if want_colsum else 0)
     buf = zeroed if zeroed is not None else torch.zeros(need, dtype=torch.float32, device=a.device)
     assert buf.numel() == need
