@@ -806,16 +806,28 @@ def config_epochs(dev, pubmed_sets):
             a_ = torch.sparse_coo_tensor(nl, torch.ones(nl.shape[1], device=dev), (n, n)).coalesce()
             sets.append((s_["x"], a_, nl))
 
-        def gat_step(i):
+        def gat_step(i, o=None):
+            o = opt if o is None else o
             xg, ag, eg = sets[i % len(sets)]
             net.train()
-            opt.zero_grad(set_to_none=True)
+            o.zero_grad(set_to_none=True)
             logp, _, _ = net(xg, ag, edge_index=eg)
-            F.nll_loss(logp[ti], labels[ti]).backward()
-            opt.step()
+            loss = F.nll_loss(logp[ti], labels[ti])
+            loss.backward()
+            o.step()
+            return loss
 
+        eager_ms = _step_timer(gat_step, iters=10)
+        graph_ms, graph_err = None, None
+        try:      # one captured step per resident input set (two sets: the 9-head step holds ~0.3 GB of activations)
+            opt_g = torch.optim.Adam(net.parameters(), lr=0.005, weight_decay=5e-4, capturable=True, fused=True)
+            gsteps = [dgg_b200.GraphedStep(lambda j=j: gat_step(j, opt_g)) for j in range(2)]
+            graph_ms = _step_timer(lambda i: gsteps[i % 2](), iters=20)
+        except Exception as e:
+            graph_err = repr(e)[:200]
         out.append(dict(model="GAT_DGG_00", shape="pubmed", n=n, f=shape["f"], heads="8 + 1",
-                        train_step_ms=_step_timer(gat_step, iters=10),
+                        train_step_ms=eager_ms, train_step_graph_ms=graph_ms,
+                        **({"train_step_graph_error": graph_err} if graph_err else {}),
                         reference_cpu="not runnable: 9 heads x dense [N, N] fp32 attention = 1.55 GB each, ~40 GB live in "
                                       "the backward (SURVEY 3.3)"))
     except Exception as e:
@@ -848,20 +860,31 @@ def kernel_roofline(m, dsets, shape, iters=30):
     n, h = shape["n"], shape["h"]
     E = prepared[0][0].nnz
 
-    def timed(fn):
-        t_end = time.perf_counter() + 0.05      # >= 50 ms of back-to-back launches first: the clocks have
-        i = 0                                   # dropped while the host was busy, let them ramp up again
-        while time.perf_counter() < t_end or i < 20:
-            fn(i)
-            i += 1
+    def timed(fn, reps=24):
+        """Average duration of one call of fn: `reps` calls (rotating input sets) captured into ONE CUDA graph and
+        replayed back to back, CUDA events around the replays -- the same launch mechanism as the timed step (an eager
+        loop of 10-20 us kernels measures the host's launch rate instead)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(N_SETS):
+                fn(i)
+        torch.cuda.current_stream().wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for i in range(reps):
+                fn(i)
+        t_end = time.perf_counter() + 0.05      # >= 50 ms of replays first: the clocks have dropped while the host
+        while time.perf_counter() < t_end:      # was busy, let them ramp up again
+            gr.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            fn(i)
+        for _ in range(iters):
+            gr.replay()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters * 1e-3
+        return e0.elapsed_time(e1) / (iters * reps) * 1e-3
 
     from dgg_b200._lib import check, i32, lib, p, stream
 

@@ -273,6 +273,19 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     const int q = warp & 3;
     const int r_in_tile = q * 32 + lane;          // == TMEM lane this thread may access
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    if (addend != nullptr || act_src != nullptr) {
+      // the epilogue's operand rows: start them towards L2 now (after the dependency wait: they may come from the
+      // preceding kernel), the k-loop hides the HBM latency
+      pdl_wait();
+      const int prow = row0 + r_in_tile;
+      if (prow < n) {
+#pragma unroll
+        for (int c = 0; c < H * 4; c += 128) {
+          if (addend != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(addend + (size_t)prow * H) + c));
+          if (act_src != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(act_src + (size_t)prow * H) + c));
+        }
+      }
+    }
     for (int kb = 0; kb < num_kb; ++kb) {
       const int ab = kb % kAB, xs = kb % XS;
       tc::mbar_wait(x_full + xs, (kb / XS) & 1);
@@ -355,7 +368,10 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     constexpr int kLanesPerRow = H / 4, kRowsPerIt = 32 / kLanesPerRow, kIters = 32 / kRowsPerIt;
     const int er = lane / kLanesPerRow, ec = (lane % kLanesPerRow) * 4;
     const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + ec)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    constexpr int kBatch = kIters < 4 ? kIters : 4;   // global loads of a batch are issued before they are used
+    // global loads of a batch are issued before they are used: the backward form reads two [128, H] tiles (addend,
+    // act_src) here, four batches of four were four exposed memory round trips (~1 us each) per CTA
+    constexpr int kBatchMax = FUSE2 ? 4 : 8;
+    constexpr int kBatch = kIters < kBatchMax ? kIters : kBatchMax;
     for (int it0 = 0; it0 < kIters; it0 += kBatch) {
       float4 ad[kBatch], ac[kBatch];
 #pragma unroll
