@@ -244,10 +244,12 @@ int dggb_spmm_edge_bwd(const int32_t* erow, const int32_t* col, const float* val
  * direction instead of SpMM + axpby + library GEMM + axpby + add + relu:
  *     s_i = c1 * rs_i * sum_e a_e x[col_e] + c2 * h0_i ;   y_i = act(theta * (s_i W) + beta * s_i + resid_i)
  * W [Fin, Fout] row-major (held in shared memory); h0 / resid / row_scale / s_out may be NULL; relu != 0: act = ReLU.
- * Fin % 4 == 0, Fin <= 128, Fout <= 128; beta != 0 requires Fout == Fin.  s_out [N, Fin] is what the weight gradient
- * dW = theta * s^T dY needs (dggb_gemm_tn_splitk).
- * bwd (gy = dL/dy already masked by the ReLU): ds_i = theta * (gy_i W^T) + beta * gy_i  -> ds_out [N, Fin] (d h0 =
- * c2 * ds), dval_e = rs_i c1 <ds_i, x_col> (OVERWRITTEN; NULL: skipped), dx_col += a_e rs_i c1 ds_i (ACCUMULATED).
+ * Fin % 4 == 0, Fin <= 128, Fout <= 128; beta != 0 requires Fout == Fin.  s_out [N, Fin] receives theta * s: what the
+ * weight gradient dW = (theta s)^T dY needs (dggb_gemm_tn_splitk).
+ * bwd (gy = dL/dy already masked by the ReLU): ds_i = theta * (gy_i W^T) + beta * gy_i  -> ds_out [N, Fin] =
+ * ds_scale * ds (d h0 = c2 * ds: pass ds_scale = c2), dval_e = rs_i c1 <ds_i, x_col> (OVERWRITTEN; NULL: skipped),
+ * dx_col += a_e rs_i c1 ds_i (ACCUMULATED).  zero_ws / zero_count: optional fp32 buffer cleared by this launch (the
+ * split-K accumulator of the weight gradient that follows).
  * ---------------------------------------------------------------------------------- */
 int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
                        int32_t fin, const float* row_scale, const float* h0, float c1, float c2, const float* w,
@@ -255,7 +257,8 @@ int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* v
                        float* s_out, void* stream);
 int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
                        int32_t fin, const float* row_scale, float c1, const float* w, int32_t fout, float theta,
-                       float beta, const float* gy, float* dval, float* dx, float* ds_out, void* stream);
+                       float beta, const float* gy, float* dval, float* dx, float* ds_out, float ds_scale,
+                       float* zero_ws, int64_t zero_count, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)

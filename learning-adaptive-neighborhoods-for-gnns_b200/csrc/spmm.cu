@@ -406,13 +406,23 @@ __device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld
 // degree distribution inside the block, no per-row shuffle reduction.  Phase 2 (dense part) is row-parallel: each warp
 // takes RB rows out of shared memory.  (r02 measurements of the first version, warp-per-row aggregation: 32 us at
 // Pubmed shape against 9.7 + 3.7 us for the entry-parallel SpMM + a library GEMM.)
-__device__ __forceinline__ int row_of_entry(const int32_t* __restrict__ rowptr, int r0, int r1, int e) {
-  int lo = r0, hi = r1 - 1;                         // last row r in [r0, r1) with rowptr[r] <= e
+// rp = the block's slice of rowptr in SHARED memory (rp[j] = rowptr[r0 + j], j <= nr): the search and the row
+// boundaries of phase 1 were 4-6 dependent global loads per group on the critical path of a 3 k-node layer
+__device__ __forceinline__ int row_of_entry(const int* rp, int nr, int e) {
+  int lo = 0, hi = nr - 1;                          // last local row j in [0, nr) with rp[j] <= e
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(rowptr + mid) <= e) lo = mid; else hi = mid - 1;
+    if (rp[mid] <= e) lo = mid; else hi = mid - 1;
   }
   return lo;
+}
+// W (or any [count] fp32 array) global -> shared, 128-bit when both sides allow
+__device__ __forceinline__ void stage_floats(float* dst, const float* __restrict__ src, int count) {
+  if ((count & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    for (int c = threadIdx.x; c < count / 4; c += blockDim.x) reinterpret_cast<float4*>(dst)[c] = ldg4(src + 4 * c);
+  } else {
+    for (int c = threadIdx.x; c < count; c += blockDim.x) dst[c] = __ldg(src + c);
+  }
 }
 
 template <int T, int Q, int RB>
@@ -423,22 +433,43 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                                   // [fin][fout]
   float* S = sm + A.fin * A.fout;                   // [R][fin] row accumulators, then s
+  int* rp = reinterpret_cast<int*>(S + R * A.fin);  // [R + 1] this block's slice of rowptr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R);
+  const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R), nr = r1 - r0;
   for (int c = threadIdx.x; c < R * A.fin; c += blockDim.x) S[c] = 0.f;
   pdl_wait();
-  for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) Ws[c] = __ldg(A.w + c);
-  const int eb0 = __ldg(A.rowptr + r0), eb1 = __ldg(A.rowptr + r1);
+  // everything the block needs from global memory besides the gathered rows goes in flight together: W, the rowptr
+  // slice, and -- into registers -- the phase-2 operands of this warp's rows (row_scale, h0, resid)
+  stage_floats(Ws, A.w, A.fin * A.fout);
+  for (int c = threadIdx.x; c <= nr; c += blockDim.x) rp[c] = __ldg(A.rowptr + r0 + c);
+  float k1v[RB], h0v[RB][4], rsv[RB][Q];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int i = r0 + warp * RB + r;
+    const bool ok = i < A.n;
+    k1v[r] = A.c1 * ((A.row_scale && ok) ? __ldg(A.row_scale + i) : 1.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      h0v[r][j] = (A.h0 && ok && c < A.fin) ? __ldg(A.h0 + (size_t)i * A.fin + c) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int c = lane + 32 * q;
+      rsv[r][q] = (A.resid && ok && c < A.fout) ? __ldg(A.resid + (size_t)i * A.fout + c) : 0.f;
+    }
+  }
   __syncthreads();
   // ---- phase 1: entry-parallel aggregation into S ----
   {
+    const int eb0 = rp[0], eb1 = rp[nr];
     const int nE = eb1 - eb0, groups = kSpmmWarps * G;
     const int per = (nE + groups - 1) / groups;
     const int e_beg = eb0 + (warp * G + grp) * per, e_end = min(eb1, e_beg + per);
     if (e_beg < e_end) {
-      int cur = row_of_entry(A.rowptr, r0, r1, e_beg);
-      int next_start = __ldg(A.rowptr + cur + 1);
+      int cur = row_of_entry(rp, nr, e_beg);        // local row
+      int next_start = rp[cur + 1];
       Vec<4> acc[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) acc[t].zero();
@@ -447,7 +478,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         for (int t = 0; t < T; ++t) {
           const int c = 4 * (lg + L * t);
           if (c < A.fin) {
-            float* d = S + (cur - r0) * A.fin + c;
+            float* d = S + cur * A.fin + c;
             atomicAdd(d + 0, acc[t].v.x); atomicAdd(d + 1, acc[t].v.y);
             atomicAdd(d + 2, acc[t].v.z); atomicAdd(d + 3, acc[t].v.w);
           }
@@ -459,7 +490,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         while (e >= next_start) {                   // group-uniform: the run crossed into the next (non-empty) row
           flush();
           ++cur;
-          next_start = __ldg(A.rowptr + cur + 1);
+          next_start = rp[cur + 1];
         }
         const int v = __ldg(A.col + e);
         const float a = __ldg(A.val + e);
@@ -479,17 +510,20 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   }
   __syncthreads();
   // ---- phase 2: s = c1 rs agg + c2 h0 (in place), y = act(theta s W + beta s + resid), RB rows per warp ----
+  // s_out receives theta * s: its only consumer is the weight gradient dW = theta s^T dY
   float* srows = S + warp * RB * A.fin;
 #pragma unroll
   for (int r = 0; r < RB; ++r) {
     const int i = r0 + warp * RB + r;
     if (i >= A.n) break;
-    const float k1 = A.c1 * (A.row_scale ? __ldg(A.row_scale + i) : 1.f);
-    for (int c = lane; c < A.fin; c += kWarp) {
-      float v = k1 * srows[r * A.fin + c];
-      if (A.h0) v = fmaf(A.c2, __ldg(A.h0 + (size_t)i * A.fin + c), v);
-      srows[r * A.fin + c] = v;
-      if (s_out) s_out[(size_t)i * A.fin + c] = v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      if (c < A.fin) {
+        const float v = fmaf(A.c2, h0v[r][j], k1v[r] * srows[r * A.fin + c]);
+        srows[r * A.fin + c] = v;
+        if (s_out) s_out[(size_t)i * A.fin + c] = A.theta * v;
+      }
     }
   }
   __syncwarp();
@@ -505,7 +539,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       if (c < A.fout) {
         float v = A.theta * d[r][q];
         if (A.beta != 0.f) v = fmaf(A.beta, srows[r * A.fin + c], v);      // fout == fin (checked on the host)
-        if (A.resid) v += __ldg(A.resid + (size_t)i * A.fout + c);
+        v += rsv[r][q];
         if (A.relu) v = fmaxf(v, 0.f);
         y[(size_t)i * A.fout + c] = v;
       }
@@ -513,10 +547,96 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   }
 }
 
+// Small graphs (one row per warp): the entry-parallel aggregation above combines the partial rows with shared-memory
+// float atomics (a CAS loop each) and two block barriers -- at Citeseer size (3 327 rows, ~4 entries per row) the ncu
+// source view charged 27 % of the instructions and 30 % of the stall samples to those atomics and another 24 % of the
+// samples to the barrier behind them (17 us per layer).  Here lane == column: the warp walks its row's entries, every
+// neighbour row is one or two coalesced 128-byte loads, eight entries in flight, the sum lands in the registers of the
+// lanes that own the columns -- no reduction, no atomics, no barrier besides the one behind the W staging.
+template <int Q>
+__global__ void __launch_bounds__(kSpmmWarps* kWarp)
+    spmm_gemm_fwd_row_kernel(SpmmGemmArgs A, float* __restrict__ y, float* __restrict__ s_out) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                                   // [fin][fout]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* srow = sm + A.fin * A.fout + warp * A.fin; // this warp's row of s
+  const int i = blockIdx.x * kSpmmWarps + warp;
+  const bool ok = i < A.n;
+  pdl_wait();
+  stage_floats(Ws, A.w, A.fin * A.fout);
+  const int beg = ok ? __ldg(A.rowptr + i) : 0, end = ok ? __ldg(A.rowptr + i + 1) : 0;
+  const float k1 = A.c1 * ((A.row_scale && ok) ? __ldg(A.row_scale + i) : 1.f);
+  float h0v[4], rsv[Q], acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    h0v[j] = (A.h0 && ok && c < A.fin) ? __ldg(A.h0 + (size_t)i * A.fin + c) : 0.f;
+    acc[j] = 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int c = lane + 32 * q;
+    rsv[q] = (A.resid && ok && c < A.fout) ? __ldg(A.resid + (size_t)i * A.fout + c) : 0.f;
+  }
+  const int nj = (A.fin + 31) >> 5;
+  for (int e0 = beg; e0 < end; e0 += kWarp) {
+    const int e = e0 + lane;
+    const int c_l = (e < end) ? __ldg(A.col + e) : 0;
+    const float a_l = (e < end) ? __ldg(A.val + e) : 0.f;
+    const int cnt = min(kWarp, end - e0);
+    for (int k0 = 0; k0 < cnt; k0 += 8) {
+      float xv[8][4];
+      float av[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {                 // slots beyond the row: a = 0, column 0 (a valid row)
+        const int v = __shfl_sync(0xffffffffu, c_l, (k0 + k) & 31);
+        av[k] = (k0 + k < cnt) ? __shfl_sync(0xffffffffu, a_l, (k0 + k) & 31) : 0.f;
+        const float* xr = A.x + (size_t)((k0 + k < cnt) ? v : 0) * A.fin;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = lane + 32 * j;
+          xv[k][j] = (j < nj && c < A.fin) ? __ldg(xr + c) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(av[k], xv[k][j], acc[j]);
+    }
+  }
+  // s = c1 rs agg + c2 h0;  s_out receives theta * s (see spmm_gemm_fwd_kernel)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < A.fin) {
+      const float v = fmaf(A.c2, h0v[j], k1 * acc[j]);
+      srow[c] = v;
+      if (s_out && ok) s_out[(size_t)i * A.fin + c] = A.theta * v;
+    }
+  }
+  __syncthreads();                                  // W staged (and this warp's srow written)
+  float d[1][Q];
+  dense_rows<Q, 1>(srow, A.fin, Ws, A.fin, A.fout, lane, d);
+  if (!ok) return;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int c = lane + 32 * q;
+    if (c < A.fout) {
+      float v = A.theta * d[0][q];
+      if (A.beta != 0.f) v = fmaf(A.beta, srow[c], v);                     // fout == fin (checked on the host)
+      v += rsv[q];
+      if (A.relu) v = fmaxf(v, 0.f);
+      y[(size_t)i * A.fout + c] = v;
+    }
+  }
+}
+
 template <int T, int Q, int RB>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_bwd_kernel(SpmmGemmArgs A, const float* __restrict__ gy, float* __restrict__ dval,
-                         float* __restrict__ dx, float* __restrict__ ds_out) {
+                         float* __restrict__ dx, float* __restrict__ ds_out, float ds_scale, float* zero_ws,
+                         long long zero_count) {
   constexpr int R = kSpmmWarps * RB;
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
@@ -524,20 +644,29 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   const int fo4 = (A.fout + 3) & ~3;                        // 16-byte aligned rows
   float* Gs = sm + ((A.fin * A.fout + 3) & ~3);             // [R][fo4] rows of gy
   float* DS = Gs + R * fo4;                                 // [R][fin]  ds rows (scaled by c1 rs for phase B)
+  int* rp = reinterpret_cast<int*>(DS + R * A.fin);         // [R + 1] this block's slice of rowptr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = A.L, G = kWarp / L, lg = lane % L, grp = lane / L;
-  const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R);
+  const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R), nr = r1 - r0;
   pdl_wait();
+  zero_fill(zero_ws, zero_count);       // the split-K buffer of the weight gradient that follows this launch
   for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
     const int f = c / A.fout, o = c % A.fout;
     Wt[o * A.fin + f] = __ldg(A.w + c);
+  }
+  for (int c = threadIdx.x; c <= nr; c += blockDim.x) rp[c] = __ldg(A.rowptr + r0 + c);
+  float k1v[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int i = r0 + warp * RB + r;
+    k1v[r] = (i < A.n) ? A.c1 * (A.row_scale ? __ldg(A.row_scale + i) : 1.f) : 0.f;
   }
   for (int c = threadIdx.x; c < R * fo4; c += blockDim.x) {
     const int r = c / fo4, o = c % fo4, i = r0 + r;
     Gs[c] = (i < A.n && o < A.fout) ? __ldg(gy + (size_t)i * A.fout + o) : 0.f;
   }
-  const int eb0 = __ldg(A.rowptr + r0), eb1 = __ldg(A.rowptr + r1);
   __syncthreads();
+  const int eb0 = rp[0], eb1 = rp[nr];
   // ---- phase A: ds[r][f] = theta * sum_c g[r][c] Wt[c][f] + beta * g[r][f], RB rows per warp ----
   {
     float* grows = Gs + warp * RB * fo4;
@@ -546,14 +675,14 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       const int i = r0 + warp * RB + r;
-      const float k1 = (i < A.n) ? A.c1 * (A.row_scale ? __ldg(A.row_scale + i) : 1.f) : 0.f;
+      const float k1 = k1v[r];
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const int f = lane + 32 * q;
         if (f < A.fin) {
           float v = A.theta * d[r][q];
           if (A.beta != 0.f) v = fmaf(A.beta, grows[r * fo4 + f], v);
-          if (ds_out && i < A.n) ds_out[(size_t)i * A.fin + f] = v;
+          if (ds_out && i < A.n) ds_out[(size_t)i * A.fin + f] = ds_scale * v;
           DS[(warp * RB + r) * A.fin + f] = k1 * v;
         }
       }
@@ -565,14 +694,14 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   const int per = (nE + groups - 1) / groups;
   const int e_beg = eb0 + (warp * G + grp) * per, e_end = min(eb1, e_beg + per);
   if (e_beg < e_end) {
-    int cur = row_of_entry(A.rowptr, r0, r1, e_beg);
-    int next_start = __ldg(A.rowptr + cur + 1);
+    int cur = row_of_entry(rp, nr, e_beg);          // local row
+    int next_start = rp[cur + 1];
     Vec<4> g[T];
     auto load_row = [&]() {
 #pragma unroll
       for (int t = 0; t < T; ++t) {
         const int c = 4 * (lg + L * t);
-        if (c < A.fin) g[t].v = *reinterpret_cast<const float4*>(DS + (cur - r0) * A.fin + c);
+        if (c < A.fin) g[t].v = *reinterpret_cast<const float4*>(DS + cur * A.fin + c);
         else g[t].zero();
       }
     };
@@ -582,7 +711,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       if (e >= next_start) {
         while (e >= next_start) {
           ++cur;
-          next_start = __ldg(A.rowptr + cur + 1);
+          next_start = rp[cur + 1];
         }
         load_row();
       }
@@ -697,7 +826,7 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
   const int rb = n >= kSmallGraphRows ? 4 : 1;
-  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * rb * fin) * sizeof(float);
+  const size_t smem = ((size_t)fin * fout + (size_t)kSpmmWarps * rb * fin + kSpmmWarps * rb + 4) * sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
@@ -706,6 +835,9 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
     return launch_status();
   };
   const int Q = fout <= 32 ? 1 : (fout <= 64 ? 2 : 4);
+  static const bool no_row = getenv("DGGB_SPMM_GEMM_NO_ROW") != nullptr;      // A/B: entry-parallel kernel on small graphs
+  if (rb == 1 && !no_row)
+    return Q == 1 ? go(spmm_gemm_fwd_row_kernel<1>) : (Q == 2 ? go(spmm_gemm_fwd_row_kernel<2>) : go(spmm_gemm_fwd_row_kernel<4>));
 #define DGGB_SG_Q(T_, R_) (Q == 1 ? go(spmm_gemm_fwd_kernel<T_, 1, R_>) : (Q == 2 ? go(spmm_gemm_fwd_kernel<T_, 2, R_>) : go(spmm_gemm_fwd_kernel<T_, 4, R_>)))
 #define DGGB_SG_F(T_) (rb == 4 ? DGGB_SG_Q(T_, 4) : DGGB_SG_Q(T_, 1))
   return T == 1 ? DGGB_SG_F(1) : (T == 2 ? DGGB_SG_F(2) : DGGB_SG_F(4));
@@ -716,22 +848,24 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
 extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
                                   const float* x, int32_t fin, const float* row_scale, float c1, const float* w,
                                   int32_t fout, float theta, float beta, const float* gy, float* dval, float* dx,
-                                  float* ds_out, void* stream) {
+                                  float* ds_out, float ds_scale, float* zero_ws, int64_t zero_count, void* stream) {
   SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, nullptr, w, nullptr, c1, 0.f, theta, beta, 0};
   int rc = spmm_gemm_check(A);
   if (rc != DGGB_OK) return rc;
-  if (!gy || (dx && ((uintptr_t)dx % 16))) return DGGB_ERR_BAD_ARG;
+  if (!gy || (dx && ((uintptr_t)dx % 16)) || zero_count < 0) return DGGB_ERR_BAD_ARG;
   if (n == 0) return DGGB_OK;
   int T = 1;
   A.L = spmm_gemm_lanes(fin, &T);
   const int rb = n >= kSmallGraphRows ? 4 : 1;
   const size_t smem =
-      ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * rb * (fin + ((fout + 3) & ~3))) * sizeof(float);
+      ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * rb * (fin + ((fout + 3) & ~3)) + kSpmmWarps * rb + 4) *
+      sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (n + kSpmmWarps * rb - 1) / (kSpmmWarps * rb);
-    launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out);
+    launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out, ds_scale,
+               zero_ws, (long long)zero_count);
     return launch_status();
   };
   const int Q = fin <= 32 ? 1 : (fin <= 64 ? 2 : 4);

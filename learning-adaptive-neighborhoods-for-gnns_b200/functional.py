@@ -217,17 +217,20 @@ class _SpmmGemm(torch.autograd.Function):
         need_v, need_x, need_w, need_h0 = ctx.needs_input_grad[:4]
         dval = torch.empty_like(vals) if need_v else None
         dx = torch.zeros_like(x) if need_x else None
-        ds = torch.empty_like(x) if (need_h0 and has_h0) else None
-        if need_v or need_x or ds is not None:
+        ds = torch.empty_like(x) if (need_h0 and has_h0) else None           # receives c2 * ds = d h0
+        launch = need_v or need_x or ds is not None
+        # the weight gradient's split-K accumulator is cleared by the layer's own backward launch (no fill kernel)
+        dwbuf = (torch.empty(w.numel(), dtype=torch.float32, device=x.device)
+                 if (need_w and launch and w.shape[1] % 4 == 0) else None)
+        if launch:
             check(lib().dggb_spmm_gemm_bwd(p(g.rowptr), p(g.col), p(vals), i32(g.n), p(x), i32(x.shape[1]),
                                            p(row_scale), float(c1), p(w), i32(w.shape[1]), float(theta), float(beta),
-                                           p(gy), p(dval), p(dx), p(ds), stream()), "spmm_gemm_bwd")
+                                           p(gy), p(dval), p(dx), p(ds), float(c2), p(dwbuf),
+                                           i64(0 if dwbuf is None else dwbuf.numel()), stream()), "spmm_gemm_bwd")
         dw = None
         if need_w:
-            dw = gemm_tn(s, gy, False)[0]
-            if theta != 1.0:
-                dw = dw * theta
-        dh0 = ds * c2 if ds is not None else None
+            dw = gemm_tn(s, gy, False, zeroed=dwbuf)[0]       # s was saved as theta * s
+        dh0 = ds
         dres = gy if (has_resid and ctx.needs_input_grad[4]) else None
         return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None
 
