@@ -640,9 +640,13 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   constexpr int R = kSpmmWarps * RB;
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
-  float* Wt = sm;                                           // [fout][fin] (transposed copy)
+  // W as it lies in memory ([fin][fout]) with rows padded to fout + 1 floats: lane f reads Wp[f][c] without bank
+  // conflicts, and the staging is a straight copy (the transposed copy of the first version -- 32-way conflicting
+  // stores plus a division per element -- was 36 % of this kernel's stall samples at Citeseer size)
+  float* Wp = sm;
+  const int wp = A.fout + 1;
   const int fo4 = (A.fout + 3) & ~3;                        // 16-byte aligned rows
-  float* Gs = sm + ((A.fin * A.fout + 3) & ~3);             // [R][fo4] rows of gy
+  float* Gs = sm + ((A.fin * wp + 3) & ~3);                 // [R][fo4] rows of gy
   float* DS = Gs + R * fo4;                                 // [R][fin]  ds rows (scaled by c1 rs for phase B)
   int* rp = reinterpret_cast<int*>(DS + R * A.fin);         // [R + 1] this block's slice of rowptr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -650,9 +654,19 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   const int r0 = blockIdx.x * R, r1 = min(A.n, r0 + R), nr = r1 - r0;
   pdl_wait();
   zero_fill(zero_ws, zero_count);       // the split-K buffer of the weight gradient that follows this launch
-  for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
-    const int f = c / A.fout, o = c % A.fout;
-    Wt[o * A.fin + f] = __ldg(A.w + c);
+  if ((A.fout & 3) == 0 && (reinterpret_cast<uintptr_t>(A.w) & 15) == 0) {
+    const int per_row = A.fout >> 2;
+    for (int c4 = threadIdx.x; c4 < A.fin * per_row; c4 += blockDim.x) {
+      const int f = c4 / per_row, o = (c4 - f * per_row) * 4;
+      const float4 v = ldg4(A.w + (size_t)f * A.fout + o);
+      float* d = Wp + f * wp + o;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int c = threadIdx.x; c < A.fin * A.fout; c += blockDim.x) {
+      const int f = c / A.fout;
+      Wp[f * wp + (c - f * A.fout)] = __ldg(A.w + c);
+    }
   }
   for (int c = threadIdx.x; c <= nr; c += blockDim.x) rp[c] = __ldg(A.rowptr + r0 + c);
   float k1v[RB];
@@ -671,7 +685,24 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   {
     float* grows = Gs + warp * RB * fo4;
     float d[RB][Q];
-    dense_rows_k<Q, RB>(grows, fo4, Wt, A.fout, A.fin, lane, d);
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) d[r][q] = 0.f;
+    for (int c = 0; c < A.fout; ++c) {                      // d[r][f] = sum_c g[r][c] W[f][c], lane owns f = lane + 32 q
+      float wv[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int f = lane + 32 * q;
+        wv[q] = (f < A.fin) ? Wp[f * wp + c] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float gv = grows[r * fo4 + c];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) d[r][q] = fmaf(gv, wv[q], d[r][q]);
+      }
+    }
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
       const int i = r0 + warp * RB + r;
@@ -858,7 +889,7 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
   A.L = spmm_gemm_lanes(fin, &T);
   const int rb = n >= kSmallGraphRows ? 4 : 1;
   const size_t smem =
-      ((size_t)fin * fout + 4 + (size_t)kSpmmWarps * rb * (fin + ((fout + 3) & ~3)) + kSpmmWarps * rb + 4) *
+      ((size_t)fin * (fout + 1) + 4 + (size_t)kSpmmWarps * rb * (fin + ((fout + 3) & ~3)) + kSpmmWarps * rb + 4) *
       sizeof(float);
   auto go = [&](auto kern) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -27,6 +27,8 @@ _NO_EDGE_SPMM = bool(_os.environ.get("DGGB_NO_EDGE_SPMM"))
 # its SIMT dense part (N x 64 x 64 FMAs next to the gathers) loses to the entry-parallel SpMM + a library GEMM:
 # GCN_DGG_00 train step 0.337 vs 0.308 ms (scripts/model_ab.py, DGGB_NO_FUSED_CONV A/B).
 _FUSED_CONV_MAX_N = int(_os.environ.get("DGGB_FUSED_CONV_MAX_N", "8192"))
+# rows from which the weight-gradient GEMM of a wide encoder (Q >= 256) runs on the tensor-core kernel
+_TN_TC_MIN_N = int(_os.environ.get("DGGB_TN_TC_MIN_N", "2048"))
 _FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu
 _LONG_ROW = 1024       # kRankCap of csrc/dgg_edge.cu: longer rows are ranked by a grid-wide launch
 
@@ -664,7 +666,7 @@ def gemm_tn(a, b, want_colsum=False, use_tc=None, zeroed=None):
     cs = buf[pp * q:] if want_colsum else None
     if use_tc is None:
         # wide outputs amortise the transpose pre-pass; narrow ones (dWe, Q = h) stay on the SIMT split-K kernel
-        use_tc = n >= 4096 and q % 4 == 0 and q >= 256 and pp in (16, 32, 64, 128)
+        use_tc = n >= _TN_TC_MIN_N and q % 4 == 0 and q >= 256 and pp in (16, 32, 64, 128)
     if use_tc:
         L = lib()
         ws_bytes = int(L.dggb_gemm_tn_tc_workspace_bytes(i32(n), i32(pp)))
