@@ -284,7 +284,13 @@ int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, cons
                       void* workspace, int64_t workspace_bytes,
                       float* zero_ws /* or NULL: zero_count floats cleared before the GEMM starts (the
                                         split-K buffers of the weight gradients that follow) */,
-                      int64_t zero_count, void* stream);
+                      int64_t zero_count,
+                      void* splitk_ws /* or NULL: [splits, N, H] fp32 scratch of dggb_linear_splitk_workspace_bytes:
+                                         few row tiles and a wide x (Cora / Citeseer raw features) are then split
+                                         over k so that every SM streams; the partial tiles are summed in a fixed
+                                         order by a second small launch (w2 == NULL only) */,
+                      int64_t splitk_ws_bytes, void* stream);
+int64_t dggb_linear_splitk_workspace_bytes(int32_t n, int32_t f, int32_t h);   /* 0: the call would not split */
 int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n,
                         int32_t f, int32_t h, float* out, void* workspace, int64_t workspace_bytes,
                         void* stream);

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kLinThreads, 1)
                          const float* __restrict__ act_src, float slope, int n, int f, float* __restrict__ out,
                          float* __restrict__ out2, int wait_first, float* __restrict__ outT_hi,
                          float* __restrict__ outT_lo, int npad, float* __restrict__ colsum,
-                         float* __restrict__ xT_hi, float* __restrict__ xT_lo) {
+                         float* __restrict__ xT_hi, float* __restrict__ xT_lo, int kb_per_split,
+                         float* __restrict__ part) {
   static_assert(!FUSE2 || H == 32 || H == 64, "fused second GEMM: K = H must be one or two 32-float k-blocks");
   constexpr uint32_t kXBytes = kLinBM * 128;       // one k-block of x: [128 rows][32 floats], 128-B swizzled
   constexpr uint32_t kWBytes = H * 128;            // one k-block of W hi (or lo): [H rows][32 floats]
@@ -129,17 +130,21 @@ __global__ void __launch_bounds__(kLinThreads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kLinBM;
-  const int num_kb = (f + 31) / 32;
+  // split-K (part != NULL; few row tiles, wide x): blockIdx.y owns k-blocks [kb0, kb0 + num_kb) and leaves its raw
+  // partial tile in part[blockIdx.y]; bias / addend / activation are applied by linear_splitk_epilogue_kernel, which
+  // sums the partials in a fixed order (deterministic, no atomics)
+  const int kb0 = part != nullptr ? (int)blockIdx.y * kb_per_split : 0;
+  const int num_kb = part != nullptr ? min(kb_per_split, (f + 31) / 32 - kb0) : (f + 31) / 32;
 
   auto load_x = [&](int kb) {
     const int s = kb % XS;
     tc::mbar_arrive_expect_tx(x_full + s, kXBytes);
-    tc::tma_load_2d(smem + s * kXBytes, &tm_x, x_full + s, kb * 32, row0);
+    tc::tma_load_2d(smem + s * kXBytes, &tm_x, x_full + s, (kb0 + kb) * 32, row0);
   };
   auto load_w = [&](int kb) {
     const int s = kb % WS;
     tc::mbar_arrive_expect_tx(w_full + s, kWStage);
-    tc::tma_load_2d(smem + XS * kXBytes + s * kWStage, &tm_w, w_full + s, kb * 32, 0);
+    tc::tma_load_2d(smem + XS * kXBytes + s * kWStage, &tm_w, w_full + s, (kb0 + kb) * 32, 0);
   };
 
   if (warp == 0 && lane == 0) {
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int colx = kb * 32 + 4 * c + j;
+              const int colx = (kb0 + kb) * 32 + 4 * c + j;
               if (colx < f) {
                 const size_t o = (size_t)colx * npad + node;
                 xT_hi[o] = __uint_as_float(__float_as_uint(vv[j]) & 0xffffe000u);
@@ -364,6 +369,16 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     };
     drain_acc();
     if (threadIdx.x == 64) LTRACE(6);
+    if (!FUSE2 && part != nullptr) {                 // split-K: raw partial tile, coalesced 128-bit rows
+      constexpr int kLpr = H / 4, kRpi = 32 / kLpr;
+      float* dst = part + (size_t)blockIdx.y * n * H;
+      for (int it = 0; it < 32 / kRpi; ++it) {
+        const int lr = it * kRpi + lane / kLpr, pc = (lane % kLpr) * 4;
+        const int row = row0 + q * 32 + lr;
+        if (row < n)
+          *reinterpret_cast<float4*>(dst + (size_t)row * H + pc) = *reinterpret_cast<const float4*>(stg + lr * kPitch + pc);
+      }
+    } else {
     // coalesced 128-bit rows: lane -> (row = it * kRowsPerIt + lane / kLanesPerRow, 16-B chunk = lane % kLanesPerRow)
     constexpr int kLanesPerRow = H / 4, kRowsPerIt = 32 / kLanesPerRow, kIters = 32 / kRowsPerIt;
     const int er = lane / kLanesPerRow, ec = (lane % kLanesPerRow) * 4;
@@ -485,6 +500,7 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           *reinterpret_cast<float4*>(out2 + (size_t)row * H + ec) = *reinterpret_cast<const float4*>(stg + lr * kPitch + ec);
       }
     }
+    }   // !split-K
   }
   __syncwarp();
   tc::fence_before_sync();
@@ -494,6 +510,56 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// out = epi(sum_s part[s] + bias + addend) for the split-K form of the kernel above (fixed summation order)
+__global__ void __launch_bounds__(256)
+    linear_splitk_epilogue_kernel(const float* __restrict__ part, int splits, int n, int h, const float* __restrict__ bias,
+                                  const float* __restrict__ addend, const float* __restrict__ act_src, float slope,
+                                  float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total4 = (long long)n * h / 4;
+  const int h4 = h / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = ldg4(part + 4 * i);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 u = ldg4(part + (size_t)sp * n * h + 4 * i);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    const int c = (int)(i % h4) * 4;
+    if (bias != nullptr) {
+      const float4 b = ldg4(bias + c);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (addend != nullptr) {
+      const float4 a = ldg4(addend + 4 * i);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (act_src != nullptr) {
+      const float4 a = ldg4(act_src + 4 * i);
+      v.x *= a.x > 0.f ? 1.f : slope; v.y *= a.y > 0.f ? 1.f : slope;
+      v.z *= a.z > 0.f ? 1.f : slope; v.w *= a.w > 0.f ? 1.f : slope;
+    } else {
+      v.x = v.x > 0.f ? v.x : slope * v.x; v.y = v.y > 0.f ? v.y : slope * v.y;
+      v.z = v.z > 0.f ? v.z : slope * v.z; v.w = v.w > 0.f ? v.w : slope * v.w;
+    }
+    st4(out + 4 * i, v);
+  }
+}
+
+// k-splits of a call: few row tiles (small graphs with wide raw features: Cora 22 tiles x 45 k-blocks, Citeseer
+// 26 x 116) leave most SMs idle and make one CTA stream its whole 128-row slab alone (72 us at Citeseer shape)
+static int linear_splits(int n, int f, int* kb_per_split) {
+  const int tiles = (n + kLinBM - 1) / kLinBM, total_kb = (f + 31) / 32;
+  int splits = 1;
+  if (tiles * 2 <= kNumSMs && total_kb >= 16) {
+    splits = kNumSMs / tiles;
+    if (splits > total_kb / 8) splits = total_kb / 8;
+    if (splits < 1) splits = 1;
+  }
+  *kb_per_split = (total_kb + splits - 1) / splits;
+  return (total_kb + *kb_per_split - 1) / *kb_per_split;
 }
 
 // Optional pieces of one call (all pointers may be NULL):
@@ -509,6 +575,8 @@ struct LinearExtra {
   float* colsum = nullptr;
   float* xT_hi = nullptr;       // out, [F, npad]: transposed TF32 split of x (see the converter loop)
   float* xT_lo = nullptr;
+  float* splitk_ws = nullptr;   // [splits, N, H] partial tiles: enables the split-K form when it pays (linear_splits)
+  long long splitk_ws_bytes = 0;
 };
 
 template <int H>
@@ -556,7 +624,7 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
       launch_pdl((linear_tf32x3_kernel<H, XS, WS, true>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w,
                  tm_w2hi, tm_w2lo, b, addend, act_src, slope, n, f, out, out2, 0, static_cast<float*>(nullptr),
                  static_cast<float*>(nullptr), 0, static_cast<float*>(nullptr), static_cast<float*>(nullptr),
-                 static_cast<float*>(nullptr));
+                 static_cast<float*>(nullptr), 0, static_cast<float*>(nullptr));
       return launch_status();
     }
   }
@@ -564,9 +632,24 @@ static int launch_linear(const float* x, const float* w, int w_transposed, const
   cudaError_t e = cudaFuncSetAttribute(linear_tf32x3_kernel<H, XS, WS, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
+  int kb_per_split = 0;
+  const int splits = (ex.splitk_ws && !ex.outT_hi && !ex.xT_hi && out) ? linear_splits(n, f, &kb_per_split) : 1;
+  if (splits > 1 && ex.splitk_ws_bytes >= (long long)splits * n * H * (long long)sizeof(float)) {
+    launch_pdl((linear_tf32x3_kernel<H, XS, WS, false>), dim3(grid, splits), dim3(kLinThreads), smem, st, tm_x, tm_w,
+               tm_w, tm_w, b, addend, act_src, slope, n, f, out, static_cast<float*>(nullptr), wait_first,
+               static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0, static_cast<float*>(nullptr),
+               static_cast<float*>(nullptr), static_cast<float*>(nullptr), kb_per_split, ex.splitk_ws);
+    rc = launch_status();
+    if (rc != DGGB_OK) return rc;
+    const long long total4 = (long long)n * H / 4;
+    const int eblocks = (int)min((long long)kNumSMs * 4, (total4 + 255) / 256);
+    launch_pdl(linear_splitk_epilogue_kernel, dim3(eblocks), dim3(256), 0, st, static_cast<const float*>(ex.splitk_ws),
+               splits, n, H, b, addend, act_src, slope, out);
+    return launch_status();
+  }
   launch_pdl((linear_tf32x3_kernel<H, XS, WS, false>), dim3(grid), dim3(kLinThreads), smem, st, tm_x, tm_w, tm_w, tm_w,
              b, addend, act_src, slope, n, f, out, static_cast<float*>(nullptr), wait_first, ex.outT_hi, ex.outT_lo,
-             ex.npad, ex.colsum, ex.xT_hi, ex.xT_lo);
+             ex.npad, ex.colsum, ex.xT_hi, ex.xT_lo, 0, static_cast<float*>(nullptr));
   return launch_status();
 }
 
@@ -589,14 +672,23 @@ extern "C" int64_t dggb_linear_act_workspace_bytes(int32_t f, int32_t h) {
   return ((int64_t)2 * h * f + (int64_t)2 * h * h) * 4;   // W hi/lo (+ W2 hi/lo of the chained GEMM)
 }
 
+// bytes of the split-K partial-tile workspace dggb_linear_fused can use for this shape (0: the call would not split)
+extern "C" int64_t dggb_linear_splitk_workspace_bytes(int32_t n, int32_t f, int32_t h) {
+  if (n <= 0 || f <= 0 || h <= 0) return 0;
+  int kbps = 0;
+  const int splits = linear_splits(n, f, &kbps);
+  return splits > 1 ? (int64_t)splits * n * h * (int64_t)sizeof(float) : 0;
+}
+
 static bool misaligned(const void* p) { return p != nullptr && ((uintptr_t)p % 16) != 0; }
 
 extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_transposed, const float* b,
                                  const float* addend, const float* act_src, float slope, int32_t n, int32_t f,
                                  int32_t h, float* out, const float* w2, float* out2, void* workspace,
-                                 int64_t workspace_bytes, float* zero_ws, int64_t zero_count, void* stream) {
+                                 int64_t workspace_bytes, float* zero_ws, int64_t zero_count, void* splitk_ws,
+                                 int64_t splitk_ws_bytes, void* stream) {
   if (!x || !w || !out || !workspace || n < 0 || f <= 0 || h <= 0 || ((w2 == nullptr) != (out2 == nullptr)) ||
-      zero_count < 0)
+      zero_count < 0 || splitk_ws_bytes < 0 || misaligned(splitk_ws))
     return DGGB_ERR_BAD_ARG;
   if (workspace_bytes < dggb_linear_act_workspace_bytes(f, h)) return DGGB_ERR_WORKSPACE;
   if ((uintptr_t)workspace % 16) return DGGB_ERR_BAD_ARG;
@@ -606,14 +698,19 @@ extern "C" int dggb_linear_fused(const float* x, const float* w, int32_t w_trans
       misaligned(addend) || misaligned(act_src) || misaligned(b) || misaligned(out2))
     return DGGB_ERR_BAD_SHAPE;
   if (n == 0) return DGGB_OK;
+  LinearExtra ex;
+  if (w2 == nullptr && splitk_ws != nullptr) {
+    ex.splitk_ws = reinterpret_cast<float*>(splitk_ws);
+    ex.splitk_ws_bytes = (long long)splitk_ws_bytes;
+  }
   return dispatch_linear(h, x, w, (int)w_transposed, b, addend, act_src, slope, (int)n, (int)f, out, ws, w2, out2,
-                         zero_ws, (long long)zero_count, as_stream(stream), LinearExtra());
+                         zero_ws, (long long)zero_count, as_stream(stream), ex);
 }
 
 extern "C" int dggb_linear_act_fwd(const float* x, const float* w, const float* b, float slope, int32_t n, int32_t f,
                                    int32_t h, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
   return dggb_linear_fused(x, w, 0, b, nullptr, nullptr, slope, n, f, h, out, nullptr, nullptr, workspace,
-                           workspace_bytes, nullptr, 0, stream);
+                           workspace_bytes, nullptr, 0, nullptr, 0, stream);
 }
 
 // (x_enc, y) = (LeakyReLU_slope(x Wn^T + bn), x_enc We^T) in one launch (+ the weight-split launch), see dggb.h

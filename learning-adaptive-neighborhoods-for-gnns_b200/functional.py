@@ -542,9 +542,13 @@ def _linear_act_tc(x, w, b, slope, w_transposed=False, addend=None, act_src=None
     ws = torch.empty(2 * h * f_in + 2 * h * h, dtype=torch.float32, device=x.device)
     out2 = torch.empty(n, h, dtype=torch.float32, device=x.device) if w2 is not None else None
     w2c = None if w2 is None else w2.contiguous()
+    # few row tiles and wide features (Cora / Citeseer raw inputs): partial-tile scratch for the split-K form
+    sk_bytes = int(lib().dggb_linear_splitk_workspace_bytes(i32(n), i32(f_in), i32(h))) if w2 is None else 0
+    sk = torch.empty(sk_bytes // 4, dtype=torch.float32, device=x.device) if sk_bytes > 0 else None
     rc = lib().dggb_linear_fused(p(x), p(w), i32(1 if w_transposed else 0), p(bb), p(ad), p(ac),
                                  float(slope), i32(n), i32(f_in), i32(h), p(out), p(w2c), p(out2), p(ws),
-                                 i64(ws.numel() * 4), p(zero), i64(0 if zero is None else zero.numel()), stream())
+                                 i64(ws.numel() * 4), p(zero), i64(0 if zero is None else zero.numel()), p(sk),
+                                 i64(sk_bytes), stream())
     if rc == -2:
         return None
     check(rc, "linear_fused")

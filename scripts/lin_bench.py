@@ -16,7 +16,7 @@ ws_tn_bytes = int(L.dggb_gemm_tn_tc_workspace_bytes(n, h)); ws_tn = torch.empty(
 dw = torch.zeros(h * f + h, device="cuda")
 def lin(i, fuse):
     check(L.dggb_linear_fused(p(xs[i % 6]), p(w), 0, p(b), None, None, 0.01, n, f, h, p(out), p(we) if fuse else None,
-                              p(out2) if fuse else None, p(ws), ws.numel() * 4, None, 0, stream()), "lin")
+                              p(out2) if fuse else None, p(ws), ws.numel() * 4, None, 0, None, 0, stream()), "lin")
 def tn(i):
     check(L.dggb_gemm_tn_tc(p(dpre), p(xs[i % 6]), n, h, f, p(dw[:h * f]), p(dw[h * f:]), p(ws_tn), ws_tn_bytes, stream()), "tn")
 def graph_time(fn, reps=200):

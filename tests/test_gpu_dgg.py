@@ -414,3 +414,30 @@ def test_spmm_gemm_fused_layer_vs_tensor_ops(n, fin, fout, h0, relu, resid, thet
     for name, a, b in zip(["val", "x", "w", "h0", "resid"], g_got, g_ref):
         if b is not None:
             assert_grad_close(a, b, what=name)
+
+
+
+@pytest.mark.parametrize("n,f,h,slope,bias", [(3327, 3704, 64, 0.01, True), (2708, 1436, 64, 0.0, True),
+                                              (1500, 1024, 32, 1.0, False), (3000, 2048, 128, 0.01, True)])
+def test_linear_splitk_small_n_wide_f_matches_fp64(n, f, h, slope, bias):
+    """Few row tiles + wide features take the split-K form of the encoder GEMM (partial tiles summed in a fixed order
+    by a second launch): values against fp64, run-to-run bit-identical, backward form (addend / act_src) included."""
+    from dgg_b200 import functional as K
+    from dgg_b200._lib import lib
+
+    assert int(lib().dggb_linear_splitk_workspace_bytes(n, f, h)) > 0
+    gen = torch.Generator().manual_seed(n + f)
+    x = torch.rand(n, f, generator=gen).cuda()
+    w = (torch.randn(h, f, generator=gen) / f ** 0.5).cuda()
+    b = torch.randn(h, generator=gen).cuda() if bias else None
+    out = K._linear_act_tc(x, w, b, slope)
+    pre = x.double() @ w.double().t() + (b.double() if bias else 0.0)
+    want = torch.where(pre > 0, pre, pre * slope)
+    torch.testing.assert_close(out, want.float(), rtol=2e-5, atol=2e-5)
+    assert torch.equal(out, K._linear_act_tc(x, w, b, slope))
+    # backward form: out = (x W^T + addend) * LeakyReLU'(act_src)
+    ad = torch.randn(n, h, generator=gen).cuda()
+    ac = torch.randn(n, h, generator=gen).cuda()
+    got = K._linear_act_tc(x, w, None, slope, addend=ad, act_src=ac)
+    ref = (x.double() @ w.double().t() + ad.double()) * torch.where(ac > 0, 1.0, slope).double()
+    torch.testing.assert_close(got, ref.float(), rtol=2e-5, atol=2e-5)
