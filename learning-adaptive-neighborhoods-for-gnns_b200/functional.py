@@ -719,6 +719,40 @@ class _TallMatmul(torch.autograd.Function):
         return dx, dw
 
 
+class _HeadDots(torch.autograd.Function):
+    """pq[n, k, c] = sum_f h[n, k, f] a[k, f, c] -- the per-node halves p_i = a1^T h_i, q_j = a2^T h_j of the GAT logits
+    e_ij = LeakyReLU(a^T [h_i || h_j]) (model.py:561-563) for all heads.  The forward is a skinny batched product; its
+    weight gradient da[k] = h_k^T g_k reduces over the N nodes into a [F, 2] output per head, which the batched
+    library GEMM runs on a handful of CTAs (455 us at Pubmed shape, 8 heads): it goes through the split-K kernel as
+    ONE [heads F, N] x [N, 2 heads] product whose diagonal blocks are the answer (~15 us)."""
+
+    @staticmethod
+    def forward(ctx, h, a):
+        ctx.save_for_backward(h, a)
+        return torch.einsum("nkf,kfc->nkc", h, a)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, a = ctx.saved_tensors
+        n, heads, f = h.shape
+        g = _f32c(g)
+        dh = torch.einsum("nkc,kfc->nkf", g, a) if ctx.needs_input_grad[0] else None
+        da = None
+        if ctx.needs_input_grad[1]:
+            if h.is_cuda and n >= 2048 and (heads * f) % 4 == 0:
+                full = gemm_tn(h.reshape(n, heads * f), g.reshape(n, heads * 2), False)[0]      # [heads f, heads 2]
+                full = full.view(heads, f, heads, 2)
+                idx = torch.arange(heads, device=h.device)
+                da = full[idx, :, idx, :]                                                        # diagonal blocks
+            else:
+                da = torch.einsum("nkf,nkc->kfc", h, g)
+        return dh, da
+
+
+def head_dots(h, a):
+    return _HeadDots.apply(h, a)
+
+
 def tall_matmul(x, w):
     if x.is_cuda and x.dtype == torch.float32 and x.shape[0] >= 2048 and x.shape[1] <= 512:
         return _TallMatmul.apply(x, w)

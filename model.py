@@ -477,11 +477,13 @@ def gat_heads(convs, x, edge_list, adj):
     if not plan.csr_aligned or any(c.bias is None for c in convs):
         return torch.cat([c._attend_eager(x, edge_list, adj) for c in convs], dim=1)
     if training and p_drop > 0:      # every head draws its own input-dropout mask (model.py:558 inside each conv)
-        h = torch.stack([torch.matmul(F.dropout(x, p_drop, training=True), c.weight) for c in convs], dim=1)
+        # (tall_matmul: the weight gradients x^T g reduce over the N nodes -- split-K kernels instead of a library GEMM
+        # that leaves them on a handful of CTAs: 8 x 81 us at Pubmed shape)
+        h = torch.stack([K.tall_matmul(F.dropout(x, p_drop, training=True), c.weight) for c in convs], dim=1)
     else:
-        h = torch.matmul(x, torch.cat([c.weight for c in convs], dim=1)).view(n, heads, f)
+        h = K.tall_matmul(x, torch.cat([c.weight for c in convs], dim=1)).view(n, heads, f)
     a = torch.stack([torch.cat([c.a[:f], c.a[f:]], dim=1) for c in convs])              # [heads, F, 2]
-    pq = torch.einsum("nkf,kfc->nkc", h, a)       # e_ij = LeakyReLU(a^T [h_i || h_j]) = LeakyReLU(p_i + q_j)
+    pq = K.head_dots(h, a)                        # e_ij = LeakyReLU(a^T [h_i || h_j]) = LeakyReLU(p_i + q_j)
     hd = F.dropout(h, p_drop, training=training)
     bias = torch.stack([c.bias for c in convs])
     fp = (f + 3) // 4 * 4                         # 128-bit gathers: pad e.g. the 3 / 7 class logits to 4 / 8
