@@ -249,11 +249,24 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         tc::mma_commit(a_empty + ab);
         LTRACE(40 + kb);
       };
+      // Issue order.  DGGB_LIN_HI_AHEAD: hi(kb + 1) before lo(kb) (the order of the first versions, when the lo operand
+      // was the late one).  r02b trace: x lands ~2 000 cycles before its MMAs issue and the lo operand ~450 cycles after
+      // that, so nothing waits for the converters any more -- but W(kb + 3) can only be requested once lo(kb) has
+      // retired, and with hi(kb + 1), hi(kb + 2) queued in front of it that request came too late for hi(kb + 3)
+      // (~300 cycles of every 1 100-cycle k-block were spent waiting for the W stage).  In order, lo(kb) retires two
+      // MMA groups earlier.
+#ifdef DGGB_LIN_HI_AHEAD
       issue_hi(0);
       for (int kb = 0; kb < num_kb; ++kb) {
         if (kb + 1 < num_kb) issue_hi(kb + 1);
         issue_lo(kb);
       }
+#else
+      for (int kb = 0; kb < num_kb; ++kb) {
+        issue_hi(kb);
+        issue_lo(kb);
+      }
+#endif
       tc::mma_commit(acc_full);
       if (FUSE2) {
         tc::mbar_wait_backoff(w2_full, 0);
