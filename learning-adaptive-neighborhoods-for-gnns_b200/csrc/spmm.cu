@@ -375,30 +375,6 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ S, int ld_s
   }
 }
 
-// same with a reduction length that need not be a multiple of 4 (the S rows are zero-padded to ld_s)
-template <int Q, int RB>
-__device__ __forceinline__ void dense_rows_k(const float* __restrict__ S, int ld_s, const float* __restrict__ M,
-                                             int k_dim, int n_cols, int lane, float (&acc)[RB][Q]) {
-#pragma unroll
-  for (int r = 0; r < RB; ++r)
-#pragma unroll
-    for (int q = 0; q < Q; ++q) acc[r][q] = 0.f;
-  for (int f = 0; f < k_dim; ++f) {
-    float mv[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int c = lane + 32 * q;
-      mv[q] = (c < n_cols) ? M[f * n_cols + c] : 0.f;
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const float sf = S[r * ld_s + f];
-#pragma unroll
-      for (int q = 0; q < Q; ++q) acc[r][q] = fmaf(sf, mv[q], acc[r][q]);
-    }
-  }
-}
-
 // Block b owns the kSpmmWarps * RB consecutive rows [r0, r1) and therefore the contiguous entry range
 // [rowptr[r0], rowptr[r1]).  Phase 1 (aggregation) is ENTRY-parallel inside the block: groups of L lanes walk runs of
 // consecutive entries, keep the running row sum in registers and add it to the row's accumulator in shared memory

@@ -683,20 +683,6 @@ def gemm_tn(a, b, want_colsum=False, use_tc=None, zeroed=None):
     return out, cs
 
 
-def splitk_tn(a, b, chunk=1024):
-    """a^T b for a [N, P], b [N, Q] with N large: batched over row chunks so the reduction is split."""
-    n = a.shape[0]
-    s = n // chunk
-    if s < 4:
-        return a.t() @ b
-    main = s * chunk
-    part = torch.bmm(a[:main].view(s, chunk, a.shape[1]).transpose(1, 2), b[:main].view(s, chunk, b.shape[1]))
-    out = part.sum(0)
-    if main < n:
-        out = out + a[main:].t() @ b[main:]
-    return out
-
-
 def tall_linear(x, w, b=None, slope=1.0):
     return _TallLinear.apply(x, w, b, float(slope))
 

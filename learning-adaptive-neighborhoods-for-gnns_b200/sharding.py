@@ -251,8 +251,8 @@ class RowShardedSAGE_DGG(torch.nn.Module):
             fo = p.shape[1]
             if fo % 4:                                                   # 128-bit gathers: pad 41 classes to 44
                 p = torch.nn.functional.pad(p, (0, 4 - fo % 4))
-            p_all = all_gather_rows(p, n, group) if sharded else p
-            agg = K.spmm(vals, p_all, g)[:, :fo] * scale.unsqueeze(-1)     # (scale carries gradient: not the kernel's constant row_scale)
+            # (scale carries gradient: applied outside, not as the kernel's constant row_scale)
+            agg = (sharded_spmm(vals, p, g, n, group) if sharded else K.spmm(vals, p, g))[:, :fo] * scale.unsqueeze(-1)
             h_new = agg + lin_rel.bias + lin_root(h)
             h = h_new if last else torch.nn.functional.dropout(torch.relu(h_new), 0.5, self.training)
         return torch.log_softmax(h, dim=-1), idx, ahat
