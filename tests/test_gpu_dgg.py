@@ -441,3 +441,55 @@ def test_linear_splitk_small_n_wide_f_matches_fp64(n, f, h, slope, bias):
     got = K._linear_act_tc(x, w, None, slope, addend=ad, act_src=ac)
     ref = (x.double() @ w.double().t() + ad.double()) * torch.where(ac > 0, 1.0, slope).double()
     torch.testing.assert_close(got, ref.float(), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("n,f,h,with_dx", [(4500, 256, 64, True), (5000, 500, 32, False), (4099, 260, 64, False)])
+def test_encode_project_step_path_vs_fp64_autograd(n, f, h, with_dx):
+    """The training-step form of the DGG encoder (dggb_encoder_fwd / dggb_encoder_bwd_dpre / dggb_gemm_tn_tc_presplit:
+    pre-split We^T and cleared accumulators from the forward's split launch, transposed TF32 splits from the d pre
+    kernel, dWn and dWe in one launch) against fp64 autograd of LeakyReLU(x Wn^T + bn), x_enc We^T -- every gradient,
+    incl. d x when the features require it, and a second backward through the same node (fresh accumulators)."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(n + h)
+    x = torch.rand(n, f, generator=gen).cuda().requires_grad_(with_dx)
+    wn = (torch.randn(h, f, generator=gen) / f ** 0.5).cuda().requires_grad_(True)
+    bn = torch.randn(h, generator=gen).cuda().requires_grad_(True)
+    we = (torch.randn(h, h, generator=gen) / h ** 0.5).cuda().requires_grad_(True)
+    g1 = torch.randn(n, h, generator=gen).cuda()
+    g2 = torch.randn(n, h, generator=gen).cuda()
+    x_enc, y = K.encode_project(x, wn, bn, we, 0.01)
+    ins = [t for t in (x, wn, bn, we) if t.requires_grad]
+    got = torch.autograd.grad([x_enc, y], ins, [g1, g2], retain_graph=True)
+    again = torch.autograd.grad([x_enc, y], ins, [g1, g2])
+    xd, wd, bd, ed = (t.detach().double().requires_grad_(t.requires_grad) for t in (x, wn, bn, we))
+    pre = xd @ wd.t() + bd
+    xe = torch.where(pre > 0, pre, 0.01 * pre)
+    yy = xe @ ed.t()
+    torch.testing.assert_close(x_enc, xe.float(), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(y, yy.float(), rtol=2e-5, atol=3e-5)
+    want = torch.autograd.grad([xe, yy], [t for t in (xd, wd, bd, ed) if t.requires_grad], [g1.double(), g2.double()])
+    for a, b, w in zip(got, again, want):
+        scale = float(w.abs().max())
+        assert float((a.double() - w).abs().max()) <= 2e-5 * scale + 1e-6
+        assert float((b.double() - w).abs().max()) <= 2e-5 * scale + 1e-6
+
+
+def test_head_dots_weight_gradient_through_splitk_kernel():
+    """GAT logit halves pq = h a for all heads: the batched weight gradient goes through ONE split-K product whose
+    diagonal blocks are taken (functional._HeadDots) -- against einsum autograd in fp64."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(3)
+    n, heads, f = 3000, 8, 64
+    h = torch.randn(n, heads, f, generator=gen).cuda().requires_grad_(True)
+    a = torch.randn(heads, f, 2, generator=gen).cuda().requires_grad_(True)
+    g = torch.randn(n, heads, 2, generator=gen).cuda()
+    pq = K.head_dots(h, a)
+    dh, da = torch.autograd.grad(pq, [h, a], g)
+    hd, ad = h.detach().double().requires_grad_(True), a.detach().double().requires_grad_(True)
+    ref = torch.einsum("nkf,kfc->nkc", hd, ad)
+    rdh, rda = torch.autograd.grad(ref, [hd, ad], g.double())
+    torch.testing.assert_close(pq, ref.float(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dh, rdh.float(), rtol=1e-5, atol=1e-5)
+    assert float((da.double() - rda).abs().max()) <= 1e-5 * float(rda.abs().max())
