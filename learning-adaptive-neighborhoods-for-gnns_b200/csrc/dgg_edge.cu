@@ -752,6 +752,9 @@ __global__ void __launch_bounds__(kFusedThreads)
   for (int c = threadIdx.x; c < h; c += kFusedThreads) atomicAdd(dbe + c, dbe_s[c]);
 }
 
+#ifndef DGGB_BWD2_MIN_BLOCKS
+#define DGGB_BWD2_MIN_BLOCKS 1
+#endif
 // ------------------------------------------------------------------------------------------------
 // Second generation of the fused kernels (same contract, same results up to the summation order of the row sums).
 // What the ncu source view of the first generation showed at Pubmed shape (profiles/r02_fused_edge_v2.md): a third
@@ -865,7 +868,7 @@ __global__ void __launch_bounds__(kFusedThreads)
 }
 
 template <int T, int LC>
-__global__ void __launch_bounds__(kFusedThreads)
+__global__ void __launch_bounds__(kFusedThreads, DGGB_BWD2_MIN_BLOCKS)
     dgg_bwd_fused2_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ erow,
                           const int32_t* __restrict__ col, int n, int nnz, int h, int L, int epb, int cap,
                           const float* __restrict__ y, const float* __restrict__ be,

@@ -61,7 +61,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int P>
+// STACK (P <= 64, a^T_lo stored right behind a^T_hi): the B operand of a k-block is ONE [2P rows][32 nodes] box
+// [a^T_hi ; a^T_lo]; 3xTF32 is then TWO MMAs per k-step -- A_hi x [B_hi ; B_lo] (N = 2P: hi*hi | hi*lo side by side in the
+// accumulator) and A_lo x B_hi (N = P, onto the hi*hi columns) -- instead of three N = P ones (64 + 47 against
+// 3 x 47 cycles at P = 64, scripts/micro/mma_rate.cu); the epilogue adds the two column halves.
+template <int P, bool STACK>
 __global__ void __launch_bounds__(kTcThreads, 2)
     gemm_tn_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_b1, const __grid_constant__ CUtensorMap tm_ahi1,
                           const __grid_constant__ CUtensorMap tm_alo1, int n, int q1, int kb_per_split,
@@ -79,7 +83,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   constexpr uint32_t kXBytes = 4 * 32 * 128;       // four [32 nodes][32 feats] boxes = 128 features x 32 nodes
   constexpr uint32_t kWBytes = P * 128;            // a^T hi (or lo): [P rows][32 nodes]
   constexpr uint32_t kStageBytes = kXBytes + 2 * kWBytes;
-  constexpr uint32_t kAccCols = P <= 64 ? 64 : 128;
+  static_assert(!STACK || P <= 64, "stacked B: accumulator 2P + two A buffers must fit 256 TMEM columns");
+  constexpr uint32_t kAccCols = STACK ? 128 : (P <= 64 ? 64 : 128);
   constexpr uint32_t kTmemCols = 256;
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
@@ -135,13 +140,18 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         tc::mbar_arrive_expect_tx(full + s, kStageBytes);
 #pragma unroll
         for (int bx = 0; bx < 4; ++bx) tc::tma_load_2d(st + bx * 4096, &tm_b, full + s, m0 + bx * 32, node0);
-        tc::tma_load_2d(st + kXBytes, &tm_ahi, full + s, node0, 0);
-        tc::tma_load_2d(st + kXBytes + kWBytes, &tm_alo, full + s, node0, 0);
+        if (STACK) {
+          tc::tma_load_2d(st + kXBytes, &tm_ahi, full + s, node0, 0);      // [2P][32]: hi rows, then lo rows
+        } else {
+          tc::tma_load_2d(st + kXBytes, &tm_ahi, full + s, node0, 0);
+          tc::tma_load_2d(st + kXBytes + kWBytes, &tm_alo, full + s, node0, 0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::idesc_tf32(kTcM, P);
+      constexpr uint32_t idesc2 = tc::idesc_tf32(kTcM, STACK ? 2 * P : P);
       int s = 0;
       uint32_t ph = 0, acc = 0;
       for (int i = 0; i < num_kb; ++i, (++s == kTcStages) ? (s = 0, ph ^= 1) : 0) {
@@ -152,14 +162,25 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         tc::fence_after_sync();
         const uint32_t wh = tc::smem_u32(smem + s * kStageBytes + kXBytes), wl = wh + kWBytes;
         const uint32_t ah = tmem_a0 + ab * 64, al = ah + 32;
+        if (STACK) {
 #pragma unroll
-        for (int sp = 0; sp < 3; ++sp) {
-          const uint32_t a = (sp == 2) ? al : ah;   // hi*hi, hi*lo, lo*hi
-          const uint32_t b = (sp == 1) ? wl : wh;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mma_tf32_ts(tmem_base, a + ks * 8, tc::smem_desc_k128(b + ks * 32), idesc, acc);
+          for (int ks = 0; ks < 4; ++ks) {          // A_hi x [B_hi ; B_lo] -> [hi*hi | hi*lo]
+            mma_tf32_ts(tmem_base, ah + ks * 8, tc::smem_desc_k128(wh + ks * 32), idesc2, acc);
             acc = 1;
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)            // A_lo x B_hi onto the hi*hi columns
+            mma_tf32_ts(tmem_base, al + ks * 8, tc::smem_desc_k128(wh + ks * 32), idesc, 1u);
+        } else {
+#pragma unroll
+          for (int sp = 0; sp < 3; ++sp) {
+            const uint32_t a = (sp == 2) ? al : ah;   // hi*hi, hi*lo, lo*hi
+            const uint32_t b = (sp == 1) ? wl : wh;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_tf32_ts(tmem_base, a + ks * 8, tc::smem_desc_k128(b + ks * 32), idesc, acc);
+              acc = 1;
+            }
           }
         }
         tc::mma_commit(empty + s);
@@ -209,6 +230,13 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       for (int c0 = 0; c0 < P; c0 += 16) {
         uint32_t r[16];
         tc::tmem_ld_32x16(tmem_base + lane_addr + c0, r);
+        if (STACK) {
+          uint32_t r2[16];
+          tc::tmem_ld_32x16(tmem_base + lane_addr + P + c0, r2);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r2[c]));
+        }
         tc::tmem_ld_wait();
         if (feat < q) {
 #pragma unroll
@@ -241,19 +269,34 @@ static int launch_tn_gemm(const float* a_hi, const float* a_lo, int npad, const 
   CUtensorMap tm_b, tm_ahi, tm_alo, tm_b2, tm_ahi2, tm_alo2;
   int rc = make_tmap_2d_f32(&tm_b, b, (uint64_t)n, (uint64_t)q, 32, 32);
   if (rc != DGGB_OK) return rc;
-  rc = make_tmap_2d_f32(&tm_ahi, a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
-  if (rc != DGGB_OK) return rc;
-  rc = make_tmap_2d_f32(&tm_alo, a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
-  if (rc != DGGB_OK) return rc;
+  static const bool no_stack = getenv("DGGB_TN_NO_STACK") != nullptr;     // A/B: three N = P MMAs per k-step
+  const bool stack = (P <= 64) && !no_stack && a_lo == a_hi + (size_t)P * npad &&
+                     (s2.b == nullptr || s2.a_lo == s2.a_hi + (size_t)P * npad);
+  if (stack) {
+    rc = make_tmap_2d_f32(&tm_ahi, a_hi, (uint64_t)2 * P, (uint64_t)npad, 2 * P, 32);
+    if (rc != DGGB_OK) return rc;
+    tm_alo = tm_ahi;
+  } else {
+    rc = make_tmap_2d_f32(&tm_ahi, a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
+    if (rc != DGGB_OK) return rc;
+    rc = make_tmap_2d_f32(&tm_alo, a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
+    if (rc != DGGB_OK) return rc;
+  }
   tm_b2 = tm_b, tm_ahi2 = tm_ahi, tm_alo2 = tm_alo;
   int m_tiles2 = 0;
   if (s2.b != nullptr) {
     rc = make_tmap_2d_f32(&tm_b2, s2.b, (uint64_t)n, (uint64_t)s2.q, 32, 32);
     if (rc != DGGB_OK) return rc;
-    rc = make_tmap_2d_f32(&tm_ahi2, s2.a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
-    if (rc != DGGB_OK) return rc;
-    rc = make_tmap_2d_f32(&tm_alo2, s2.a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
-    if (rc != DGGB_OK) return rc;
+    if (stack) {
+      rc = make_tmap_2d_f32(&tm_ahi2, s2.a_hi, (uint64_t)2 * P, (uint64_t)npad, 2 * P, 32);
+      if (rc != DGGB_OK) return rc;
+      tm_alo2 = tm_ahi2;
+    } else {
+      rc = make_tmap_2d_f32(&tm_ahi2, s2.a_hi, (uint64_t)P, (uint64_t)npad, P, 32);
+      if (rc != DGGB_OK) return rc;
+      rc = make_tmap_2d_f32(&tm_alo2, s2.a_lo, (uint64_t)P, (uint64_t)npad, P, 32);
+      if (rc != DGGB_OK) return rc;
+    }
     m_tiles2 = (s2.q + kTcM - 1) / kTcM;
   }
   const int m_tiles1 = (q + kTcM - 1) / kTcM;
@@ -264,10 +307,21 @@ static int launch_tn_gemm(const float* a_hi, const float* a_lo, int npad, const 
   const int kb_per_split = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per_split - 1) / kb_per_split;
   const size_t smem = kTcStages * (4 * 4096 + 2 * P * 128) + 256 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if constexpr (P <= 64) {
+    if (stack) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return cuda_status(e);
+      launch_pdl((gemm_tn_tf32x3_kernel<P, true>), dim3(m_tiles, splits), dim3(kTcThreads), smem, st, tm_b, tm_ahi,
+                 tm_alo, n, q, kb_per_split, out, m_tiles1, tm_b2, tm_ahi2, tm_alo2, s2.q, s2.out);
+      return launch_status();
+    }
+  }
+  cudaError_t e = cudaFuncSetAttribute(gemm_tn_tf32x3_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
   if (e != cudaSuccess) return cuda_status(e);
-  launch_pdl(gemm_tn_tf32x3_kernel<P>, dim3(m_tiles, splits), dim3(kTcThreads), smem, st, tm_b, tm_ahi, tm_alo, n, q,
-             kb_per_split, out, m_tiles1, tm_b2, tm_ahi2, tm_alo2, s2.q, s2.out);
+  launch_pdl((gemm_tn_tf32x3_kernel<P, false>), dim3(m_tiles, splits), dim3(kTcThreads), smem, st, tm_b, tm_ahi, tm_alo,
+             n, q, kb_per_split, out, m_tiles1, tm_b2, tm_ahi2, tm_alo2, s2.q, s2.out);
   return launch_status();
 }
 
