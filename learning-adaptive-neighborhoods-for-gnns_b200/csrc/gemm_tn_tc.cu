@@ -103,20 +103,21 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int kb_total = (n + 31) / 32;
   const int num_kb = max(0, min(kb_per_split, kb_total - kb_begin));
 
-  if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&tm_b);
-    tc::tma_prefetch_desc(&tm_ahi);
-    tc::tma_prefetch_desc(&tm_alo);
-    for (int s = 0; s < kTcStages; ++s) {
-      tc::mbar_init(full + s, 1);
-      tc::mbar_init(empty + s, 5);
+  if (warp == 0) {
+    constexpr int kNumBars = 2 * kTcStages + 5;      // full | empty | a_full[2] | a_empty[2] | acc_full: one per lane
+    if (lane < kNumBars) {
+      uint32_t count = 1;
+      if (lane >= kTcStages && lane < 2 * kTcStages) count = 5;                   // empty: 4 converter warps + commit
+      else if (lane >= 2 * kTcStages && lane < 2 * kTcStages + 2) count = 4;      // a_full: 4 converter warps
+      tc::mbar_init(bars + lane, count);
     }
-    for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(a_full + s, 4);
-      tc::mbar_init(a_empty + s, 1);
-    }
-    tc::mbar_init(acc_full, 1);
     tc::fence_barrier_init();
+    __syncwarp();
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tm_b);
+      tc::tma_prefetch_desc(&tm_ahi);
+      tc::tma_prefetch_desc(&tm_alo);
+    }
   }
   if (warp == 1) {
     tc::tmem_alloc(tmem_slot, kTmemCols);

@@ -147,27 +147,24 @@ __global__ void __launch_bounds__(kLinThreads, 1)
     tc::tma_load_2d(smem + XS * kXBytes + s * kWStage, &tm_w, w_full + s, (kb0 + kb) * 32, 0);
   };
 
+  if (warp == 0) {
+    // one barrier per lane (26 serial mbarrier.init by one thread were ~700 of the ~1 500 cycles before the first TMA)
+    constexpr int kNumBars = 2 * XS + 2 * WS + 2 * kAB + 4;
+    static_assert(kNumBars <= 32, "one barrier per lane of warp 0");
+    if (lane < kNumBars) {
+      uint32_t count = 1;                                                     // TMA / commit barriers
+      if (lane >= XS && lane < 2 * XS) count = 5;                             // x_empty: 4 converter warps + hi commit
+      else if (lane >= 2 * XS + 2 * WS && lane < 2 * XS + 2 * WS + kAB) count = 4;   // a_full: 4 converter warps
+      else if (lane == kNumBars - 2) count = 4;                               // a2_full: 4 epilogue warps
+      tc::mbar_init(bars + lane, count);
+    }
+    tc::fence_barrier_init();
+    __syncwarp();
+  }
   if (warp == 0 && lane == 0) {
     if (tc::smem_u32(smem) & 1023u) __trap();      // 128-B swizzle atoms need a 1024-B aligned window
     tc::tma_prefetch_desc(&tm_x);
     tc::tma_prefetch_desc(&tm_w);
-    for (int s = 0; s < XS; ++s) {
-      tc::mbar_init(x_full + s, 1);
-      tc::mbar_init(x_empty + s, 5);
-    }
-    for (int s = 0; s < WS; ++s) {
-      tc::mbar_init(w_full + s, 1);
-      tc::mbar_init(w_empty + s, 1);
-    }
-    for (int s = 0; s < kAB; ++s) {
-      tc::mbar_init(a_full + s, 4);
-      tc::mbar_init(a_empty + s, 1);
-    }
-    tc::mbar_init(acc_full, 1);
-    tc::mbar_init(w2_full, 1);
-    tc::mbar_init(a2_full, 4);
-    tc::mbar_init(acc2_full, 1);
-    tc::fence_barrier_init();
     // The preceding grid is split_w_kernel of the same call, which triggers this launch only AFTER its own
     // dependency wait: x (and everything else older than the split) is complete and visible, only the split W is not.
     // The first round of both rings needs no "empty" wait: x goes in flight right away, W after the wait.
@@ -424,8 +421,9 @@ __global__ void __launch_bounds__(kLinThreads, 1)
           v.x = v.x > 0.f ? v.x : slope * v.x; v.y = v.y > 0.f ? v.y : slope * v.y;
           v.z = v.z > 0.f ? v.z : slope * v.z; v.w = v.w > 0.f ? v.w : slope * v.w;
         }
+        // (chained form: x_enc leaves for global memory later, while the second GEMM's MMAs run)
         if (row >= n) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        else if (out != nullptr) *reinterpret_cast<float4*>(out + (size_t)row * H + ec) = v;
+        else if (!FUSE2 && out != nullptr) *reinterpret_cast<float4*>(out + (size_t)row * H + ec) = v;
         // the finished tile goes back to the staging slice for the chained GEMM / the transposed copy
         if (FUSE2 || outT_hi != nullptr) *reinterpret_cast<float4*>(stg + lr * kPitch + ec) = v;
       }
@@ -501,6 +499,15 @@ __global__ void __launch_bounds__(kLinThreads, 1)
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a2_full);
+      // the activated tile (still in the staging slice) -> out, overlapped with the chained MMAs
+#pragma unroll 4
+      for (int it = 0; it < kIters; ++it) {
+        const int lr = it * kRowsPerIt + er;
+        const int row = row0 + q * 32 + lr;
+        if (row < n)
+          *reinterpret_cast<float4*>(out + (size_t)row * H + ec) = *reinterpret_cast<const float4*>(stg + lr * kPitch + ec);
+      }
+      __syncwarp();                                  // stg is overwritten by the second drain below
       tc::mbar_wait(acc2_full, 0);
       if (threadIdx.x == 64) LTRACE(4);
       tc::fence_after_sync();
