@@ -1029,7 +1029,7 @@ def kernel_roofline(m, dsets, shape, iters=30):
          E * (8 + h * 4) + n * h * 4 + n * 4),
         ("spmm_bwd_kernel (F=64, dA + dX)", lambda i: check(L.dggb_spmm_csr_bwd(p(G(i).rowptr), p(G(i).col), p(vals[i % N_SETS]), n, p(feats[i % N_SETS]), h, None, p(gys), p(dval), p(dx), stream()), "spmm_bwd"),
          E * (8 + h * 4) + n * h * 4 + E * (h * 4 + 4) + n * 4),
-        ("spmm_gemm_fwd_kernel (SpMM + W 64x64 + ReLU)", lambda i: check(L.dggb_spmm_gemm_fwd(p(G(i).rowptr), p(G(i).col), p(vals[i % N_SETS]), n, p(feats[i % N_SETS]), h, None, None, 1.0, 0.0, p(w64), h, 1.0, 0.0, None, 1, p(y_sp), p(s_out), stream()), "spmm_gemm"),
+        ("spmm_gemm_fwd_kernel (SpMM + W 64x64 + ReLU)", lambda i: check(L.dggb_spmm_gemm_fwd(p(G(i).rowptr), p(G(i).col), p(vals[i % N_SETS]), n, p(feats[i % N_SETS]), h, None, None, 1.0, 0.0, p(w64), h, 1.0, 0.0, None, 1, None, p(y_sp), p(s_out), stream()), "spmm_gemm"),
          E * (8 + h * 4) + 2 * n * h * 4 + n * 4 + h * h * 4),
         ("row_firstk_fwd_kernel (in-row rank + soft first-k)", lambda i: check(L.dggb_row_firstk_fwd(p(G(i).rowptr), n, p(vals[i % N_SETS]), p(ks), 0, p(rk), p(fo), None, stream()), "firstk"),
          E * 12 + n * 8),

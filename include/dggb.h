@@ -249,16 +249,22 @@ int dggb_spmm_edge_bwd(const int32_t* erow, const int32_t* col, const float* val
  * bwd (gy = dL/dy already masked by the ReLU): ds_i = theta * (gy_i W^T) + beta * gy_i  -> ds_out [N, Fin] =
  * ds_scale * ds (d h0 = c2 * ds: pass ds_scale = c2), dval_e = rs_i c1 <ds_i, x_col> (OVERWRITTEN; NULL: skipped),
  * dx_col += a_e rs_i c1 ds_i (ACCUMULATED).  zero_ws / zero_count: optional fp32 buffer cleared by this launch (the
- * split-K accumulator of the weight gradient that follows).
+ * split-K accumulator of the weight gradient that follows).  relu_y [N, Fout] (or NULL): the forward's ReLU output --
+ * gy is then the UNMASKED upstream gradient and the kernel applies the threshold itself; gy_masked [N, Fout] (or NULL)
+ * receives the masked gradient (what the weight gradient needs).
+ * out_keep [N, Fout] (or NULL, both directions): dropout multipliers (0 or 1 / (1 - p)) applied to the layer OUTPUT,
+ * y = act(...) * out_keep -- the F.dropout in front of the NEXT GCNII layer (model.py:725) and its backward are two
+ * launches per layer and direction otherwise; the backward takes gy = dL/dy of that dropped output.
  * ---------------------------------------------------------------------------------- */
 int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
                        int32_t fin, const float* row_scale, const float* h0, float c1, float c2, const float* w,
-                       int32_t fout, float theta, float beta, const float* resid, int32_t relu, float* y,
-                       float* s_out, void* stream);
+                       int32_t fout, float theta, float beta, const float* resid, int32_t relu,
+                       const float* out_keep, float* y, float* s_out, void* stream);
 int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
                        int32_t fin, const float* row_scale, float c1, const float* w, int32_t fout, float theta,
                        float beta, const float* gy, float* dval, float* dx, float* ds_out, float ds_scale,
-                       float* zero_ws, int64_t zero_count, void* stream);
+                       float* zero_ws, int64_t zero_count, const float* relu_y, float* gy_masked,
+                       const float* out_keep, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)

@@ -24,6 +24,7 @@ template <> struct Vec<4> {
     v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
   }
   __device__ __forceinline__ void red(float* p, float a) const { red_add4(p, make_float4(a * v.x, a * v.y, a * v.z, a * v.w)); }
+  __device__ __forceinline__ void mul(const Vec& o) { v.x *= o.v.x; v.y *= o.v.y; v.z *= o.v.z; v.w *= o.v.w; }
 };
 template <> struct Vec<2> {
   float2 v;
@@ -338,6 +339,9 @@ struct SpmmGemmArgs {
   const float* resid;    // [n, fout] or NULL
   float c1, c2, theta, beta;
   int relu;
+  const float* okeep;    // [n, fout] or NULL: dropout multipliers (0 or 1/(1-p)) applied to the layer OUTPUT in the
+                         // epilogue (the next layer's F.dropout(input) and its backward are two launches per layer and
+                         // direction otherwise; a per-row product, not a per-entry gather)
 };
 
 // RB = rows per warp iteration: the W tile is read from shared memory once per RB rows (RB = 4: large graphs, the
@@ -517,6 +521,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         if (A.beta != 0.f) v = fmaf(A.beta, srows[r * A.fin + c], v);      // fout == fin (checked on the host)
         v += rsv[r][q];
         if (A.relu) v = fmaxf(v, 0.f);
+        if (A.okeep) v *= __ldg(A.okeep + (size_t)i * A.fout + c);
         y[(size_t)i * A.fout + c] = v;
       }
     }
@@ -603,6 +608,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       if (A.beta != 0.f) v = fmaf(A.beta, srow[c], v);                     // fout == fin (checked on the host)
       v += rsv[q];
       if (A.relu) v = fmaxf(v, 0.f);
+      if (A.okeep) v *= __ldg(A.okeep + (size_t)i * A.fout + c);
       y[(size_t)i * A.fout + c] = v;
     }
   }
@@ -612,7 +618,7 @@ template <int T, int Q, int RB>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp)
     spmm_gemm_bwd_kernel(SpmmGemmArgs A, const float* __restrict__ gy, float* __restrict__ dval,
                          float* __restrict__ dx, float* __restrict__ ds_out, float ds_scale, float* zero_ws,
-                         long long zero_count) {
+                         long long zero_count, const float* __restrict__ relu_y, float* __restrict__ gy_masked) {
   constexpr int R = kSpmmWarps * RB;
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
@@ -653,7 +659,16 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
   }
   for (int c = threadIdx.x; c < R * fo4; c += blockDim.x) {
     const int r = c / fo4, o = c % fo4, i = r0 + r;
-    Gs[c] = (i < A.n && o < A.fout) ? __ldg(gy + (size_t)i * A.fout + o) : 0.f;
+    float gv = 0.f;
+    if (i < A.n && o < A.fout) {
+      gv = __ldg(gy + (size_t)i * A.fout + o);
+      // the layer's ReLU backward (threshold on the forward output) folded in; the masked gradient also leaves for
+      // the weight gradient dW = (theta s)^T gy that follows
+      if (A.okeep) gv *= __ldg(A.okeep + (size_t)i * A.fout + o);        // y = act(z) * keep
+      if (relu_y != nullptr && __ldg(relu_y + (size_t)i * A.fout + o) <= 0.f) gv = 0.f;
+      if (gy_masked != nullptr) gy_masked[(size_t)i * A.fout + o] = gv;
+    }
+    Gs[c] = gv;
   }
   __syncthreads();
   const int eb0 = rp[0], eb1 = rp[nr];
@@ -824,8 +839,10 @@ static int spmm_gemm_check(const SpmmGemmArgs& A) {
 extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
                                   const float* x, int32_t fin, const float* row_scale, const float* h0, float c1,
                                   float c2, const float* w, int32_t fout, float theta, float beta,
-                                  const float* resid, int32_t relu, float* y, float* s_out, void* stream) {
-  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, h0, w, resid, c1, c2, theta, beta, relu};
+                                  const float* resid, int32_t relu, const float* out_keep, float* y, float* s_out,
+                                  void* stream) {
+  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, h0, w, resid, c1, c2, theta, beta, relu, out_keep};
+  if (out_keep && ((uintptr_t)out_keep % 16)) return DGGB_ERR_BAD_ARG;
   int rc = spmm_gemm_check(A);
   if (rc != DGGB_OK) return rc;
   if (!y || (s_out && ((uintptr_t)s_out % 16))) return DGGB_ERR_BAD_ARG;
@@ -855,8 +872,10 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
 extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
                                   const float* x, int32_t fin, const float* row_scale, float c1, const float* w,
                                   int32_t fout, float theta, float beta, const float* gy, float* dval, float* dx,
-                                  float* ds_out, float ds_scale, float* zero_ws, int64_t zero_count, void* stream) {
-  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, nullptr, w, nullptr, c1, 0.f, theta, beta, 0};
+                                  float* ds_out, float ds_scale, float* zero_ws, int64_t zero_count,
+                                  const float* relu_y, float* gy_masked, const float* out_keep, void* stream) {
+  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, nullptr, w, nullptr, c1, 0.f, theta, beta, 0, out_keep};
+  if (out_keep && ((uintptr_t)out_keep % 16)) return DGGB_ERR_BAD_ARG;
   int rc = spmm_gemm_check(A);
   if (rc != DGGB_OK) return rc;
   if (!gy || (dx && ((uintptr_t)dx % 16)) || zero_count < 0) return DGGB_ERR_BAD_ARG;
@@ -872,7 +891,7 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (n + kSpmmWarps * rb - 1) / (kSpmmWarps * rb);
     launch_pdl(kern, dim3(grid), dim3(kSpmmWarps * kWarp), smem, as_stream(stream), A, gy, dval, dx, ds_out, ds_scale,
-               zero_ws, (long long)zero_count);
+               zero_ws, (long long)zero_count, relu_y, gy_masked);
     return launch_status();
   };
   const int Q = fin <= 32 ? 1 : (fin <= 64 ? 2 : 4);

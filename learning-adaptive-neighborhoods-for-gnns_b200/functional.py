@@ -191,9 +191,10 @@ class _SpmmGemm(torch.autograd.Function):
     (GCNConv model.py:594-598; GraphConvolution model.py:32-44, 65-77); see include/dggb.h."""
 
     @staticmethod
-    def forward(ctx, vals, x, w, h0, resid, graph: CSRGraph, row_scale, c1, c2, theta, beta, relu):
-        _require_cuda(vals, x, w, h0, resid)
+    def forward(ctx, vals, x, w, h0, resid, graph: CSRGraph, row_scale, c1, c2, theta, beta, relu, out_keep):
+        _require_cuda(vals, x, w, h0, resid, out_keep)
         vals, x, w = _f32c(vals), _f32c(x), _f32c(w)
+        out_keep = None if out_keep is None else _f32c(out_keep)
         h0 = None if h0 is None else _f32c(h0)
         resid = None if resid is None else _f32c(resid)
         n, fin, fout = graph.n, x.shape[1], w.shape[1]
@@ -202,20 +203,18 @@ class _SpmmGemm(torch.autograd.Function):
         s = torch.empty(n, fin, dtype=torch.float32, device=x.device) if need_s else None
         check(lib().dggb_spmm_gemm_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(n), p(x), i32(fin), p(row_scale),
                                        p(h0), float(c1), float(c2 if h0 is not None else 0.0), p(w), i32(fout),
-                                       float(theta), float(beta), p(resid), i32(1 if relu else 0), p(y), p(s),
-                                       stream()), "spmm_gemm_fwd")
+                                       float(theta), float(beta), p(resid), i32(1 if relu else 0), p(out_keep), p(y),
+                                       p(s), stream()), "spmm_gemm_fwd")
         ctx.graph, ctx.meta = graph, (c1, c2, theta, beta, relu, h0 is not None, resid is not None)
-        ctx.save_for_backward(vals, x, w, row_scale, s, y if relu else None)
+        ctx.save_for_backward(vals, x, w, row_scale, s, y if relu else None, out_keep)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        vals, x, w, row_scale, s, y = ctx.saved_tensors
+        vals, x, w, row_scale, s, y, out_keep = ctx.saved_tensors
         c1, c2, theta, beta, relu, has_h0, has_resid = ctx.meta
         g = ctx.graph
         gy = _f32c(gy)
-        if relu:
-            gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
         need_v, need_x, need_w, need_h0 = ctx.needs_input_grad[:4]
         dval = torch.empty_like(vals) if need_v else None
         dx = torch.zeros_like(x) if need_x else None
@@ -225,21 +224,35 @@ class _SpmmGemm(torch.autograd.Function):
         dwbuf = (torch.empty(w.numel(), dtype=torch.float32, device=x.device)
                  if (need_w and launch and w.shape[1] % 4 == 0) else None)
         if launch:
+            # the ReLU backward runs inside the layer's launch (relu_y = forward output); the masked gradient comes
+            # back for dW and for a residual branch
+            fold = relu or out_keep is not None
+            gm = torch.empty_like(gy) if (fold and (need_w or has_resid)) else None
             check(lib().dggb_spmm_gemm_bwd(p(g.rowptr), p(g.col), p(vals), i32(g.n), p(x), i32(x.shape[1]),
                                            p(row_scale), float(c1), p(w), i32(w.shape[1]), float(theta), float(beta),
                                            p(gy), p(dval), p(dx), p(ds), float(c2), p(dwbuf),
-                                           i64(0 if dwbuf is None else dwbuf.numel()), stream()), "spmm_gemm_bwd")
+                                           i64(0 if dwbuf is None else dwbuf.numel()), p(y if relu else None), p(gm),
+                                           p(out_keep), stream()), "spmm_gemm_bwd")
+            if gm is not None:
+                gy = gm
+        else:
+            if out_keep is not None:
+                gy = gy * out_keep
+            if relu:
+                gy = torch.ops.aten.threshold_backward(gy, y, 0.0)
         dw = None
         if need_w:
             dw = gemm_tn(s, gy, False, zeroed=dwbuf)[0]       # s was saved as theta * s
         dh0 = ds
         dres = gy if (has_resid and ctx.needs_input_grad[4]) else None
-        return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None
+        return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None, None
 
 
-def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2=0.0, theta=1.0, beta=0.0, relu=False):
-    """act(theta * (s W) + beta * s + resid) with s = c1 * rs * (A x) + c2 * h0; None if the shape is outside the
-    fused kernel's range (Fin % 4 != 0, Fin or Fout > 128)."""
+def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2=0.0, theta=1.0, beta=0.0, relu=False,
+              out_keep=None):
+    """act(theta * (s W) + beta * s + resid) * out_keep with s = c1 * rs * (A x) + c2 * h0; None if the shape is outside
+    the fused kernel's range (Fin % 4 != 0, Fin or Fout > 128).  out_keep: optional dropout multipliers
+    (0 or 1 / (1 - p)) of the layer OUTPUT (the dropout in front of the next layer), applied in the epilogue."""
     fin, fout = x.shape[1], w.shape[1]
     if not (x.is_cuda and fin % 4 == 0 and fin <= 128 and fout <= 128 and (beta == 0.0 or fin == fout)):
         return None
@@ -248,7 +261,7 @@ def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2
     if graph.n >= _FUSED_CONV_MAX_N:
         return None
     return _SpmmGemm.apply(vals, x, w, h0, resid, graph, row_scale, float(c1), float(c2), float(theta), float(beta),
-                           bool(relu))
+                           bool(relu), out_keep)
 
 
 class _AllPairsTopK(torch.autograd.Function):

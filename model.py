@@ -198,18 +198,20 @@ class GraphConvolution(nn.Module):
         stdv = 1.0 / math.sqrt(self.out_features)
         self.weight.data.uniform_(-stdv, stdv)
 
-    def forward(self, input, adj, h0, lamda, alpha, l, act=None):
+    def forward(self, input, adj, h0, lamda, alpha, l, act=None, out_keep=None):
         """``act="relu"``: the caller's activation (GCNII applies ``act_fn`` to every layer output, model.py:728)
-        is folded into the fused kernel."""
+        is folded into the fused kernel.  ``out_keep``: dropout multipliers (0 or 1 / (1 - p)) of the layer OUTPUT --
+        the caller's ``F.dropout`` in front of the next layer (model.py:725) applied in this layer's epilogue."""
         theta = math.log(lamda / l + 1)
         if adj.is_sparse and not self.variant:
             g, v = CSRGraph.from_coo(adj)
             out = K.spmm_gemm(v, input, self.weight, g, h0=h0, resid=input if self.residual else None, c1=1 - alpha,
-                              c2=alpha, theta=theta, beta=1 - theta, relu=(act == "relu"))
+                              c2=alpha, theta=theta, beta=1 - theta, relu=(act == "relu"), out_keep=out_keep)
             if out is not None:
                 return out
         out = self._forward_unfused(input, adj, h0, theta, alpha)
-        return torch.relu(out) if act == "relu" else out
+        out = torch.relu(out) if act == "relu" else out
+        return out if out_keep is None else out * out_keep
 
     def _forward_unfused(self, input, adj, h0, theta, alpha):
         hi = _aggregate(adj, input)
@@ -267,14 +269,24 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
         _layers.append(layer_inner)
         in_adj = add_self_loops_coo(in_adj)
         unnorm_adj = in_adj
+        keeps = None
+        if self.training and self.dropout > 0 and x.is_cuda:
+            # the F.dropout(layer_inner) after every layer of the reference (model.py:725, 729): all layers' multipliers
+            # in ONE draw, applied in each layer's epilogue (two launches per layer and direction otherwise)
+            keeps = torch.empty(len(self.convs), layer_inner.shape[0], layer_inner.shape[1],
+                                device=x.device).bernoulli_(1.0 - self.dropout).mul_(1.0 / (1.0 - self.dropout))
+            layer_inner = F.dropout(layer_inner, self.dropout, training=True)
         for i, con in enumerate(self.convs):
             if i < len(self.dggs):
                 src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
                 unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
                 norm_adj = self.normalize_adj(unnorm_adj)
+            if keeps is None:
+                layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+            layer_inner = con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1, act="relu",
+                              out_keep=None if keeps is None else keeps[i])
+        if keeps is None:
             layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
-            layer_inner = con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1, act="relu")
-        layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
         layer_inner = self.fcs[-1](layer_inner)
         return F.log_softmax(layer_inner, dim=1)
 

@@ -28,13 +28,13 @@ def gt(fn, k=20):
     e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / (50 * k) * 1e3
 print("N", n, "E", E)
 print("spmm_csr_fwd        %.2f us" % gt(lambda: check(L.dggb_spmm_csr_fwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, P(y), stream()), "a")))
-print("spmm_gemm_fwd       %.2f us" % gt(lambda: check(L.dggb_spmm_gemm_fwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, P(x), 0.9, 0.1, P(w), h, 0.4, 0.6, None, 1, P(y), P(s), stream()), "b")))
+print("spmm_gemm_fwd       %.2f us" % gt(lambda: check(L.dggb_spmm_gemm_fwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, P(x), 0.9, 0.1, P(w), h, 0.4, 0.6, None, 1, None, P(y), P(s), stream()), "b")))
 def efwd():
     y.zero_()
     check(L.dggb_spmm_edge_fwd(P(g.rowptr), P(g.erow), P(g.col), P(v), n, E, P(x), h, None, P(y), stream()), "e")
 print("spmm_edge_fwd+zero  %.2f us" % gt(efwd))
 print("spmm_csr_bwd        %.2f us" % gt(lambda: check(L.dggb_spmm_csr_bwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, P(gy), P(dv), P(dx), stream()), "c")))
 print("spmm_edge_bwd       %.2f us" % gt(lambda: check(L.dggb_spmm_edge_bwd(P(g.erow), P(g.col), P(v), E, P(x), h, None, P(gy), P(dv), P(dx), stream()), "c")))
-print("spmm_gemm_bwd       %.2f us" % gt(lambda: check(L.dggb_spmm_gemm_bwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, 0.9, P(w), h, 0.4, 0.6, P(gy), P(dv), P(dx), P(ds), 0.1, None, 0, stream()), "d")))
+print("spmm_gemm_bwd       %.2f us" % gt(lambda: check(L.dggb_spmm_gemm_bwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, 0.9, P(w), h, 0.4, 0.6, P(gy), P(dv), P(dx), P(ds), 0.1, None, 0, None, None, None, stream()), "d")))
 print("torch mm            %.2f us" % gt(lambda: torch.mm(x, w, out=y)))
 print("torch add           %.2f us" % gt(lambda: torch.add(x, gy, out=y)))

@@ -493,3 +493,37 @@ def test_head_dots_weight_gradient_through_splitk_kernel():
     torch.testing.assert_close(pq, ref.float(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(dh, rdh.float(), rtol=1e-5, atol=1e-5)
     assert float((da.double() - rda).abs().max()) <= 1e-5 * float(rda.abs().max())
+
+
+@pytest.mark.parametrize("n,avg_deg,relu", [(3000, 5, True), (777, 30, False)])
+def test_spmm_gemm_keep_mask_and_folded_relu_match_explicit_ops(n, avg_deg, relu):
+    """GCNII layer with the following dropout applied in the epilogue (out_keep multipliers) and the ReLU backward
+    folded into the backward launch, against the same layer followed by ``* keep`` through autograd."""
+    from dgg_b200 import CSRGraph, functional as K
+
+    gen = torch.Generator().manual_seed(n)
+    m = n * avg_deg
+    a = torch.sparse_coo_tensor(torch.stack([torch.randint(0, n, (m,), generator=gen), torch.randint(0, n, (m,), generator=gen)]),
+                                torch.ones(m), (n, n)).coalesce()
+    g = CSRGraph.from_indices(a.indices().cuda(), n)
+    h = 64
+    v = (torch.rand(g.nnz, generator=gen) + 0.1).cuda()
+    x = torch.randn(n, h, generator=gen).cuda()
+    h0 = torch.randn(n, h, generator=gen).cuda()
+    w = (torch.randn(h, h, generator=gen) / 8).cuda()
+    keep = (torch.rand(n, h, generator=gen) > 0.4).float().cuda() / 0.6
+    wl = torch.randn(n, h, generator=gen).cuda()
+
+    def run(fused_keep):
+        ps = [t.clone().requires_grad_(True) for t in (v, x, w, h0)]
+        y = K.spmm_gemm(ps[0], ps[1], ps[2], g, h0=ps[3], c1=0.9, c2=0.1, theta=0.4, beta=0.6, relu=relu,
+                        out_keep=keep if fused_keep else None)
+        if not fused_keep:
+            y = y * keep
+        (y * wl).sum().backward()
+        return y.detach(), [q.grad for q in ps]
+
+    (ya, ga), (yb, gb) = run(True), run(False)
+    torch.testing.assert_close(ya, yb, rtol=1e-5, atol=1e-5)
+    for qa, qb in zip(ga, gb):
+        torch.testing.assert_close(qa, qb, rtol=2e-4, atol=2e-5)
