@@ -96,6 +96,11 @@ __device__ __forceinline__ float sqrt_fast(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // g = -scale * log(E), E = -log1p(-v) ~ Exp(1), v = ((x >> 8) + 0.5) 2^-24 in (0,1).
 // The LARGE Gumbel values (small v, small E) are the ones top-k keeps, so E must be accurate exactly
 // there: series for v < 2^-6, fast log otherwise (|dg| <~ 2e-5 either way).
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
                           const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
                           unsigned long long seed, float noise_scale, int kc, int stages, int qcap, int qflush,
                           int32_t* __restrict__ out_idx, float* __restrict__ out_val, float inv_temp,
-                          float* __restrict__ out_rowsum) {
+                          float* __restrict__ out_rowsum, int no_prefilter) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const AP2Smem L = ap2_smem_layout(KB, SPLIT, stages, kc, qcap);   // queue: qcap >= qflush - 1 + kChunk slots
@@ -665,6 +670,11 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
     float zsum = 0.f;
     const float* nz = (NOISE == 1 && row_ok) ? noise + (size_t)lrow * noise_ld : nullptr;
     const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    // candidate pre-filter of the Philox path (see the streaming loop): log2(e) / scale; off for a degenerate scale and,
+    // per row, while |thr| is so large that the rounding of base - thr could exceed the filter's margin
+    const float pf_k = 1.4426950408889634f / noise_scale;
+    const bool pf_scale_ok = NOISE == 2 && noise_scale > 1e-20f && noise_scale < 1e20f && !no_prefilter;
+    bool prefilter = pf_scale_ok;
     auto flush = [&](unsigned need) {
       __syncwarp();
       while (need) {
@@ -675,6 +685,7 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
         if (lane == src) {
           thr = kth;
           qn = 0;
+          prefilter = pf_scale_ok && !(fabsf(kth) > 3e4f * noise_scale && kth > -INFINITY);
         }
       }
       __syncwarp();
@@ -707,6 +718,42 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
             }
             uint4 bits = make_uint4(0u, 0u, 0u, 0u);
             unsigned pass = 0u;
+            if (NOISE == 2 && prefilter) {
+              // Philox noise, two steps.  y = base + g > thr needs g > thr - base, and g = -scale log(E) with
+              // E = -log1p(-v) >= v, so a candidate must have v < exp((base - thr) / scale): ONE ex2 per score decides
+              // (with a 2^-7 relative margin over the rounding of base, thr and the fast logs) whether the two logs of
+              // the Gumbel transform are evaluated at all.  Once a row's list is warm that is ~Kc / N of the scores;
+              // the survivors take exactly the arithmetic of the one-step path, so the selection is unchanged.
+              uint32_t xb[kChunk];
+              const float tk = -thr * pf_k;               // thr = -inf (cold list): +inf, every score is a candidate
+#pragma unroll
+              for (int c = 0; c < kChunk; ++c) {
+                const int j = jbase + c;
+                float d2 = fmaf(-2.f, __uint_as_float(r[c]), ni + njv[c]);
+                if (decltype(diag_c)::value && j == row_begin + lrow) d2 = 0.f;
+                y[c] = -t * sqrt_fast(fmaxf(d2, 0.f));
+                if ((c & 3) == 0) bits = philox4x32_7((uint32_t)(row_begin + lrow), (uint32_t)(j >> 2), key0, key1);
+                xb[c] = (c & 3) == 0 ? bits.x : ((c & 3) == 1 ? bits.y : ((c & 3) == 2 ? bits.z : bits.w));
+                // v floored to 23 bits (<= v): exponent of 1.0 | mantissa, minus 1 -- no integer conversion
+                const float vq = __uint_as_float(0x3f800000u | (xb[c] >> 9)) - 1.0f;
+                const float u = ex2_fast(fmaf(y[c], pf_k, tk)) * 1.0078125f;
+                pass |= (vq < u) ? (1u << c) : 0u;
+              }
+              if (pass) {
+#pragma unroll
+                for (int c = 0; c < kChunk; ++c) {
+                  if (pass & (1u << c)) {
+                    const float yy = y[c] + gumbel_from_bits(xb[c], noise_scale);
+                    if (jbase + c < n && yy > thr) {
+                      qv[qn * kBM + row_t] = yy;
+                      qi[qn * kBM + row_t] = jbase + c;
+                      ++qn;
+                    }
+                  }
+                }
+              }
+              return;
+            }
 #pragma unroll
             for (int c = 0; c < kChunk; ++c) {
               const int j = jbase + c;
@@ -908,6 +955,7 @@ extern "C" int dggb_allpairs_topk_after_fwd(const float* z, int32_t n, int32_t d
     if (L2.total + 1024 <= 227 * 1024) {
       const size_t smem2 = L2.total + 1024;
       const int grid2 = (row_count + kBM - 1) / kBM;
+      const int no_pf = getenv("DGGB_AP_NO_PREFILTER") ? 1 : 0;     // A/B switch: one-step Philox scoring
 #define DGGB_AP2_LAUNCH1(KB_, SP_, NM_)                                                                           \
   do {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(allpairs_topk2_kernel<KB_, SP_, NM_>,                                    \
@@ -915,7 +963,8 @@ extern "C" int dggb_allpairs_topk_after_fwd(const float* z, int32_t n, int32_t d
     if (e != cudaSuccess) return cuda_status(e);                                                                  \
     allpairs_topk2_kernel<KB_, SP_, NM_><<<grid2, kAP2Threads, smem2, st>>>(                                      \
         tm_hi, tm_lo, hi, lo, npad, dpad, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld,            \
-        (unsigned long long)seed, noise_scale, kc, st2, qcap, qflush, out_idx, out_val, inv_temp, out_rowsum);    \
+        (unsigned long long)seed, noise_scale, kc, st2, qcap, qflush, out_idx, out_val, inv_temp, out_rowsum,     \
+        no_pf);                                                                                                   \
   } while (0)
 #define DGGB_AP2_LAUNCH(KB_, SP_)                                                                                 \
   do {                                                                                                            \

@@ -150,3 +150,24 @@ def test_philox_noise_matches_host_restatement():
     # shards regenerate the same noise without communication
     idx_c, val_c = K.allpairs_topk(z, t, None, kc, 3, 256, 300, seed=seed, noise_scale=scale)
     assert torch.equal(idx_c, idx_a[256:556]) and torch.equal(val_c, val_a[256:556])
+
+
+@pytest.mark.parametrize("n,d,kc,t,scale,zmul", [(3000, 64, 32, 4.0, 1.0, 1.0),       # noise-dominated (tiny distances)
+                                                  (2500, 64, 16, 1.0, 1.0, 40.0),      # Reddit-bench-like: D ~ 6
+                                                  (1800, 32, 32, 30.0, 0.05, 60.0),    # distance-dominated
+                                                  (1500, 64, 8, -2.0, 0.5, 40.0),      # negative temperature
+                                                  (1200, 64, 32, 2000.0, 1.0, 40.0)])  # |thr| beyond the filter's range
+def test_philox_candidate_prefilter_selects_identically(n, d, kc, t, scale, zmul, monkeypatch):
+    """The two-step Philox scoring (one ex2 decides whether a score can enter the row's list before the Gumbel logs
+    are evaluated) returns bit-identical indices and values to the one-step path (DGGB_AP_NO_PREFILTER=1)."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(n + kc)
+    z = (torch.softmax(torch.randn(n, d, generator=gen), -1) * zmul).cuda()
+    tt = torch.tensor([t]).cuda()
+    monkeypatch.delenv("DGGB_AP_NO_PREFILTER", raising=False)
+    idx_a, val_a = K.allpairs_topk(z, tt, None, kc, 3, seed=77, noise_scale=scale)
+    monkeypatch.setenv("DGGB_AP_NO_PREFILTER", "1")
+    idx_b, val_b = K.allpairs_topk(z, tt, None, kc, 3, seed=77, noise_scale=scale)
+    assert torch.equal(idx_a, idx_b) and torch.equal(val_a, val_b)
+    assert int((idx_a >= 0).sum()) == n * kc
