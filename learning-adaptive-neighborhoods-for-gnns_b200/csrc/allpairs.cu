@@ -501,6 +501,11 @@ __global__ void __launch_bounds__(kAPThreads, 1)
 //     g+2 (double-buffered, so its MMA overlaps its own epilogue) and scores tiles jt = g, g+2, ... into its own
 //     per-row list/queue; the two sorted lists of a row are merged once at the end.
 //     10 warps: w0 TMA producer, w1 MMA issuer, w2-5 group 0, w6-9 group 1.  TMEM: 4 x 64 + 128 columns.
+//   * a key stage is released by the MMA commit alone: the column norms the epilogue reads travel in their own ring of
+//     stages + 4 slots (one mbarrier each).  The producer can be at most stages + 4 tiles ahead of the oldest tile an
+//     epilogue group still reads (stage <- MMA commit <- accumulator free <- epilogue of four tiles earlier), so a slot
+//     needs no "empty" barrier.  (With the norms inside the stage, a group held its stage for the whole scoring of a
+//     tile and the next load + MMA for its buffer arrived late: 16 % of the samples sat in that wait.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kAP2Threads = 320;
 
@@ -513,15 +518,15 @@ __host__ __device__ inline AP2Smem ap2_smem_layout(int kb, int split, int stages
   L.b0 = off;
   L.b_stage_bytes = kb * kBN * 128 * (split == 3 ? 2 : 1);
   off += L.b_stage_bytes * stages;
-  L.nrm = off; off += stages * kBN * 4;
+  L.nrm = off; off += (stages + 4) * kBN * 4;     // column-norm ring, see the kernel's header
   for (int g = 0; g < 2; ++g) {
     L.vals[g] = off; off += kc * kBM * 4;
     L.idx[g] = off; off += kc * kBM * 4;
     L.qv[g] = off; off += qcap * kBM * 4;
     L.qi[g] = off; off += qcap * kBM * 4;
   }
-  L.zpart = off; off += kBM * 4;
-  L.bars = off; off += 192;
+  L.zpart = L.qv[1];                              // group 1's queue is idle when the partial sums are exchanged
+  L.bars = off; off += 256;
   L.total = off;
   return L;
 }
@@ -540,11 +545,13 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
   const AP2Smem L = ap2_smem_layout(KB, SPLIT, stages, kc, qcap);   // queue: qcap >= qflush - 1 + kChunk slots
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* full = bars;            // [stages]  TMA -> MMA / epilogue
-  uint64_t* empty = bars + 4;       // [stages]  MMA commit + the 4 warps of the group that scored the tile
+  uint64_t* empty = bars + 4;       // [stages]  MMA commit -> TMA (the epilogue never touches a key stage)
   uint64_t* tfull = bars + 8;       // [4]       MMA -> epilogue group (accumulators g and g+2 belong to group g)
   uint64_t* tempty = bars + 12;     // [4]       epilogue group -> MMA
   uint64_t* aready = bars + 16;     // query tile written to TMEM (8 epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* nfull = bars + 18;      // [stages + 4 <= 8]  column norms of a tile landed
+  const int nslots = stages + 4;
   constexpr uint32_t kTmemCols = 512;   // 4 accumulators x 64 columns + the query tile (hi | lo)
   constexpr uint32_t kAHi = 4 * kBN, kALo = 4 * kBN + KB * 32;
 
@@ -557,13 +564,14 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
     if (SPLIT == 3) tc::tma_prefetch_desc(&tm_lo);
     for (int s = 0; s < stages; ++s) {
       tc::mbar_init(full + s, 1);
-      tc::mbar_init(empty + s, 5);
+      tc::mbar_init(empty + s, 1);
     }
     for (int b = 0; b < 4; ++b) {
       tc::mbar_init(tfull + b, 1);
       tc::mbar_init(tempty + b, 4);
     }
     tc::mbar_init(aready, 8);
+    for (int i = 0; i < nslots; ++i) tc::mbar_init(nfull + i, 1);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -578,17 +586,18 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
   if (warp == 0) {
     // ================= TMA producer: key tiles only =================
     if (lane == 0) {
-      int s = 0;
+      int s = 0, ns = 0;
       uint32_t ph = 0;
-      for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
+      for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0, (++ns == nslots) ? (ns = 0) : 0) {
         tc::mbar_wait_backoff(empty + s, ph ^ 1);
-        tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes + kBN * 4);
+        tc::mbar_arrive_expect_tx(nfull + ns, kBN * 4);
+        tc::bulk_load_1d(smem + L.nrm + ns * kBN * 4, nrm + (size_t)jt * kBN, kBN * 4, nfull + ns);
+        tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes);
         uint8_t* bs = smem + L.b0 + s * L.b_stage_bytes;
         for (int kb = 0; kb < KB; ++kb) {
           tc::tma_load_2d(bs + kb * kBN * 128, &tm_hi, full + s, kb * 32, jt * kBN);
           if (SPLIT == 3) tc::tma_load_2d(bs + (KB + kb) * kBN * 128, &tm_lo, full + s, kb * 32, jt * kBN);
         }
-        tc::bulk_load_1d(smem + L.nrm + s * kBN * 4, nrm + (size_t)jt * kBN, kBN * 4, full + s);
       }
     }
   } else if (warp == 1) {
@@ -690,16 +699,16 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       }
       __syncwarp();
     };
-    int s = g % stages;
-    uint32_t ph = (g / stages) & 1;
+    int ns = g;                                  // norm-ring slot of tile jt (== jt % nslots), and its phase
+    uint32_t nph = 0;
     int it = 0;
     for (int jt = g; jt < num_tiles; jt += 2, ++it) {
       const int buf = g + 2 * (it & 1);          // == jt & 3
       const uint32_t bph = (it >> 1) & 1;        // == (jt >> 2) & 1
-      tc::mbar_wait(full + s, ph);
+      tc::mbar_wait(nfull + ns, nph);
       tc::mbar_wait(tfull + buf, bph);
       tc::fence_after_sync();
-      const float* nj = reinterpret_cast<const float*>(smem + L.nrm + s * kBN * 4);
+      const float* nj = reinterpret_cast<const float*>(smem + L.nrm + ns * kBN * 4);
       const bool diag_tile = (jt * kBN < row0 + kBM) && (jt * kBN + kBN > row0);
 #pragma unroll 1
       for (int c0 = 0; c0 < kBN; c0 += kChunk) {
@@ -789,12 +798,9 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(tempty + buf);
-        tc::mbar_arrive(empty + s);
-      }
-      s += 2;
-      if (s >= stages) { s -= stages; ph ^= 1; }
+      if (lane == 0) tc::mbar_arrive(tempty + buf);
+      ns += 2;
+      if (ns >= nslots) { ns -= nslots; nph ^= 1; }
     }
     flush(__ballot_sync(0xffffffffu, qn > 0));
     // ---- merge the two groups' lists (named barrier over the 8 epilogue warps), group 0 writes out ----
