@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       int s = 0, ns = 0;
       uint32_t ph = 0;
       for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0, (++ns == nslots) ? (ns = 0) : 0) {
-        tc::mbar_wait_backoff(empty + s, ph ^ 1);
+        tc::mbar_wait_sleep(empty + s, ph ^ 1, 400);
         tc::mbar_arrive_expect_tx(nfull + ns, kBN * 4);
         tc::bulk_load_1d(smem + L.nrm + ns * kBN * 4, nrm + (size_t)jt * kBN, kBN * 4, nfull + ns);
         tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes);
@@ -611,8 +611,8 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0) {
         const int buf = jt & 3;
         const uint32_t bph = (jt >> 2) & 1;
-        tc::mbar_wait_backoff(tempty + buf, bph ^ 1);
-        tc::mbar_wait_backoff(full + s, ph);
+        tc::mbar_wait_sleep(tempty + buf, bph ^ 1, 200);
+        tc::mbar_wait_sleep(full + s, ph, 200);
         tc::fence_after_sync();
         const uint32_t b_hi = tc::smem_u32(smem + L.b0 + s * L.b_stage_bytes);
         const uint32_t b_lo = b_hi + KB * kBN * 128;
@@ -734,7 +734,8 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
               // the Gumbel transform are evaluated at all.  Once a row's list is warm that is ~Kc / N of the scores;
               // the survivors take exactly the arithmetic of the one-step path, so the selection is unchanged.
               uint32_t xb[kChunk];
-              const float tk = -thr * pf_k;               // thr = -inf (cold list): +inf, every score is a candidate
+              // thr = -inf (cold list): +inf, every score is a candidate; log2(1 + 2^-7) is the margin
+              const float tk = fmaf(-thr, pf_k, 0.011227255f);
 #pragma unroll
               for (int c = 0; c < kChunk; ++c) {
                 const int j = jbase + c;
@@ -745,13 +746,15 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
                 xb[c] = (c & 3) == 0 ? bits.x : ((c & 3) == 1 ? bits.y : ((c & 3) == 2 ? bits.z : bits.w));
                 // v floored to 23 bits (<= v): exponent of 1.0 | mantissa, minus 1 -- no integer conversion
                 const float vq = __uint_as_float(0x3f800000u | (xb[c] >> 9)) - 1.0f;
-                const float u = ex2_fast(fmaf(y[c], pf_k, tk)) * 1.0078125f;
-                pass |= (vq < u) ? (1u << c) : 0u;
+                const float u = ex2_fast(fmaf(y[c], pf_k, tk));
+                // candidate <=> vq - u < 0: its sign bit is shifted into the mask (one funnel shift; column c ends up
+                // at bit kChunk - 1 - c).  A NaN difference may set the bit: the exact test below rejects it.
+                pass = __funnelshift_l(__float_as_uint(vq - u), pass, 1);
               }
               if (pass) {
 #pragma unroll
                 for (int c = 0; c < kChunk; ++c) {
-                  if (pass & (1u << c)) {
+                  if (pass & (1u << (kChunk - 1 - c))) {
                     const float yy = y[c] + gumbel_from_bits(xb[c], noise_scale);
                     if (jbase + c < n && yy > thr) {
                       qv[qn * kBM + row_t] = yy;

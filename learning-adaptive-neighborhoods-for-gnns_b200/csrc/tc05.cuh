@@ -52,6 +52,12 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
 #endif
 }
 
+// same, for roles whose wait has a whole tile period of slack (all-pairs kernels): at 40 ns the two single-thread warps
+// still issued 20 % of the kernel's instructions (ncu r02d), on the schedulers they share with epilogue warps
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
