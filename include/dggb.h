@@ -366,8 +366,14 @@ int dggb_gemm_tn_tc_presplit(const float* a_t_hi, const float* a_t_lo, int32_t n
  *   out_rowsum (optional): sum_j exp(y_ij * inv_temp) over ALL n columns -- the normaliser of the
  *          evaluation branch softmax(log_p / temp) (dgm.py:298), accumulated in the same pass.
  * Requires d <= 128, kc <= 64.
+ *   Column parts: when the row blocks of a call fill the SMs badly (a row-sharded rank: 228 blocks on 148 SMs), the
+ *   column range is cut into up to 8 parts scored by separate CTAs and a merge launch picks the best kc of a row's
+ *   parts (same order, identical result).  That needs parts * row_count * kc * 8 more workspace bytes:
+ *   dggb_allpairs_workspace_bytes_rows() returns the size including them; with only the base size the call runs unsplit.
+ *   DGGB_AP_PARTS=1..8 overrides the choice.
  * ---------------------------------------------------------------------------------- */
 int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d);
+int64_t dggb_allpairs_workspace_bytes_rows(int32_t n, int32_t d, int32_t row_count, int32_t kc);
 int dggb_allpairs_topk_fwd(const float* z /* [n,d] */, int32_t n, int32_t d, int32_t row_begin,
                            int32_t row_count, const float* t /* [1] device */, const float* noise,
                            int64_t noise_ld, uint64_t seed, float noise_scale, int32_t kc,

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include "philox.cuh"
+#include <algorithm>
 #include <climits>
 #include <cstdlib>
 
@@ -539,7 +540,8 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
                           const float* __restrict__ t_ptr, const float* __restrict__ noise, long long noise_ld,
                           unsigned long long seed, float noise_scale, int kc, int stages, int qcap, int qflush,
                           int32_t* __restrict__ out_idx, float* __restrict__ out_val, float inv_temp,
-                          float* __restrict__ out_rowsum, int no_prefilter) {
+                          float* __restrict__ out_rowsum, int no_prefilter, int tiles_per_part,
+                          int32_t* __restrict__ part_idx, float* __restrict__ part_val) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const AP2Smem L = ap2_smem_layout(KB, SPLIT, stages, kc, qcap);   // queue: qcap >= qflush - 1 + kChunk slots
@@ -556,7 +558,10 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
   constexpr uint32_t kAHi = 4 * kBN, kALo = 4 * kBN + KB * 32;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = (n + kBN - 1) / kBN;
+  // column parts (gridDim.y > 1): this CTA scores key tiles [tile0, tile0 + num_tiles) and leaves its sorted list in
+  // part_idx / part_val [part][row][kc]; allpairs_merge_parts_kernel picks the best kc of a row's parts
+  const int tile0 = blockIdx.y * tiles_per_part;
+  const int num_tiles = min(tiles_per_part, (n + kBN - 1) / kBN - tile0);
   const int row0 = row_begin + blockIdx.x * kBM;
 
   if (warp == 0 && lane == 0) {
@@ -591,12 +596,12 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       for (int jt = 0; jt < num_tiles; ++jt, (++s == stages) ? (s = 0, ph ^= 1) : 0, (++ns == nslots) ? (ns = 0) : 0) {
         tc::mbar_wait_sleep(empty + s, ph ^ 1, 400);
         tc::mbar_arrive_expect_tx(nfull + ns, kBN * 4);
-        tc::bulk_load_1d(smem + L.nrm + ns * kBN * 4, nrm + (size_t)jt * kBN, kBN * 4, nfull + ns);
+        tc::bulk_load_1d(smem + L.nrm + ns * kBN * 4, nrm + (size_t)(tile0 + jt) * kBN, kBN * 4, nfull + ns);
         tc::mbar_arrive_expect_tx(full + s, L.b_stage_bytes);
         uint8_t* bs = smem + L.b0 + s * L.b_stage_bytes;
         for (int kb = 0; kb < KB; ++kb) {
-          tc::tma_load_2d(bs + kb * kBN * 128, &tm_hi, full + s, kb * 32, jt * kBN);
-          if (SPLIT == 3) tc::tma_load_2d(bs + (KB + kb) * kBN * 128, &tm_lo, full + s, kb * 32, jt * kBN);
+          tc::tma_load_2d(bs + kb * kBN * 128, &tm_hi, full + s, kb * 32, (tile0 + jt) * kBN);
+          if (SPLIT == 3) tc::tma_load_2d(bs + (KB + kb) * kBN * 128, &tm_lo, full + s, kb * 32, (tile0 + jt) * kBN);
         }
       }
     }
@@ -709,14 +714,15 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
       tc::mbar_wait(tfull + buf, bph);
       tc::fence_after_sync();
       const float* nj = reinterpret_cast<const float*>(smem + L.nrm + ns * kBN * 4);
-      const bool diag_tile = (jt * kBN < row0 + kBM) && (jt * kBN + kBN > row0);
+      const int col0 = (tile0 + jt) * kBN;
+      const bool diag_tile = (col0 < row0 + kBM) && (col0 + kBN > row0);
 #pragma unroll 1
       for (int c0 = 0; c0 < kBN; c0 += kChunk) {
         uint32_t r[kChunk];
         tc::tmem_ld_32x16(tmem_base + lane_addr + buf * kBN + c0, r);
         tc::tmem_ld_wait();
         if (row_ok) {
-          const int jbase = jt * kBN + c0;
+          const int jbase = col0 + c0;
           auto body = [&](auto diag_c) {
             float y[kChunk];
             float njv[kChunk];
@@ -819,6 +825,14 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
         if (!(lr < row_count && (row_begin + lr) < n)) continue;   // warp-uniform
         merge_row<1>(vals, idxs, vals1, idxs1, kc, rt, kc, lane);
         __syncwarp();
+        if (gridDim.y > 1) {
+          const size_t o = ((size_t)blockIdx.y * row_count + lr) * kc;
+          for (int r = lane; r < kc; r += kWarp) {
+            part_idx[o + r] = idxs[r * kBM + rt];
+            part_val[o + r] = vals[r * kBM + rt];       // -inf where the slot is unused (idx -1)
+          }
+          continue;
+        }
         for (int r = lane; r < kc; r += kWarp) {
           const int32_t id = idxs[r * kBM + rt];
           out_idx[(size_t)lr * kc + r] = id;
@@ -838,6 +852,58 @@ __global__ void __launch_bounds__(kAP2Threads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Column parts -> one list.  A row block x all columns is the natural work unit, but a row-sharded rank holds few row
+// blocks (Reddit shape on 8 GPUs: 228 on 148 SMs = 1.54 waves, i.e. two).  The host then cuts the column range into S
+// parts (grid.y) so that ceil(blocks S / SMs) / S comes closer to blocks / SMs, and this kernel picks the best kc of a
+// row's S sorted part lists: one warp per row, rank by counting over the <= 8 x 32 candidates (value descending, column
+// ascending among equal values: the order of the single-part kernel, so the result is identical).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMergeWarps = 8;
+constexpr int kMaxParts = 8;
+__global__ void __launch_bounds__(kMergeWarps* kWarp)
+    allpairs_merge_parts_kernel(const int32_t* __restrict__ part_idx, const float* __restrict__ part_val, int parts,
+                                int row_count, int rows_valid, int kc, int32_t* __restrict__ out_idx,
+                                float* __restrict__ out_val) {
+  __shared__ float sv[kMergeWarps][kMaxParts * 32];
+  __shared__ int32_t si[kMergeWarps][kMaxParts * 32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = parts * kc;
+  for (int lr = blockIdx.x * kMergeWarps + w; lr < rows_valid; lr += gridDim.x * kMergeWarps) {
+    int valid = 0;
+    for (int i = lane; i < total; i += kWarp) {
+      const int pt = i / kc, r = i - pt * kc;
+      const size_t o = ((size_t)pt * row_count + lr) * kc + r;
+      const int32_t id = __ldg(part_idx + o);
+      si[w][i] = id;
+      sv[w][i] = __ldg(part_val + o);
+      valid += id >= 0;
+    }
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    __syncwarp();
+    for (int i = lane; i < total; i += kWarp) {
+      const int32_t id = si[w][i];
+      if (id < 0) continue;
+      const float v = sv[w][i];
+      int rank = 0;
+      for (int j = 0; j < total; ++j) {
+        const int32_t idj = si[w][j];
+        const float vj = sv[w][j];
+        rank += (idj >= 0 && (vj > v || (vj == v && idj < id))) ? 1 : 0;
+      }
+      if (rank < kc) {
+        out_idx[(size_t)lr * kc + rank] = id;
+        out_val[(size_t)lr * kc + rank] = v;
+      }
+    }
+    for (int r = valid + lane; r < kc; r += kWarp) {
+      out_idx[(size_t)lr * kc + r] = -1;
+      out_val[(size_t)lr * kc + r] = 0.f;
+    }
+    __syncwarp();
+  }
+}
+
 // sparse recompute backward: for every selected pair (i, j) with upstream gy = dL/dy_ij,
 //   y = -t |z_i - z_j|  =>  dt += -D gy ;  g = -t gy / D ;  dz_i += g (z_i - z_j) ;  dz_j -= g (z_i - z_j)
 // (zero gradient at D == 0, like torch.cdist's backward).  O(rows * Kc * d), no N^2 work.
@@ -898,12 +964,49 @@ __global__ void __launch_bounds__(kPairWarps* kWarp)
 }  // namespace dggb
 using namespace dggb;
 
-extern "C" int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d) {
-  if (n < 0 || d <= 0) return DGGB_ERR_BAD_ARG;
+// Column parts for the two-group kernel: S in [1, 8] minimising ceil(blocks S / SMs) / S (waves of full-length work),
+// each part at least 64 key tiles long.  Every part warms up its own lists (Kc ln(N_part / Kc) insertions per row and
+// part instead of Kc ln(N / Kc) per row), measured at 11-14 % of a full-length block per extra part (Reddit shape,
+// gpurun_out/ap_prefilter_ab4.txt: 228 blocks in 5 parts = 1.6 instead of 2 waves ran 23.1 instead of 20.3 ms), so
+// parts only pay where the row blocks leave SMs idle in EVERY wave (fewer blocks than SMs), not for a ragged last wave.
+static int ap_choose_parts(int row_count, int n, int kc) {
+  if (kc > 32 || row_count <= 0) return 1;
+  if (const char* e = getenv("DGGB_AP_PARTS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kMaxParts) return std::min(v, std::max(1, ((n + kBN - 1) / kBN) / 8));
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = (row_count + kBM - 1) / kBM, tiles = (n + kBN - 1) / kBN;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int sp = 1; sp <= kMaxParts; ++sp) {
+    if (sp > 1 && tiles / sp < 64) break;
+    const double cost = (double)((blocks * sp + sms - 1) / sms) / sp * (1.0 + 0.12 * (sp - 1));
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  return best;
+}
+
+static int64_t ap_base_workspace(int32_t n, int32_t d) {
   const int64_t npad = ((int64_t)n + 127) / 128 * 128;
   int64_t dpad = ((int64_t)d + 31) / 32 * 32;
   if (dpad == 96) dpad = 128;   // k-blocks come in 1, 2 or 4 (zero-padded columns)
   return npad * dpad * 4 * 2 + npad * 4;
+}
+
+extern "C" int64_t dggb_allpairs_workspace_bytes_rows(int32_t n, int32_t d, int32_t row_count, int32_t kc) {
+  if (n < 0 || d <= 0 || row_count < 0 || kc <= 0) return DGGB_ERR_BAD_ARG;
+  const int parts = ap_choose_parts(row_count, n, kc);
+  return ap_base_workspace(n, d) + (parts > 1 ? (int64_t)parts * row_count * kc * 8 : 0);
+}
+
+extern "C" int64_t dggb_allpairs_workspace_bytes(int32_t n, int32_t d) {
+  if (n < 0 || d <= 0) return DGGB_ERR_BAD_ARG;
+  return ap_base_workspace(n, d);
 }
 
 extern "C" int dggb_allpairs_topk_fwd(const float* z, int32_t n, int32_t d, int32_t row_begin, int32_t row_count,
@@ -965,15 +1068,25 @@ extern "C" int dggb_allpairs_topk_after_fwd(const float* z, int32_t n, int32_t d
       const size_t smem2 = L2.total + 1024;
       const int grid2 = (row_count + kBM - 1) / kBM;
       const int no_pf = getenv("DGGB_AP_NO_PREFILTER") ? 1 : 0;     // A/B switch: one-step Philox scoring
+      // column parts when the row blocks fill the SMs badly and the caller's workspace has room for the part lists
+      int parts = (nmode2 == 3) ? 1 : ap_choose_parts(row_count, n, kc);
+      const int64_t base_ws = ap_base_workspace(n, d);
+      if (parts > 1 && workspace_bytes < base_ws + (int64_t)parts * row_count * kc * 8) parts = 1;
+      const int total_tiles = (n + kBN - 1) / kBN;
+      const int tpp = (total_tiles + parts - 1) / parts;
+      parts = (total_tiles + tpp - 1) / tpp;                        // no empty part
+      int32_t* part_idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + base_ws);
+      float* part_val = reinterpret_cast<float*>(part_idx + (size_t)parts * row_count * kc);
+      const dim3 grid2d(grid2, parts);
 #define DGGB_AP2_LAUNCH1(KB_, SP_, NM_)                                                                           \
   do {                                                                                                            \
     cudaError_t e = cudaFuncSetAttribute(allpairs_topk2_kernel<KB_, SP_, NM_>,                                    \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);                \
     if (e != cudaSuccess) return cuda_status(e);                                                                  \
-    allpairs_topk2_kernel<KB_, SP_, NM_><<<grid2, kAP2Threads, smem2, st>>>(                                      \
+    allpairs_topk2_kernel<KB_, SP_, NM_><<<grid2d, kAP2Threads, smem2, st>>>(                                     \
         tm_hi, tm_lo, hi, lo, npad, dpad, nrm, n, row_begin, row_count, t, noise, (long long)noise_ld,            \
         (unsigned long long)seed, noise_scale, kc, st2, qcap, qflush, out_idx, out_val, inv_temp, out_rowsum,     \
-        no_pf);                                                                                                   \
+        no_pf, tpp, part_idx, part_val);                                                                          \
   } while (0)
 #define DGGB_AP2_LAUNCH(KB_, SP_)                                                                                 \
   do {                                                                                                            \
@@ -991,6 +1104,13 @@ extern "C" int dggb_allpairs_topk_after_fwd(const float* z, int32_t n, int32_t d
       else return DGGB_ERR_BAD_SHAPE;
 #undef DGGB_AP2_LAUNCH
 #undef DGGB_AP2_LAUNCH1
+      if (parts > 1) {
+        rc = launch_status();
+        if (rc != DGGB_OK) return rc;
+        allpairs_merge_parts_kernel<<<std::min((row_count + kMergeWarps - 1) / kMergeWarps, 148 * 8), kMergeWarps * kWarp,
+                                      0, st>>>(part_idx, part_val, parts, row_count,
+                                               std::min(row_count, n - row_begin), kc, out_idx, out_val);
+      }
       return launch_status();
     }
   }

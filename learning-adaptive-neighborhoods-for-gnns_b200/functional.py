@@ -274,7 +274,7 @@ class _AllPairsTopK(torch.autograd.Function):
         z, t = _f32c(z), _f32c(t).reshape(-1)
         n, d = z.shape
         L = lib()
-        ws_bytes = int(L.dggb_allpairs_workspace_bytes(i32(n), i32(d)))
+        ws_bytes = int(L.dggb_allpairs_workspace_bytes_rows(i32(n), i32(d), i32(row_count), i32(kc)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
         idx = torch.empty(row_count, kc, dtype=torch.int32, device=z.device)
         val = torch.empty(row_count, kc, dtype=torch.float32, device=z.device)

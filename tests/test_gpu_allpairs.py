@@ -171,3 +171,25 @@ def test_philox_candidate_prefilter_selects_identically(n, d, kc, t, scale, zmul
     idx_b, val_b = K.allpairs_topk(z, tt, None, kc, 3, seed=77, noise_scale=scale)
     assert torch.equal(idx_a, idx_b) and torch.equal(val_a, val_b)
     assert int((idx_a >= 0).sum()) == n * kc
+
+
+@pytest.mark.parametrize("parts,n,rows,kc,noise", [(3, 20000, 700, 32, True), (8, 33000, 300, 16, True),
+                                                    (2, 9000, 1000, 32, False), (5, 21000, 129, 8, True)])
+def test_column_parts_return_the_unsplit_lists(parts, n, rows, kc, noise, monkeypatch):
+    """Column parts (grid.y CTAs per row block + the merge launch) == the single-part kernel, bit for bit: the
+    selection is exact and the order (value descending, column ascending) is the same in both."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(parts * 1000 + kc)
+    z = (torch.randn(n, 64, generator=gen) * 0.5).cuda()
+    z[5] = z[4]                                   # a duplicate point: equal scores in different parts' columns
+    t = torch.tensor([1.5]).cuda()
+    kw = dict(seed=11, noise_scale=1.0) if noise else {}
+    monkeypatch.setenv("DGGB_AP_PARTS", "1")
+    idx_a, val_a = K.allpairs_topk(z, t, None, kc, 3, 37, rows, **kw)
+    monkeypatch.setenv("DGGB_AP_PARTS", str(parts))
+    idx_b, val_b = K.allpairs_topk(z, t, None, kc, 3, 37, rows, **kw)
+    assert torch.equal(idx_a, idx_b) and torch.equal(val_a, val_b)
+    monkeypatch.delenv("DGGB_AP_PARTS")           # the automatic choice
+    idx_c, val_c = K.allpairs_topk(z, t, None, kc, 3, 37, rows, **kw)
+    assert torch.equal(idx_a, idx_c) and torch.equal(val_a, val_c)
