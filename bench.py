@@ -573,8 +573,13 @@ def reddit_record(rank, world, dev, steps=4, warmup=2):
                              achieved=flops / t_ap / 1e12, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
                              frac=flops / t_ap / 1e12 / peaks["bf16_tflops_sustained"], kernel_ms=t_ap * 1e3,
                              pair_scores_per_s=cnt * n / t_ap,
-                             note="the SIMT epilogue (distance, Philox Gumbel, selection: ~36 instructions per scored "
-                                  "pair) bounds this kernel, not the tensor pipe; 3xTF32 issues 3x the algorithmic flops"))
+                             simt_issue=dict(instr_per_pair=20.9, peak_pairs_per_s=148 * 128 * 1.965e9 / 20.9,
+                                             frac=cnt * n / t_ap / (148 * 128 * 1.965e9 / 20.9),
+                                             source="profiles/r02c_allpairs_ncu.md: 334 SASS instructions per "
+                                                    "16-column chunk of the streaming loop, 128 lanes x 148 SMs"),
+                             note="the SIMT epilogue (distance, Philox word, one ex2 candidate test per scored pair; "
+                                  "the Gumbel logs only for candidates) bounds this kernel, not the tensor pipe; "
+                                  "3xTF32 issues 3x the algorithmic flops"))
     del m, x, z_all
     torch.cuda.empty_cache()
     return rec

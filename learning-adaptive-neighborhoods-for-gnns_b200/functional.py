@@ -701,21 +701,35 @@ def tall_linear(x, w, b=None, slope=1.0):
 
 
 class _TallMatmul(torch.autograd.Function):
-    """x [N, P] @ w [P, Q] for tall x (the (A x) W products of the conv layers, model.py:596, 74): the weight
-    gradient x^T g reduces over the N nodes into a tiny [P, Q] output, which cuBLAS leaves on a handful of
-    CTAs (81 us at Pubmed shape); it goes through the split-K kernels instead."""
+    """act(x [N, P] @ w [P, Q]) for tall x (the (A x) W products of the conv layers, model.py:596, 74; act = ReLU or
+    identity).  Forward and d x = dpre w^T run on the tcgen05 3xTF32 kernel (dggb_linear_fused; the ReLU is its
+    epilogue) when its shapes allow -- Q resp. P in {16, 32, 64, 128}, the other one a multiple of 4 -- and on the
+    library GEMM otherwise (e.g. the 64 -> 3 class logits).  The weight gradient x^T dpre reduces over the N nodes into
+    a tiny [P, Q] output, which cuBLAS leaves on a handful of CTAs (81 us at Pubmed shape): split-K kernels instead."""
 
     @staticmethod
-    def forward(ctx, x, w):
-        ctx.save_for_backward(x, w)
-        return torch.mm(x, w)
+    def forward(ctx, x, w, relu: bool):
+        out = _linear_act_tc(x, w, None, 0.0 if relu else 1.0, w_transposed=True)
+        if out is None:
+            out = torch.mm(x, w)
+            if relu:
+                out = torch.relu_(out)
+        ctx.relu = relu
+        ctx.save_for_backward(x, w, out if relu else None)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        x, w = ctx.saved_tensors
-        dx = torch.mm(g, w.t()) if ctx.needs_input_grad[0] else None
-        dw = gemm_tn(x, g, False)[0] if ctx.needs_input_grad[1] else None
-        return dx, dw
+        x, w, out = ctx.saved_tensors
+        g = _f32c(g)
+        dpre = torch.ops.aten.threshold_backward(g, out, 0.0) if ctx.relu else g
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _linear_act_tc(dpre, w, None, 1.0)           # dpre [N, Q] w[P, Q]^T: w is the [h = P, F = Q] weight
+            if dx is None:
+                dx = torch.mm(dpre, w.t())
+        dw = gemm_tn(x, dpre, False)[0] if ctx.needs_input_grad[1] else None
+        return dx, dw, None
 
 
 class _HeadDots(torch.autograd.Function):
@@ -752,7 +766,9 @@ def head_dots(h, a):
     return _HeadDots.apply(h, a)
 
 
-def tall_matmul(x, w):
+def tall_matmul(x, w, relu=False):
+    """relu?(x @ w) for a tall x [N, P] and a small w [P, Q]."""
     if x.is_cuda and x.dtype == torch.float32 and x.shape[0] >= 2048 and x.shape[1] <= 512:
-        return _TallMatmul.apply(x, w)
-    return torch.mm(x, w)
+        return _TallMatmul.apply(x, w, bool(relu))
+    out = torch.mm(x, w)
+    return torch.relu(out) if relu else out

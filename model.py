@@ -72,7 +72,7 @@ class GCNConv(nn.Module):
             # (A x) W == A (x W): aggregate in the narrower space (model.py:594-596 order otherwise).  Raw features
             # (Cora 1433, Citeseer 3703 wide): the tall product runs on the tensor cores, features padded once
             return torch.relu(_aggregate(adj, K.encoder_linear(x, self.W.t(), None, 1.0)))
-        return torch.relu(K.tall_matmul(_aggregate(adj, x), self.W))
+        return K.tall_matmul(_aggregate(adj, x), self.W, relu=True)       # ReLU in the GEMM's epilogue
 
 
 # --------------------------------------------------------------------------- GCN + DGG

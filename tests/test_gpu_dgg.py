@@ -527,3 +527,27 @@ def test_spmm_gemm_keep_mask_and_folded_relu_match_explicit_ops(n, avg_deg, relu
     torch.testing.assert_close(ya, yb, rtol=1e-5, atol=1e-5)
     for qa, qb in zip(ga, gb):
         torch.testing.assert_close(qa, qb, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("n,p_,q,relu", [(3000, 64, 64, True), (2500, 500, 64, False), (2100, 64, 3, True),
+                                         (4100, 128, 16, True), (2049, 36, 32, False)])
+def test_tall_matmul_matches_fp64_autograd(n, p_, q, relu):
+    """relu?(x @ w) of the conv layers: tcgen05 forward / d x where the shapes allow (library GEMM otherwise, e.g. 3
+    output columns), split-K weight gradient; values and both gradients against fp64 autograd (3xTF32: rtol 2e-5)."""
+    from dgg_b200 import functional as K
+
+    gen = torch.Generator().manual_seed(n + q)
+    x = torch.randn(n, p_, generator=gen).cuda().requires_grad_(True)
+    w = (torch.randn(p_, q, generator=gen) / p_ ** 0.5).cuda().requires_grad_(True)
+    wl = torch.randn(n, q, generator=gen).cuda()
+    y = K.tall_matmul(x, w, relu=relu)
+    (y * wl).sum().backward()
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    yd = xd @ wd
+    if relu:
+        # the ReLU mask is taken from the fp32 result: entries within rounding of 0 may differ in sign
+        yd = yd * (y.detach() > 0)
+    (yd * wl.double()).sum().backward()
+    torch.testing.assert_close(y, yd.float(), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(x.grad, xd.grad.float(), rtol=2e-5, atol=2e-5)
+    assert float((w.grad.double() - wd.grad).abs().max()) <= 2e-5 * float(wd.grad.abs().max())
