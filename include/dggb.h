@@ -255,6 +255,8 @@ int dggb_spmm_edge_bwd(const int32_t* erow, const int32_t* col, const float* val
  * out_keep [N, Fout] (or NULL, both directions): dropout multipliers (0 or 1 / (1 - p)) applied to the layer OUTPUT,
  * y = act(...) * out_keep -- the F.dropout in front of the NEXT GCNII layer (model.py:725) and its backward are two
  * launches per layer and direction otherwise; the backward takes gy = dL/dy of that dropped output.
+ * accumulate (bwd): bit 0: dval += instead of =, bit 1: ds_out += instead of = -- the layers of a deep stack that share
+ * the adjacency values / h0 (GCNII: all 64) sum their gradients in place instead of through 2 x 63 add launches.
  * ---------------------------------------------------------------------------------- */
 int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x,
                        int32_t fin, const float* row_scale, const float* h0, float c1, float c2, const float* w,
@@ -264,7 +266,7 @@ int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* v
                        int32_t fin, const float* row_scale, float c1, const float* w, int32_t fout, float theta,
                        float beta, const float* gy, float* dval, float* dx, float* ds_out, float ds_scale,
                        float* zero_ws, int64_t zero_count, const float* relu_y, float* gy_masked,
-                       const float* out_keep, void* stream);
+                       const float* out_keep, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)

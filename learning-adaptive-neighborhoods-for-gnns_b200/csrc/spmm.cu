@@ -339,6 +339,8 @@ struct SpmmGemmArgs {
   const float* resid;    // [n, fout] or NULL
   float c1, c2, theta, beta;
   int relu;
+  int accum;             // backward: bit 0: dval += (instead of =), bit 1: ds_out += -- layers of a stack that share the
+                         // adjacency values / h0 accumulate their gradients in place (autograd would add 64 tensors)
   const float* okeep;    // [n, fout] or NULL: dropout multipliers (0 or 1/(1-p)) applied to the layer OUTPUT in the
                          // epilogue (the next layer's F.dropout(input) and its backward are two launches per layer and
                          // direction otherwise; a per-row product, not a per-entry gather)
@@ -704,7 +706,10 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         if (f < A.fin) {
           float v = A.theta * d[r][q];
           if (A.beta != 0.f) v = fmaf(A.beta, grows[r * fo4 + f], v);
-          if (ds_out && i < A.n) ds_out[(size_t)i * A.fin + f] = ds_scale * v;
+          if (ds_out && i < A.n) {
+            float* dst = ds_out + (size_t)i * A.fin + f;
+            *dst = (A.accum & 2) ? *dst + ds_scale * v : ds_scale * v;
+          }
           DS[(warp * RB + r) * A.fin + f] = k1 * v;
         }
       }
@@ -754,7 +759,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       }
       if (dval) {
         dot = group_sum(dot, L);
-        if (lg == 0) dval[e] = dot;
+        if (lg == 0) dval[e] = (A.accum & 1) ? dval[e] + dot : dot;
       }
     }
   }
@@ -841,7 +846,7 @@ extern "C" int dggb_spmm_gemm_fwd(const int32_t* rowptr, const int32_t* col, con
                                   float c2, const float* w, int32_t fout, float theta, float beta,
                                   const float* resid, int32_t relu, const float* out_keep, float* y, float* s_out,
                                   void* stream) {
-  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, h0, w, resid, c1, c2, theta, beta, relu, out_keep};
+  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, h0, w, resid, c1, c2, theta, beta, relu, 0, out_keep};
   if (out_keep && ((uintptr_t)out_keep % 16)) return DGGB_ERR_BAD_ARG;
   int rc = spmm_gemm_check(A);
   if (rc != DGGB_OK) return rc;
@@ -873,8 +878,9 @@ extern "C" int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, con
                                   const float* x, int32_t fin, const float* row_scale, float c1, const float* w,
                                   int32_t fout, float theta, float beta, const float* gy, float* dval, float* dx,
                                   float* ds_out, float ds_scale, float* zero_ws, int64_t zero_count,
-                                  const float* relu_y, float* gy_masked, const float* out_keep, void* stream) {
-  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, nullptr, w, nullptr, c1, 0.f, theta, beta, 0, out_keep};
+                                  const float* relu_y, float* gy_masked, const float* out_keep, int32_t accumulate,
+                                  void* stream) {
+  SpmmGemmArgs A{rowptr, col, val, n, fin, fout, 1, x, row_scale, nullptr, w, nullptr, c1, 0.f, theta, beta, 0, (int)accumulate, out_keep};
   if (out_keep && ((uintptr_t)out_keep % 16)) return DGGB_ERR_BAD_ARG;
   int rc = spmm_gemm_check(A);
   if (rc != DGGB_OK) return rc;

@@ -186,12 +186,25 @@ def spmm(vals, x, graph, row_scale=None):
     return _Spmm.apply(vals, x, graph, row_scale)
 
 
+class GradShare:
+    """One gradient accumulator shared by the layers of a stack that consume the SAME tensor (GCNII: h0 in all 64
+    layers, the normalised adjacency values in all layers behind the last DGG layer).  Autograd would add the per-layer
+    gradients with one launch per layer; here the layer that runs its backward FIRST (the last one of the group in
+    forward order) allocates and overwrites the buffer, the others accumulate in place inside their backward launch,
+    and only the group's first layer -- whose backward runs last -- hands the buffer to autograd.  Valid because the
+    layers form a chain (each consumes its predecessor's output), so their backwards run in reverse forward order."""
+
+    def __init__(self):
+        self.buf = None
+
+
 class _SpmmGemm(torch.autograd.Function):
     """y = act(theta * (s W) + beta * s + resid), s = c1 * rs * (A x) + c2 * h0 in one launch per direction
     (GCNConv model.py:594-598; GraphConvolution model.py:32-44, 65-77); see include/dggb.h."""
 
     @staticmethod
-    def forward(ctx, vals, x, w, h0, resid, graph: CSRGraph, row_scale, c1, c2, theta, beta, relu, out_keep):
+    def forward(ctx, vals, x, w, h0, resid, graph: CSRGraph, row_scale, c1, c2, theta, beta, relu, out_keep,
+                h0_share, val_share):
         _require_cuda(vals, x, w, h0, resid, out_keep)
         vals, x, w = _f32c(vals), _f32c(x), _f32c(w)
         out_keep = None if out_keep is None else _f32c(out_keep)
@@ -206,6 +219,7 @@ class _SpmmGemm(torch.autograd.Function):
                                        float(theta), float(beta), p(resid), i32(1 if relu else 0), p(out_keep), p(y),
                                        p(s), stream()), "spmm_gemm_fwd")
         ctx.graph, ctx.meta = graph, (c1, c2, theta, beta, relu, h0 is not None, resid is not None)
+        ctx.h0_share, ctx.val_share = h0_share, val_share      # (GradShare, first in group, last in group) or None
         ctx.save_for_backward(vals, x, w, row_scale, s, y if relu else None, out_keep)
         return y
 
@@ -216,9 +230,24 @@ class _SpmmGemm(torch.autograd.Function):
         g = ctx.graph
         gy = _f32c(gy)
         need_v, need_x, need_w, need_h0 = ctx.needs_input_grad[:4]
-        dval = torch.empty_like(vals) if need_v else None
+        accumulate = 0
+
+        def shared(share, like, bit):
+            # the group's LAST layer runs its backward first: fresh buffer, overwritten; the others add in place
+            nonlocal accumulate
+            sh, _first, last = share
+            if last:
+                sh.buf = torch.empty_like(like)
+            else:
+                accumulate |= bit
+            return sh.buf
+
+        dval = ds = None
+        if need_v:
+            dval = shared(ctx.val_share, vals, 1) if ctx.val_share is not None else torch.empty_like(vals)
         dx = torch.zeros_like(x) if need_x else None
-        ds = torch.empty_like(x) if (need_h0 and has_h0) else None           # receives c2 * ds = d h0
+        if need_h0 and has_h0:                                               # receives c2 * ds = d h0
+            ds = shared(ctx.h0_share, x, 2) if ctx.h0_share is not None else torch.empty_like(x)
         launch = need_v or need_x or ds is not None
         # the weight gradient's split-K accumulator is cleared by the layer's own backward launch (no fill kernel)
         dwbuf = (torch.empty(w.numel(), dtype=torch.float32, device=x.device)
@@ -232,7 +261,7 @@ class _SpmmGemm(torch.autograd.Function):
                                            p(row_scale), float(c1), p(w), i32(w.shape[1]), float(theta), float(beta),
                                            p(gy), p(dval), p(dx), p(ds), float(c2), p(dwbuf),
                                            i64(0 if dwbuf is None else dwbuf.numel()), p(y if relu else None), p(gm),
-                                           p(out_keep), stream()), "spmm_gemm_bwd")
+                                           p(out_keep), i32(accumulate), stream()), "spmm_gemm_bwd")
             if gm is not None:
                 gy = gm
         else:
@@ -243,25 +272,38 @@ class _SpmmGemm(torch.autograd.Function):
         dw = None
         if need_w:
             dw = gemm_tn(s, gy, False, zeroed=dwbuf)[0]       # s was saved as theta * s
+        # a shared accumulator reaches autograd once: through the group's first layer, whose backward runs last
+        if ctx.val_share is not None and dval is not None and not ctx.val_share[1]:
+            dval = None
         dh0 = ds
+        if ctx.h0_share is not None and ds is not None and not ctx.h0_share[1]:
+            dh0 = None
         dres = gy if (has_resid and ctx.needs_input_grad[4]) else None
-        return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None, None
+        return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None, None, None, None
+
+
+def spmm_gemm_applies(x, w, n, beta=0.0):
+    """Whether ``spmm_gemm`` takes this layer shape (callers that set up gradient sharing over a stack need to know
+    beforehand: every layer of a group has to go the same way)."""
+    fin, fout = x.shape[1], w.shape[1]
+    if not (x.is_cuda and fin % 4 == 0 and fin <= 128 and fout <= 128 and (beta == 0.0 or fin == fout)):
+        return False
+    if _NO_FUSED_CONV:      # A/B measurements: DGGB_NO_FUSED_CONV=1 selects SpMM + library GEMM + elementwise ops
+        return False
+    return n < _FUSED_CONV_MAX_N
 
 
 def spmm_gemm(vals, x, w, graph, h0=None, resid=None, row_scale=None, c1=1.0, c2=0.0, theta=1.0, beta=0.0, relu=False,
-              out_keep=None):
+              out_keep=None, h0_share=None, val_share=None):
     """act(theta * (s W) + beta * s + resid) * out_keep with s = c1 * rs * (A x) + c2 * h0; None if the shape is outside
     the fused kernel's range (Fin % 4 != 0, Fin or Fout > 128).  out_keep: optional dropout multipliers
-    (0 or 1 / (1 - p)) of the layer OUTPUT (the dropout in front of the next layer), applied in the epilogue."""
-    fin, fout = x.shape[1], w.shape[1]
-    if not (x.is_cuda and fin % 4 == 0 and fin <= 128 and fout <= 128 and (beta == 0.0 or fin == fout)):
-        return None
-    if _NO_FUSED_CONV:      # A/B measurements: DGGB_NO_FUSED_CONV=1 selects SpMM + library GEMM + elementwise ops
-        return None
-    if graph.n >= _FUSED_CONV_MAX_N:
+    (0 or 1 / (1 - p)) of the layer OUTPUT (the dropout in front of the next layer), applied in the epilogue.
+    h0_share / val_share: (GradShare, first_in_group, last_in_group) when this call is one of a chain of layers that
+    share h0 resp. vals (see GradShare); every layer of the group must pass the same object."""
+    if not spmm_gemm_applies(x, w, graph.n, beta):
         return None
     return _SpmmGemm.apply(vals, x, w, h0, resid, graph, row_scale, float(c1), float(c2), float(theta), float(beta),
-                           bool(relu), out_keep)
+                           bool(relu), out_keep, h0_share, val_share)
 
 
 class _AllPairsTopK(torch.autograd.Function):

@@ -198,15 +198,17 @@ class GraphConvolution(nn.Module):
         stdv = 1.0 / math.sqrt(self.out_features)
         self.weight.data.uniform_(-stdv, stdv)
 
-    def forward(self, input, adj, h0, lamda, alpha, l, act=None, out_keep=None):
+    def forward(self, input, adj, h0, lamda, alpha, l, act=None, out_keep=None, h0_share=None, val_share=None):
         """``act="relu"``: the caller's activation (GCNII applies ``act_fn`` to every layer output, model.py:728)
         is folded into the fused kernel.  ``out_keep``: dropout multipliers (0 or 1 / (1 - p)) of the layer OUTPUT --
-        the caller's ``F.dropout`` in front of the next layer (model.py:725) applied in this layer's epilogue."""
+        the caller's ``F.dropout`` in front of the next layer (model.py:725) applied in this layer's epilogue.
+        ``h0_share`` / ``val_share``: gradient accumulators shared over a stack of layers (``K.GradShare``)."""
         theta = math.log(lamda / l + 1)
         if adj.is_sparse and not self.variant:
             g, v = CSRGraph.from_coo(adj)
             out = K.spmm_gemm(v, input, self.weight, g, h0=h0, resid=input if self.residual else None, c1=1 - alpha,
-                              c2=alpha, theta=theta, beta=1 - theta, relu=(act == "relu"), out_keep=out_keep)
+                              c2=alpha, theta=theta, beta=1 - theta, relu=(act == "relu"), out_keep=out_keep,
+                              h0_share=h0_share, val_share=val_share)
             if out is not None:
                 return out
         out = self._forward_unfused(input, adj, h0, theta, alpha)
@@ -276,15 +278,25 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
             keeps = torch.empty(len(self.convs), layer_inner.shape[0], layer_inner.shape[1],
                                 device=x.device).bernoulli_(1.0 - self.dropout).mul_(1.0 / (1.0 - self.dropout))
             layer_inner = F.dropout(layer_inner, self.dropout, training=True)
+        # all layers read h0, and all layers behind the last DGG layer read the same adjacency values: their gradients
+        # are summed in place by the layers' own backward launches (K.GradShare) instead of 2 x 63 autograd adds
+        nl = len(self.convs)
+        share = (torch.is_grad_enabled() and not con0_variant(self.convs)
+                 and K.spmm_gemm_applies(layer_inner, self.convs[0].weight, x.shape[0], 1.0))
+        h0_sh, val_sh, val_first = (K.GradShare() if share else None), None, 0
         for i, con in enumerate(self.convs):
             if i < len(self.dggs):
                 src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
                 unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
                 norm_adj = self.normalize_adj(unnorm_adj)
+                val_sh, val_first = (K.GradShare() if share else None), i
             if keeps is None:
                 layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+            val_last = i == nl - 1 or i + 1 < len(self.dggs)          # the next layer gets a new adjacency
             layer_inner = con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1, act="relu",
-                              out_keep=None if keeps is None else keeps[i])
+                              out_keep=None if keeps is None else keeps[i],
+                              h0_share=(h0_sh, i == 0, i == nl - 1) if share else None,
+                              val_share=(val_sh, i == val_first, val_last) if share else None)
         if keeps is None:
             layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
         layer_inner = self.fcs[-1](layer_inner)
@@ -292,6 +304,11 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
 
     def dgg_net(self, x, i, unnorm_adj, writer, epoch):
         return self.dggs[i](x=x, in_adj=unnorm_adj, noise=self.training, writer=writer, epoch=epoch)
+
+
+def con0_variant(convs):
+    """True when the stack's layers do not all take the fused one-launch path (variant layers concatenate [hi, h0])."""
+    return any(c.variant for c in convs)
 
 
 # --------------------------------------------------------------------------- SAGE + DGG

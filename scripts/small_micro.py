@@ -35,6 +35,6 @@ def efwd():
 print("spmm_edge_fwd+zero  %.2f us" % gt(efwd))
 print("spmm_csr_bwd        %.2f us" % gt(lambda: check(L.dggb_spmm_csr_bwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, P(gy), P(dv), P(dx), stream()), "c")))
 print("spmm_edge_bwd       %.2f us" % gt(lambda: check(L.dggb_spmm_edge_bwd(P(g.erow), P(g.col), P(v), E, P(x), h, None, P(gy), P(dv), P(dx), stream()), "c")))
-print("spmm_gemm_bwd       %.2f us" % gt(lambda: check(L.dggb_spmm_gemm_bwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, 0.9, P(w), h, 0.4, 0.6, P(gy), P(dv), P(dx), P(ds), 0.1, None, 0, None, None, None, stream()), "d")))
+print("spmm_gemm_bwd       %.2f us" % gt(lambda: check(L.dggb_spmm_gemm_bwd(P(g.rowptr), P(g.col), P(v), n, P(x), h, None, 0.9, P(w), h, 0.4, 0.6, P(gy), P(dv), P(dx), P(ds), 0.1, None, 0, None, None, None, 0, stream()), "d")))
 print("torch mm            %.2f us" % gt(lambda: torch.mm(x, w, out=y)))
 print("torch add           %.2f us" % gt(lambda: torch.add(x, gy, out=y)))

@@ -551,3 +551,43 @@ def test_tall_matmul_matches_fp64_autograd(n, p_, q, relu):
     torch.testing.assert_close(y, yd.float(), rtol=2e-5, atol=2e-5)
     torch.testing.assert_close(x.grad, xd.grad.float(), rtol=2e-5, atol=2e-5)
     assert float((w.grad.double() - wd.grad).abs().max()) <= 2e-5 * float(wd.grad.abs().max())
+
+
+def test_grad_share_over_a_layer_stack_matches_autograd_sums():
+    """Five chained GCNII layers that share h0 and the adjacency values: the in-place gradient accumulators
+    (K.GradShare: last layer overwrites, the others add inside their backward launch, the first layer hands the sum to
+    autograd) against the same stack with autograd adding the per-layer gradients; also a second backward pass."""
+    from dgg_b200 import CSRGraph, functional as K
+
+    n, h, nl = 2000, 64, 5
+    gen = torch.Generator().manual_seed(3)
+    m = n * 6
+    a = torch.sparse_coo_tensor(torch.stack([torch.randint(0, n, (m,), generator=gen), torch.randint(0, n, (m,), generator=gen)]),
+                                torch.ones(m), (n, n)).coalesce()
+    g = CSRGraph.from_indices(a.indices().cuda(), n)
+    v0 = (torch.rand(g.nnz, generator=gen) * 0.3 + 0.05).cuda()
+    x0 = torch.randn(n, h, generator=gen).cuda()
+    h00 = torch.randn(n, h, generator=gen).cuda()
+    ws0 = [(torch.randn(h, h, generator=gen) / 8).cuda() for _ in range(nl)]
+    wl = torch.randn(n, h, generator=gen).cuda()
+
+    def run(shared, backwards=1):
+        v, x, h0 = (t.clone().requires_grad_(True) for t in (v0, x0, h00))
+        ws = [w.clone().requires_grad_(True) for w in ws0]
+        hs, vs = K.GradShare(), K.GradShare()
+        y = x
+        for i in range(nl):
+            y = K.spmm_gemm(v, y, ws[i], g, h0=h0, c1=0.9, c2=0.1, theta=0.4, beta=0.6, relu=True,
+                            h0_share=(hs, i == 0, i == nl - 1) if shared else None,
+                            val_share=(vs, i == 0, i == nl - 1) if shared else None)
+        loss = (y * wl).sum()
+        for b in range(backwards):
+            for t in [v, x, h0] + ws:
+                t.grad = None
+            loss.backward(retain_graph=b + 1 < backwards)
+        return [v.grad, x.grad, h0.grad] + [w.grad for w in ws]
+
+    ref = run(False)
+    for got in (run(True), run(True, backwards=2)):
+        for a_, b_ in zip(got, ref):
+            torch.testing.assert_close(a_, b_, rtol=1e-4, atol=1e-5)
