@@ -268,6 +268,20 @@ int dggb_spmm_gemm_bwd(const int32_t* rowptr, const int32_t* col, const float* v
                        float* zero_ws, int64_t zero_count, const float* relu_y, float* gy_masked,
                        const float* out_keep, int32_t accumulate, void* stream);
 
+/* A STACK of GCNII layers that share the adjacency and h0 in ONE cooperative launch (small graphs: one warp per row,
+ * every CTA resident, grid barrier between layers): y[k] = ReLU(theta_k (s_k W_k) + (1 - theta_k) s_k) * keep[k],
+ * s_k = c1 (A y[k-1]) + c2 h0, y[-1] = x0  (GraphConvolution, model.py:65-77, as GCNII_DGG calls it 62 times behind its
+ * last DGG layer, model.py:722-729).  w_host_ptrs / theta_host are HOST arrays of `layers` device pointers ([f, f] each)
+ * and floats; y / s_out: [layers, n, f] (s_out receives theta_k s_k, the weight gradient's left operand, or NULL);
+ * keep: [layers, n, f] or NULL; barrier_zeroed: one zeroed uint32.  f in {32, 64, 128}, layers <= 96.  Returns
+ * DGGB_ERR_UNSUPPORTED when the grid cannot be resident at once (n > dggb_gcnii_stack_max_rows(f), ~4 700 rows at
+ * f = 64): run the layers one launch each (dggb_spmm_gemm_fwd).  The backward is per layer (dggb_spmm_gemm_bwd with its accumulate flags). */
+int32_t dggb_gcnii_stack_max_rows(int32_t f);
+int dggb_gcnii_stack_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, const float* x0,
+                         const float* h0, int32_t f, int32_t layers, const float* const* w_host_ptrs,
+                         const float* theta_host, float c1, float c2, const float* keep, float* y, float* s_out,
+                         uint32_t* barrier_zeroed, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Node encoder forward: out[N,H] = LeakyReLU_slope(x[N,F] W[H,F]^T + b)  (slope = 1: plain Linear)
  * -- nn.Sequential(nn.Linear, nn.LeakyReLU) of dgm.py:1741-1744, 1097-1100, 1123-1126 and the

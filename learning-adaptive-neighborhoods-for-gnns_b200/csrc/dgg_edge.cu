@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(kEdgeWarps* kWarp)
       const float dr = __shfl_sync(0xffffffffu, dr_l, j);
       const bool valid = (base + j) < nnz;
       RowSlice<T> yu, yv;
-      load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
-      load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+      load_slice<T>(yu, y + (size_t)u * h, h, lg, L, valid);
+      load_slice<T>(yv, y + (size_t)v * h, h, lg, L, valid);
       const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
       const float r1 = sigmoidf_(z);
       const float dz = valid ? dr * r1 * (1.f - r1) : 0.f;
@@ -516,8 +516,8 @@ __global__ void __launch_bounds__(kFusedThreads)
       const int e = eb0 + (valid ? idx : 0);
       const int u = valid ? __ldg(erow + e) : 0, v = valid ? __ldg(col + e) : 0;
       RowSlice<T> yu, yv;
-      load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
-      load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+      load_slice<T>(yu, y + (size_t)u * h, h, lg, L, valid);
+      load_slice<T>(yv, y + (size_t)v * h, h, lg, L, valid);
       const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
       if (valid && lg == 0) {
         float r = sigmoidf_(z);
@@ -813,8 +813,8 @@ __global__ void __launch_bounds__(kFusedThreads)
         v_n = __ldg(col + eb0 + idx + groups);
       }
       RowSlice<T> yu, yv;
-      load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
-      load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+      load_slice<T>(yu, y + (size_t)u * h, h, lg, L, valid);
+      load_slice<T>(yv, y + (size_t)v * h, h, lg, L, valid);
       const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
       if (valid && lg == 0) {
         const int e = eb0 + idx;
@@ -975,8 +975,8 @@ __global__ void __launch_bounds__(kFusedThreads, DGGB_BWD2_MIN_BLOCKS)
     }
     const float dr = valid ? sDr[idx] : 0.f;
     RowSlice<T> yu, yv;
-    load_slice<T>(yu, y + (size_t)u * h, h, lg, L);
-    load_slice<T>(yv, y + (size_t)v * h, h, lg, L);
+    load_slice<T>(yu, y + (size_t)u * h, h, lg, L, valid);
+    load_slice<T>(yv, y + (size_t)v * h, h, lg, L, valid);
     const float z = group_sum(edge_partial<T>(yu, yv, bias), L);
     const float r1s = sigmoidf_(z);
     const float dz = valid ? dr * r1s * (1.f - r1s) : 0.f;

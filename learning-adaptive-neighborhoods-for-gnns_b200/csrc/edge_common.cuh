@@ -14,11 +14,14 @@ struct RowSlice {
 };
 
 template <int T>
-__device__ __forceinline__ void load_slice(RowSlice<T>& s, const float* row, int h, int lg, int L) {
+__device__ __forceinline__ void load_slice(RowSlice<T>& s, const float* row, int h, int lg, int L, bool live = true) {
+  // live = false: a slot beyond the entry range issues NO load.  (Pointing idle slots at row 0 looks harmless, but every
+  // block of the grid has such slots in its last iteration and they all hit the same two L2 lines at about the same
+  // time: tens of thousands of requests on one line serialise -- measured in the GCNII stack kernel, spmm.cu.)
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int c = 4 * (lg + L * t);
-    s.v[t] = (c < h) ? ldg4(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s.v[t] = (live && c < h) ? ldg4(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

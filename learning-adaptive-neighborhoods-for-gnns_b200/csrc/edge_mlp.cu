@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kMlpWarps* kWarp) edge_mlp_fwd_kernel(EdgeMlpA
     float distf = 0.f;
     if (need_dist) {
       RowSlice<T> xu, xv;
-      load_slice<T>(xu, A.xe + (size_t)u * A.hx, A.hx, lg, L);
-      load_slice<T>(xv, A.xe + (size_t)v * A.hx, A.hx, lg, L);
+      load_slice<T>(xu, A.xe + (size_t)u * A.hx, A.hx, lg, L, valid);
+      load_slice<T>(xv, A.xe + (size_t)v * A.hx, A.hx, lg, L, valid);
       const float d2 = group_sum(dist2_partial<T>(xu, xv), L);
       distf = expf(-A.dist_scale * sqrtf(d2));
     }
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(kMlpWarps* kWarp) edge_mlp_fwd_kernel(EdgeMlpA
       float ex[kMlpMaxExtra];
       gather_extras(A, ee, u, v, distf, ex);
       RowSlice<T> pu, pv;
-      load_slice<T>(pu, A.P + (size_t)u * A.ldp, A.w, lg, L);
-      load_slice<T>(pv, A.P + (size_t)v * A.ldp + A.w, A.w, lg, L);
+      load_slice<T>(pu, A.P + (size_t)u * A.ldp, A.w, lg, L, valid);
+      load_slice<T>(pv, A.P + (size_t)v * A.ldp + A.w, A.w, lg, L, valid);
       float z = 0.f;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(kMlpWarps* kWarp) edge_mlp_bwd_kernel(EdgeMlpA
     RowSlice<T> xu, xv;
     float distf = 0.f, dist = 0.f;
     if (need_dist) {
-      load_slice<T>(xu, A.xe + (size_t)u * A.hx, A.hx, lg, L);
-      load_slice<T>(xv, A.xe + (size_t)v * A.hx, A.hx, lg, L);
+      load_slice<T>(xu, A.xe + (size_t)u * A.hx, A.hx, lg, L, valid);
+      load_slice<T>(xv, A.xe + (size_t)v * A.hx, A.hx, lg, L, valid);
       dist = sqrtf(group_sum(dist2_partial<T>(xu, xv), L));
       distf = expf(-A.dist_scale * dist);
     }
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(kMlpWarps* kWarp) edge_mlp_bwd_kernel(EdgeMlpA
       float ex[kMlpMaxExtra];
       gather_extras(A, ee, u, v, distf, ex);
       RowSlice<T> pu, pv;
-      load_slice<T>(pu, A.P + (size_t)u * A.ldp, W, lg, L);
-      load_slice<T>(pv, A.P + (size_t)v * A.ldp + W, W, lg, L);
+      load_slice<T>(pu, A.P + (size_t)u * A.ldp, W, lg, L, valid);
+      load_slice<T>(pv, A.P + (size_t)v * A.ldp + W, W, lg, L, valid);
       const float ds = g * sc * (1.f - sc);            // through the sigmoid
       db2a += (lg == 0) ? ds : 0.f;
       if (valid && u != cur_u) {

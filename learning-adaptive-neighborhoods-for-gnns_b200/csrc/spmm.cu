@@ -4,6 +4,7 @@
 // time with VEC-wide (128-bit when F % 4 == 0) coalesced loads.
 // HBM-bound: nnz*(8 + F*4 gathered) + N*F*4 bytes.
 #include "common.cuh"
+#include <cstdio>
 #include <cstdlib>
 
 namespace dggb {
@@ -572,14 +573,15 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
       float xv[8][4];
       float av[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {                 // slots beyond the row: a = 0, column 0 (a valid row)
-        const int v = __shfl_sync(0xffffffffu, c_l, (k0 + k) & 31);
-        av[k] = (k0 + k < cnt) ? __shfl_sync(0xffffffffu, a_l, (k0 + k) & 31) : 0.f;
-        const float* xr = A.x + (size_t)((k0 + k < cnt) ? v : 0) * A.fin;
+      for (int k = 0; k < 8; ++k) {                 // slots beyond the row issue no load (see gcnii_stack_fwd_kernel:
+        const int v = __shfl_sync(0xffffffffu, c_l, (k0 + k) & 31);   // a shared dummy row is one hot L2 line for the grid)
+        const bool live = k0 + k < cnt;
+        av[k] = live ? __shfl_sync(0xffffffffu, a_l, (k0 + k) & 31) : 0.f;
+        const float* xr = A.x + (size_t)(live ? v : 0) * A.fin;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = lane + 32 * j;
-          xv[k][j] = (j < nj && c < A.fin) ? __ldg(xr + c) : 0.f;
+          xv[k][j] = (live && j < nj && c < A.fin) ? __ldg(xr + c) : 0.f;
         }
       }
 #pragma unroll
@@ -803,6 +805,199 @@ static int dispatch_vec(int f, Fn&& fn) {
   return fn(std::integral_constant<int, 1>{}, std::integral_constant<int, 4>{}, L);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// A STACK of GCNII layers in one launch (small graphs).  GCNII_DGG-64 on Citeseer runs 62 identical layers behind its
+// last DGG layer -- same adjacency, same h0, 0.85 MB of activations each: per layer the one-launch kernel above costs
+// ~13 us of launch + dependent-L2-round-trip latency (rowptr -> entries -> neighbour rows -> W) for ~1 us of work.
+// Here the grid is cooperative (every CTA resident), one warp owns ONE row for all layers: its entries (first 32) and
+// its h0 row stay in registers, W of layer k + 1 streams into the other half of a shared-memory double buffer
+// (cp.async) while layer k computes, and what is left per layer is one gather round trip, the 64 x 64 dense part and a
+// grid barrier (atomic counter; neighbour rows of the previous layer are read past L1 with ld.cg).
+// y[k] / s_out[k] are the per-layer outputs the backward needs (next input / ReLU mask, theta * s for dW).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStackMaxLayers = 96;
+
+struct StackArgs {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  int n, f, layers;
+  const float* x0;       // [n, f] input of the first layer
+  const float* h0;       // [n, f]
+  const float* keep;     // [layers, n, f] output dropout multipliers or NULL
+  float c1, c2;
+  float* y;              // [layers, n, f]
+  float* s_out;          // [layers, n, f] (theta * s) or NULL
+  unsigned* bar;         // one zeroed counter
+  const float* w[kStackMaxLayers];      // [f, f] each
+  float theta[kStackMaxLayers];         // beta = 1 - theta
+};
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void stack_grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();                       // cumulative: the block's stores (ordered before by bar.sync) become visible
+    atomicAdd(bar, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+#ifdef DGGB_STACK_TRACE
+__device__ long long g_stack_trace[2][kStackMaxLayers][8];   // [block 0 | block gridDim/2][layer][t0, t1, t2, t3]
+#endif
+
+template <int Q>
+__global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? 4 : 1)      // 4 CTAs per SM: 4 736 rows resident
+    gcnii_stack_fwd_kernel(const __grid_constant__ StackArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  const int f = A.f, ff = f * f;
+  float* Wbuf = sm;                                   // [2][f][f]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* srow = sm + 2 * ff + warp * f;
+  const int i = blockIdx.x * kSpmmWarps + warp;
+  const bool ok = i < A.n;
+  // layer 0's W travels while the row's static data is fetched
+#ifndef DGGB_STACK_W_L1
+  for (int c = threadIdx.x * 4; c < ff; c += blockDim.x * 4) cp_async16(Wbuf + c, A.w[0] + c);
+  cp_async_commit();
+#endif
+  const int beg = ok ? __ldg(A.rowptr + i) : 0, end = ok ? __ldg(A.rowptr + i + 1) : 0;
+  const int c_l = (beg + lane < end) ? __ldg(A.col + beg + lane) : 0;       // the row's first 32 entries: registers
+  const float a_l = (beg + lane < end) ? __ldg(A.val + beg + lane) : 0.f;
+  // Aggregation layout: LPE = f / 4 lanes per entry (one float4 column chunk each), EPS = 32 / LPE entries per step,
+  // eight steps in flight: 16 neighbour rows at f = 64.  (With lane == column and 8 rows in flight a 60-entry row took
+  // eight dependent L2 round trips per layer, and every layer of the whole grid waited for that one warp at the barrier:
+  // clock64 trace, 1 350 cycles per round, 12-17 k cycles of barrier wait for a warp with a 2-entry row.)
+  constexpr int LPE = 8 * Q, EPS = 32 / LPE;
+  const int sub = lane / LPE, cl = lane % LPE;
+  float4 h04 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok && sub == 0) h04 = __ldg(reinterpret_cast<const float4*>(A.h0 + (size_t)i * f) + cl);
+  const size_t plane = (size_t)A.n * f;
+  for (int k = 0; k < A.layers; ++k) {
+    float* Ws = Wbuf + (k & 1) * ff;
+#ifdef DGGB_STACK_NO_W
+    Ws = Wbuf;                                        // timing experiment only: W of layer 0 for every layer
+    cp_async_commit();
+#elif !defined(DGGB_STACK_W_L1)
+    if (k + 1 < A.layers) {                           // (the other half was last read by layer k - 1's dense part,
+      float* Wn = Wbuf + ((k + 1) & 1) * ff;          //  which every warp of the block left before the grid barrier)
+      for (int c = threadIdx.x * 4; c < ff; c += blockDim.x * 4) cp_async16(Wn + c, A.w[k + 1] + c);
+      cp_async_commit();
+    }
+#else
+    Ws = const_cast<float*>(A.w[k]);
+    if (k + 1 < A.layers)                             // next layer's W towards this SM's L1 (one 128-byte line per thread)
+      for (int c = threadIdx.x * 32; c < ff; c += blockDim.x * 32)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.w[k + 1] + c));
+#endif
+    const float* xin = (k == 0) ? A.x0 : A.y + (size_t)(k - 1) * plane;
+#ifdef DGGB_STACK_TRACE
+    long long t0 = clock64(), t1 = 0, t2 = 0, t3 = 0, ta = 0, tb = 0;
+#endif
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = beg; e0 < end; e0 += kWarp) {
+      int cc = c_l;
+      float aa = a_l;
+      if (e0 != beg) {                                // rows longer than 32 entries: the rest comes from memory
+        const int e = e0 + lane;
+        cc = (e < end) ? __ldg(A.col + e) : 0;
+        aa = (e < end) ? __ldg(A.val + e) : 0.f;
+      }
+      const int cnt = min(kWarp, end - e0);
+      for (int k0 = 0; k0 < cnt; k0 += 8 * EPS) {
+        float4 xv[8];
+        float av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          // slots beyond the row issue NO load: pointing them at "row 0, weight 0" made every warp of the grid hit the
+          // same two L2 lines ~14 times per layer -- 46 k requests on one line, 12-15 k cycles per gather round
+          // (clock64 trace) where a round trip is ~1 k
+          const int j = k0 + u * EPS + sub;
+          const int v = __shfl_sync(0xffffffffu, cc, j & 31);
+          const float a = __shfl_sync(0xffffffffu, aa, j & 31);
+          av[u] = (j < cnt) ? a : 0.f;
+          xv[u] = (j < cnt) ? __ldcg(reinterpret_cast<const float4*>(xin + (size_t)v * f) + cl)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc.x = fmaf(av[u], xv[u].x, acc.x); acc.y = fmaf(av[u], xv[u].y, acc.y);
+          acc.z = fmaf(av[u], xv[u].z, acc.z); acc.w = fmaf(av[u], xv[u].w, acc.w);
+        }
+      }
+    }
+#ifdef DGGB_STACK_TRACE
+    ta = clock64();
+#endif
+#pragma unroll
+    for (int o = LPE; o < kWarp; o <<= 1) {           // the EPS entry slots of a step hold partial sums
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    const float theta = A.theta[k], beta = 1.f - theta;
+    if (sub == 0) {
+      const float4 s4 = make_float4(fmaf(A.c2, h04.x, A.c1 * acc.x), fmaf(A.c2, h04.y, A.c1 * acc.y),
+                                    fmaf(A.c2, h04.z, A.c1 * acc.z), fmaf(A.c2, h04.w, A.c1 * acc.w));
+      reinterpret_cast<float4*>(srow)[cl] = s4;
+      if (A.s_out && ok)
+        reinterpret_cast<float4*>(A.s_out + (size_t)k * plane + (size_t)i * f)[cl] =
+            make_float4(theta * s4.x, theta * s4.y, theta * s4.z, theta * s4.w);
+    }
+#ifdef DGGB_STACK_TRACE
+    tb = clock64();
+#endif
+    __syncwarp();
+    float sv[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) sv[q] = srow[lane + 32 * q];
+#ifdef DGGB_STACK_TRACE
+    t1 = clock64();
+#endif
+#ifndef DGGB_STACK_W_L1
+    if (k + 1 < A.layers) asm volatile("cp.async.wait_group 1;" ::: "memory");   // W of THIS layer has landed
+    else cp_async_wait_all();
+#endif
+    __syncthreads();
+    float d[1][Q];
+    dense_rows<Q, 1>(srow, f, Ws, f, f, lane, d);
+    if (ok) {
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const int c = lane + 32 * q;
+        if (c < f) {
+          float v = fmaxf(fmaf(theta, d[0][q], beta * sv[q]), 0.f);
+          const size_t o = (size_t)k * plane + (size_t)i * f + c;
+          if (A.keep) v *= __ldg(A.keep + o);
+          A.y[o] = v;
+        }
+      }
+    }
+#ifdef DGGB_STACK_TRACE
+    t2 = clock64();
+#endif
+    if (k + 1 < A.layers) stack_grid_barrier(A.bar, (unsigned)(k + 1) * gridDim.x);
+#ifdef DGGB_STACK_TRACE
+    t3 = clock64();
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2)) {
+      long long* t = g_stack_trace[blockIdx.x == 0 ? 0 : 1][k];
+      t[0] = t0; t[1] = t1; t[2] = t2; t[3] = t3; t[4] = ta; t[5] = tb;
+    }
+#endif
+  }
+}
+
 }  // namespace dggb
 using namespace dggb;
 
@@ -945,4 +1140,84 @@ extern "C" int dggb_spmm_edge_bwd(const int32_t* erow, const int32_t* col, const
     return launch_status();
   };
   return T == 1 ? go(spmm_edge_bwd_kernel<1>) : (T == 2 ? go(spmm_edge_bwd_kernel<2>) : go(spmm_edge_bwd_kernel<4>));
+}
+
+static int stack_capacity_blocks(int f, size_t* smem_out) {
+  const size_t smem = (size_t)(2 * f * f + kSpmmWarps * f) * sizeof(float);
+  if (smem_out) *smem_out = smem;
+  int occ = 0, dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = cudaSuccess;
+  auto q = [&](auto kern) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSpmmWarps * kWarp, smem);
+  };
+  if (f == 32) q(gcnii_stack_fwd_kernel<1>);
+  else if (f == 64) q(gcnii_stack_fwd_kernel<2>);
+  else if (f == 128) q(gcnii_stack_fwd_kernel<4>);
+  else return 0;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return occ * sms;
+}
+
+// Largest row count dggb_gcnii_stack_fwd takes for feature width f on this device (one warp per row, all CTAs resident);
+// 0: width not supported.
+extern "C" int32_t dggb_gcnii_stack_max_rows(int32_t f) { return (int32_t)stack_capacity_blocks((int)f, nullptr) * kSpmmWarps; }
+
+// Forward of `layers` GCNII layers that share the adjacency and h0 (see gcnii_stack_fwd_kernel): y[k] = ReLU(theta_k
+// (s_k W_k) + (1 - theta_k) s_k) * keep[k], s_k = c1 (A y[k-1]) + c2 h0, y[-1] = x0.  Returns DGGB_ERR_UNSUPPORTED when
+// the grid (one warp per row) cannot be made resident at once or the shape is outside the kernel's range: the caller
+// then runs the layers one launch each.
+extern "C" int dggb_gcnii_stack_fwd(const int32_t* rowptr, const int32_t* col, const float* val, int32_t n,
+                                    const float* x0, const float* h0, int32_t f, int32_t layers,
+                                    const float* const* w_host_ptrs, const float* theta_host, float c1, float c2,
+                                    const float* keep, float* y, float* s_out, uint32_t* barrier_zeroed,
+                                    void* stream) {
+  if (!rowptr || !col || !val || !x0 || !h0 || !w_host_ptrs || !theta_host || !y || !barrier_zeroed || n <= 0 ||
+      layers <= 0)
+    return DGGB_ERR_BAD_ARG;
+  if (layers > kStackMaxLayers || (f != 32 && f != 64 && f != 128)) return DGGB_ERR_UNSUPPORTED;
+  StackArgs A{};
+  A.rowptr = rowptr; A.col = col; A.val = val; A.n = n; A.f = f; A.layers = layers;
+  A.x0 = x0; A.h0 = h0; A.keep = keep; A.c1 = c1; A.c2 = c2; A.y = y; A.s_out = s_out; A.bar = barrier_zeroed;
+  for (int k = 0; k < layers; ++k) {
+    if (!w_host_ptrs[k] || ((uintptr_t)w_host_ptrs[k] % 16)) return DGGB_ERR_BAD_ARG;
+    A.w[k] = w_host_ptrs[k];
+    A.theta[k] = theta_host[k];
+  }
+  size_t smem = 0;
+  const int grid = (n + kSpmmWarps - 1) / kSpmmWarps;
+  if (stack_capacity_blocks(f, &smem) < grid) return DGGB_ERR_UNSUPPORTED;
+  auto go = [&](auto kern) -> int {
+    cudaError_t e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kSpmmWarps * kWarp);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute at = {};
+    at.id = cudaLaunchAttributeCooperative;           // every CTA resident: the grid barrier cannot deadlock
+    at.val.cooperative = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, A);
+    if (e != cudaSuccess) return cuda_status(e);
+#ifdef DGGB_STACK_TRACE
+    static long long host_t[2][kStackMaxLayers][8];
+    cudaStreamSynchronize(cfg.stream);
+    cudaMemcpyFromSymbol(host_t, g_stack_trace, sizeof(host_t));
+    for (int b = 0; b < 2; ++b)
+      for (int k = 8; k < 12 && k < layers; ++k)
+        printf("blk %s layer %d: loads+fma %lld  reduce+s %lld  readback %lld | dense+store %lld  barrier %lld  (layer %lld)\n",
+               b ? "mid" : "0", k, host_t[b][k][4] - host_t[b][k][0], host_t[b][k][5] - host_t[b][k][4],
+               host_t[b][k][1] - host_t[b][k][5], host_t[b][k][2] - host_t[b][k][1],
+               host_t[b][k][3] - host_t[b][k][2], host_t[b][k][0] - host_t[b][k - 1][0]);
+#endif
+    return launch_status();
+  };
+  return f == 32 ? go(gcnii_stack_fwd_kernel<1>) : (f == 64 ? go(gcnii_stack_fwd_kernel<2>) : go(gcnii_stack_fwd_kernel<4>));
 }

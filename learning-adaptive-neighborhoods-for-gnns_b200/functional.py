@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import check, i32, i64, lib, p, stream
+from ._lib import DggbError, check, i32, i64, lib, p, stream
 from .graph import CSRGraph
 
 
@@ -27,6 +27,7 @@ _NO_EDGE_SPMM = bool(_os.environ.get("DGGB_NO_EDGE_SPMM"))
 # its SIMT dense part (N x 64 x 64 FMAs next to the gathers) loses to the entry-parallel SpMM + a library GEMM:
 # GCN_DGG_00 train step 0.337 vs 0.308 ms (scripts/model_ab.py, DGGB_NO_FUSED_CONV A/B).
 _FUSED_CONV_MAX_N = int(_os.environ.get("DGGB_FUSED_CONV_MAX_N", "8192"))
+_NO_STACK = bool(_os.environ.get("DGGB_NO_STACK"))     # A/B: GCNII layers one launch each instead of the stack kernel
 # rows from which the weight-gradient GEMM of a wide encoder (Q >= 256) runs on the tensor-core kernel
 _TN_TC_MIN_N = int(_os.environ.get("DGGB_TN_TC_MIN_N", "2048"))
 _FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu
@@ -280,6 +281,95 @@ class _SpmmGemm(torch.autograd.Function):
             dh0 = None
         dres = gy if (has_resid and ctx.needs_input_grad[4]) else None
         return dval, dx, dw, dh0, dres, None, None, None, None, None, None, None, None, None, None
+
+
+class _StackUnsupported(Exception):
+    pass
+
+
+class _GcniiStack(torch.autograd.Function):
+    """A run of GCNII layers with one adjacency and one h0 (model.py:722-729): forward = ONE cooperative launch
+    (dggb_gcnii_stack_fwd), backward = the per-layer launches of ``_SpmmGemm`` in a loop, with the h0 / adjacency-value
+    gradients accumulated in place."""
+
+    @staticmethod
+    def forward(ctx, vals, x0, h0, keep, graph: CSRGraph, c1, c2, thetas, *ws):
+        import ctypes
+
+        _require_cuda(vals, x0, h0, keep, *ws)
+        vals, x0, h0 = _f32c(vals), _f32c(x0), _f32c(h0)
+        keep = None if keep is None else _f32c(keep)
+        ws = [_f32c(w) for w in ws]
+        n, f = x0.shape
+        nl = len(ws)
+        y = torch.empty(nl, n, f, dtype=torch.float32, device=x0.device)
+        s = torch.empty(nl, n, f, dtype=torch.float32, device=x0.device)
+        bar = torch.zeros(1, dtype=torch.int32, device=x0.device)
+        wp = (ctypes.c_void_p * nl)(*[w.data_ptr() for w in ws])
+        th = (ctypes.c_float * nl)(*[float(t) for t in thetas])
+        rc = lib().dggb_gcnii_stack_fwd(p(graph.rowptr), p(graph.col), p(vals), i32(n), p(x0), p(h0), i32(f), i32(nl),
+                                        ctypes.cast(wp, ctypes.c_void_p), ctypes.cast(th, ctypes.c_void_p), float(c1),
+                                        float(c2), p(keep), p(y), p(s), p(bar), stream())
+        if rc == -3:            # DGGB_ERR_UNSUPPORTED: the grid cannot be resident at once / shape outside the range
+            raise _StackUnsupported()
+        check(rc, "gcnii_stack_fwd")
+        ctx.graph, ctx.meta = graph, (float(c1), float(c2), [float(t) for t in thetas])
+        ctx.save_for_backward(vals, x0, keep, y, s, *ws)
+        return y[nl - 1]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        vals, x0, keep, y, s, *ws = ctx.saved_tensors
+        c1, c2, thetas = ctx.meta
+        g = ctx.graph
+        nl, n, f = y.shape
+        need_v, need_x, need_h0 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dval = torch.empty_like(vals) if need_v else None
+        dh0 = torch.empty_like(x0) if need_h0 else None
+        dws = [None] * nl
+        gy = _f32c(g_out)
+        for k in range(nl - 1, -1, -1):
+            xk = x0 if k == 0 else y[k - 1]
+            need_dx = need_x or k > 0
+            dx = torch.zeros_like(x0) if need_dx else None
+            need_w = ctx.needs_input_grad[8 + k]
+            dwbuf = torch.empty(f * f, dtype=torch.float32, device=x0.device) if need_w else None
+            gm = torch.empty_like(gy) if need_w else None
+            check(lib().dggb_spmm_gemm_bwd(p(g.rowptr), p(g.col), p(vals), i32(n), p(xk), i32(f), None, float(c1),
+                                           p(ws[k]), i32(f), float(thetas[k]), float(1.0 - thetas[k]), p(gy), p(dval),
+                                           p(dx), p(dh0), float(c2), p(dwbuf), i64(0 if dwbuf is None else f * f),
+                                           p(y[k]), p(gm), p(None if keep is None else keep[k]),
+                                           i32(0 if k == nl - 1 else 3), stream()), "spmm_gemm_bwd")
+            if need_w:
+                dws[k] = gemm_tn(s[k], gm, False, zeroed=dwbuf)[0]
+            gy = dx
+        return (dval, gy if need_x else None, dh0, None, None, None, None, None, *dws)
+
+
+_STACK_MAX_ROWS = {}
+
+
+def gcnii_stack_applies(x0, ws):
+    """Whether ``gcnii_stack`` takes this run of layers: CUDA, square [f, f] weights with f in {32, 64, 128}, 2..96
+    layers, and a graph small enough for a fully resident grid (one warp per row)."""
+    n, f = x0.shape
+    if not (x0.is_cuda and f in (32, 64, 128) and 2 <= len(ws) <= 96 and not _NO_FUSED_CONV and not _NO_STACK
+            and all(tuple(w.shape) == (f, f) for w in ws)):
+        return False
+    if f not in _STACK_MAX_ROWS:
+        _STACK_MAX_ROWS[f] = int(lib().dggb_gcnii_stack_max_rows(i32(f)))
+    return n <= _STACK_MAX_ROWS[f]
+
+
+def gcnii_stack(vals, x0, h0, ws, graph, c1, c2, thetas, keep=None):
+    """-> the LAST layer's output of a run of GCNII layers sharing (graph, vals) and h0 (``gcnii_stack_applies`` says
+    beforehand whether the cooperative one-launch forward takes it)."""
+    if not gcnii_stack_applies(x0, ws):
+        raise DggbError("gcnii_stack: shape / residency outside the stack kernel's range (see gcnii_stack_applies)")
+    try:
+        return _GcniiStack.apply(vals, x0, h0, keep, graph, float(c1), float(c2), tuple(float(t) for t in thetas), *ws)
+    except _StackUnsupported:
+        raise DggbError("gcnii_stack: the grid is not resident on this device") from None
 
 
 def spmm_gemm_applies(x, w, n, beta=0.0):

@@ -278,13 +278,22 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
             keeps = torch.empty(len(self.convs), layer_inner.shape[0], layer_inner.shape[1],
                                 device=x.device).bernoulli_(1.0 - self.dropout).mul_(1.0 / (1.0 - self.dropout))
             layer_inner = F.dropout(layer_inner, self.dropout, training=True)
-        # all layers read h0, and all layers behind the last DGG layer read the same adjacency values: their gradients
-        # are summed in place by the layers' own backward launches (K.GradShare) instead of 2 x 63 autograd adds
+        # The layers from the last DGG layer on share one adjacency (and all layers share h0): that run is ONE cooperative
+        # launch in the forward (K.gcnii_stack) where the graph is small enough for a resident grid; layers in front of
+        # it -- or all layers where the stack kernel does not apply -- go one launch each, with the h0 / adjacency-value
+        # gradients summed in place by the layers' own backward launches (K.GradShare) instead of autograd adds.
         nl = len(self.convs)
-        share = (torch.is_grad_enabled() and not con0_variant(self.convs)
+        plain = not any(c.variant or c.residual for c in self.convs)
+        share = (torch.is_grad_enabled() and plain
                  and K.spmm_gemm_applies(layer_inner, self.convs[0].weight, x.shape[0], 1.0))
+        stack_from = max(len(self.dggs) - 1, 0)
+        if not (plain and nl - stack_from >= 2
+                and K.gcnii_stack_applies(layer_inner, [c.weight for c in self.convs[stack_from:]])):
+            stack_from = nl                                           # every layer one launch
         h0_sh, val_sh, val_first = (K.GradShare() if share else None), None, 0
-        for i, con in enumerate(self.convs):
+        i = 0
+        while i < nl:
+            con = self.convs[i]
             if i < len(self.dggs):
                 src = in_adj if self.dgg_adj_input == "input_adj" else unnorm_adj
                 unnorm_adj = self.dgg_net(x, i, src, writer, epoch)
@@ -292,11 +301,20 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
                 val_sh, val_first = (K.GradShare() if share else None), i
             if keeps is None:
                 layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
+            if i == stack_from:
+                g, v = CSRGraph.from_coo(norm_adj)
+                layer_inner = K.gcnii_stack(v, layer_inner, _layers[0], [c.weight for c in self.convs[i:]], g,
+                                            1 - self.alpha, self.alpha,
+                                            [math.log(self.lamda / (l + 1) + 1) for l in range(i, nl)],
+                                            keep=None if keeps is None else keeps[i:])
+                break
             val_last = i == nl - 1 or i + 1 < len(self.dggs)          # the next layer gets a new adjacency
+            h0_last = i == nl - 1 or i + 1 == stack_from              # ... or the stack takes over behind this layer
             layer_inner = con(layer_inner, norm_adj, _layers[0], self.lamda, self.alpha, i + 1, act="relu",
                               out_keep=None if keeps is None else keeps[i],
-                              h0_share=(h0_sh, i == 0, i == nl - 1) if share else None,
+                              h0_share=(h0_sh, i == 0, h0_last) if share else None,
                               val_share=(val_sh, i == val_first, val_last) if share else None)
+            i += 1
         if keeps is None:
             layer_inner = F.dropout(layer_inner, self.dropout, training=self.training)
         layer_inner = self.fcs[-1](layer_inner)

@@ -591,3 +591,43 @@ def test_grad_share_over_a_layer_stack_matches_autograd_sums():
     for got in (run(True), run(True, backwards=2)):
         for a_, b_ in zip(got, ref):
             torch.testing.assert_close(a_, b_, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,f,nl,deg,use_keep", [(3327, 64, 7, 4, True), (1000, 32, 3, 50, False), (999, 128, 4, 3, True),
+                                                  (4000, 64, 2, 8, False)])
+def test_gcnii_stack_matches_the_layer_by_layer_path(n, f, nl, deg, use_keep):
+    """The cooperative one-launch forward of a run of GCNII layers (grid barrier between layers, rows longer than 32
+    entries included) and its looped backward against the same layers as separate spmm_gemm calls: outputs and the
+    gradients of the adjacency values, the input, h0 and every weight."""
+    from dgg_b200 import CSRGraph, functional as K
+
+    gen = torch.Generator().manual_seed(n + nl)
+    m = n * deg
+    a = torch.sparse_coo_tensor(torch.stack([torch.randint(0, n, (m,), generator=gen), torch.randint(0, n, (m,), generator=gen)]),
+                                torch.ones(m), (n, n)).coalesce()
+    g = CSRGraph.from_indices(a.indices().cuda(), n)
+    v0 = (torch.rand(g.nnz, generator=gen) * (1.0 / deg) + 0.02).cuda()
+    x0 = torch.randn(n, f, generator=gen).cuda()
+    h00 = torch.randn(n, f, generator=gen).cuda()
+    ws0 = [(torch.randn(f, f, generator=gen) / f ** 0.5).cuda() for _ in range(nl)]
+    keep = ((torch.rand(nl, n, f, generator=gen) > 0.3).float() / 0.7).cuda() if use_keep else None
+    wl = torch.randn(n, f, generator=gen).cuda()
+    thetas = [0.5 / (k + 1) + 0.1 for k in range(nl)]
+
+    def run(stack):
+        v, x, h0 = (t.clone().requires_grad_(True) for t in (v0, x0, h00))
+        ws = [w.clone().requires_grad_(True) for w in ws0]
+        if stack:
+            assert K.gcnii_stack_applies(x, ws)
+            y = K.gcnii_stack(v, x, h0, ws, g, 0.9, 0.1, thetas, keep=keep)
+        else:
+            y = x
+            for k in range(nl):
+                y = K.spmm_gemm(v, y, ws[k], g, h0=h0, c1=0.9, c2=0.1, theta=thetas[k], beta=1 - thetas[k], relu=True,
+                                out_keep=None if keep is None else keep[k])
+        (y * wl).sum().backward()
+        return [y.detach(), v.grad, x.grad, h0.grad] + [w.grad for w in ws]
+
+    ref, got = run(False), run(True)
+    for a_, b_ in zip(got, ref):
+        torch.testing.assert_close(a_, b_, rtol=2e-4, atol=2e-5)
