@@ -83,15 +83,16 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp)
         const int cnt = min(kWarp, end - w0);
 #pragma unroll 4
         for (int j0 = 0; j0 < cnt; j0 += G) {
-          const int j = j0 + grp;                       // j >= cnt: a_l of that lane is 0 => contributes nothing
+          const int j = j0 + grp;
           const int v = __shfl_sync(0xffffffffu, c_l, j & 31);
-          float a = __shfl_sync(0xffffffffu, a_l, j & 31);   // shuffles stay outside any lane-dependent condition
-          if (j >= cnt) a = 0.f;
+          const float a = __shfl_sync(0xffffffffu, a_l, j & 31);   // shuffles stay outside any lane-dependent condition
           const float* xr = x + (size_t)v * f;
 #pragma unroll
           for (int t = 0; t < T; ++t) {
             const int c = f0 + VEC * (lg + L * t);
-            if (c < f) {
+            // groups beyond the row's entries issue no load: their index is 0, and row 0 would be one hot L2 line for
+            // every short row of the grid (see gcnii_stack_fwd_kernel)
+            if (c < f && j < cnt) {
               Vec<VEC> xv;
               xv.load(xr + c);
               acc[t].fma(a, xv);
