@@ -466,12 +466,23 @@ __global__ void __launch_bounds__(kLinThreads, 1)
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");                  // the four epilogue warps
         if (q == 0) {
+          if ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0) {        // 16-byte reductions: a quarter of the requests
+            for (int c = 4 * lane; c < H; c += 128) {                   // on the two lines every CTA adds into
+              float4 t;
+              t.x = cs[c] + cs[H + c] + cs[2 * H + c] + cs[3 * H + c];
+              t.y = cs[c + 1] + cs[H + c + 1] + cs[2 * H + c + 1] + cs[3 * H + c + 1];
+              t.z = cs[c + 2] + cs[H + c + 2] + cs[2 * H + c + 2] + cs[3 * H + c + 2];
+              t.w = cs[c + 3] + cs[H + c + 3] + cs[2 * H + c + 3] + cs[3 * H + c + 3];
+              red_add4(colsum + c, t);
+            }
+          } else {
 #pragma unroll
-          for (int c0 = 0; c0 < H; c0 += 32) {
-            const int c = c0 + lane;
-            if (c < H) {
-              const float t = cs[c] + cs[H + c] + cs[2 * H + c] + cs[3 * H + c];
-              if (t != 0.f) atomicAdd(colsum + c, t);
+            for (int c0 = 0; c0 < H; c0 += 32) {
+              const int c = c0 + lane;
+              if (c < H) {
+                const float t = cs[c] + cs[H + c] + cs[2 * H + c] + cs[3 * H + c];
+                if (t != 0.f) atomicAdd(colsum + c, t);
+              }
             }
           }
         }
