@@ -860,7 +860,11 @@ __device__ long long g_stack_trace[2][kStackMaxLayers][8];   // [block 0 | block
 #endif
 
 template <int Q>
-__global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? 4 : 1)      // 4 CTAs per SM: 4 736 rows resident
+#ifndef DGGB_STACK_U
+#define DGGB_STACK_U 8
+#define DGGB_STACK_MINB 4
+#endif
+__global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 1)      // 4 CTAs per SM: 4 736 rows resident
     gcnii_stack_fwd_kernel(const __grid_constant__ StackArgs A) {
   extern __shared__ __align__(16) float sm[];
   const int f = A.f, ff = f * f;
@@ -881,7 +885,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? 4 : 1)      // 4 C
   // eight steps in flight: 16 neighbour rows at f = 64.  (With lane == column and 8 rows in flight a 60-entry row took
   // eight dependent L2 round trips per layer, and every layer of the whole grid waited for that one warp at the barrier:
   // clock64 trace, 1 350 cycles per round, 12-17 k cycles of barrier wait for a warp with a 2-entry row.)
-  constexpr int LPE = 8 * Q, EPS = 32 / LPE;
+  constexpr int LPE = 8 * Q, EPS = 32 / LPE, kU = DGGB_STACK_U;
   const int sub = lane / LPE, cl = lane % LPE;
   float4 h04 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ok && sub == 0) h04 = __ldg(reinterpret_cast<const float4*>(A.h0 + (size_t)i * f) + cl);
@@ -917,11 +921,11 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? 4 : 1)      // 4 C
         aa = (e < end) ? __ldg(A.val + e) : 0.f;
       }
       const int cnt = min(kWarp, end - e0);
-      for (int k0 = 0; k0 < cnt; k0 += 8 * EPS) {
-        float4 xv[8];
-        float av[8];
+      for (int k0 = 0; k0 < cnt; k0 += kU * EPS) {
+        float4 xv[kU];
+        float av[kU];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kU; ++u) {
           // slots beyond the row issue NO load: pointing them at "row 0, weight 0" made every warp of the grid hit the
           // same two L2 lines ~14 times per layer -- 46 k requests on one line, 12-15 k cycles per gather round
           // (clock64 trace) where a round trip is ~1 k
@@ -933,7 +937,7 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? 4 : 1)      // 4 C
                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < kU; ++u) {
           acc.x = fmaf(av[u], xv[u].x, acc.x); acc.y = fmaf(av[u], xv[u].y, acc.y);
           acc.z = fmaf(av[u], xv[u].z, acc.z); acc.w = fmaf(av[u], xv[u].w, acc.w);
         }
