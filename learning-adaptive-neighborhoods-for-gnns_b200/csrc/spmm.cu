@@ -874,10 +874,8 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 
   const int i = blockIdx.x * kSpmmWarps + warp;
   const bool ok = i < A.n;
   // layer 0's W travels while the row's static data is fetched
-#ifndef DGGB_STACK_W_L1
   for (int c = threadIdx.x * 4; c < ff; c += blockDim.x * 4) cp_async16(Wbuf + c, A.w[0] + c);
   cp_async_commit();
-#endif
   const int beg = ok ? __ldg(A.rowptr + i) : 0, end = ok ? __ldg(A.rowptr + i + 1) : 0;
   const int c_l = (beg + lane < end) ? __ldg(A.col + beg + lane) : 0;       // the row's first 32 entries: registers
   const float a_l = (beg + lane < end) ? __ldg(A.val + beg + lane) : 0.f;
@@ -891,22 +889,12 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 
   if (ok && sub == 0) h04 = __ldg(reinterpret_cast<const float4*>(A.h0 + (size_t)i * f) + cl);
   const size_t plane = (size_t)A.n * f;
   for (int k = 0; k < A.layers; ++k) {
-    float* Ws = Wbuf + (k & 1) * ff;
-#ifdef DGGB_STACK_NO_W
-    Ws = Wbuf;                                        // timing experiment only: W of layer 0 for every layer
-    cp_async_commit();
-#elif !defined(DGGB_STACK_W_L1)
+    const float* Ws = Wbuf + (k & 1) * ff;
     if (k + 1 < A.layers) {                           // (the other half was last read by layer k - 1's dense part,
       float* Wn = Wbuf + ((k + 1) & 1) * ff;          //  which every warp of the block left before the grid barrier)
       for (int c = threadIdx.x * 4; c < ff; c += blockDim.x * 4) cp_async16(Wn + c, A.w[k + 1] + c);
       cp_async_commit();
     }
-#else
-    Ws = const_cast<float*>(A.w[k]);
-    if (k + 1 < A.layers)                             // next layer's W towards this SM's L1 (one 128-byte line per thread)
-      for (int c = threadIdx.x * 32; c < ff; c += blockDim.x * 32)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.w[k + 1] + c));
-#endif
     const float* xin = (k == 0) ? A.x0 : A.y + (size_t)(k - 1) * plane;
 #ifdef DGGB_STACK_TRACE
     long long t0 = clock64(), t1 = 0, t2 = 0, t3 = 0, ta = 0, tb = 0;
@@ -970,10 +958,8 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 
 #ifdef DGGB_STACK_TRACE
     t1 = clock64();
 #endif
-#ifndef DGGB_STACK_W_L1
     if (k + 1 < A.layers) asm volatile("cp.async.wait_group 1;" ::: "memory");   // W of THIS layer has landed
     else cp_async_wait_all();
-#endif
     __syncthreads();
     float d[1][Q];
     dense_rows<Q, 1>(srow, f, Ws, f, f, lane, d);
