@@ -28,6 +28,7 @@ _NO_EDGE_SPMM = bool(_os.environ.get("DGGB_NO_EDGE_SPMM"))
 # GCN_DGG_00 train step 0.337 vs 0.308 ms (scripts/model_ab.py, DGGB_NO_FUSED_CONV A/B).
 _FUSED_CONV_MAX_N = int(_os.environ.get("DGGB_FUSED_CONV_MAX_N", "8192"))
 _NO_STACK = bool(_os.environ.get("DGGB_NO_STACK"))     # A/B: GCNII layers one launch each instead of the stack kernel
+_NO_GRAD_SHARE = bool(_os.environ.get("DGGB_NO_GRAD_SHARE"))   # A/B: autograd sums the per-layer h0 / value gradients
 # rows from which the weight-gradient GEMM of a wide encoder (Q >= 256) runs on the tensor-core kernel
 _TN_TC_MIN_N = int(_os.environ.get("DGGB_TN_TC_MIN_N", "2048"))
 _FUSED_MAX_ROW = 512   # kFusedMaxDeg of csrc/dgg_edge.cu

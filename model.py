@@ -284,7 +284,7 @@ class GCNII_DGG(nn.Module, _NormalizeMixin):
         # gradients summed in place by the layers' own backward launches (K.GradShare) instead of autograd adds.
         nl = len(self.convs)
         plain = not any(c.variant or c.residual for c in self.convs)
-        share = (torch.is_grad_enabled() and plain
+        share = (torch.is_grad_enabled() and plain and not K._NO_GRAD_SHARE
                  and K.spmm_gemm_applies(layer_inner, self.convs[0].weight, x.shape[0], 1.0))
         stack_from = max(len(self.dggs) - 1, 0)
         if not (plain and nl - stack_from >= 2

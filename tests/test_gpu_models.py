@@ -221,3 +221,48 @@ def test_gat_dgg_pubmed_shape_forward_vs_dense_oracle():
         got, out_adj, x_dgg = m(s["x"].cuda(), adj, edge_index=no_loops.cuda())
     torch.testing.assert_close(x_dgg.cpu(), xe, rtol=1e-5, atol=2e-6)
     torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n_dgg,nl", [(1, 5), (2, 6), (3, 6), (3, 4)])
+def test_gcnii_dgg_stack_and_grad_sharing_match_the_plain_layer_loop(n_dgg, nl, monkeypatch):
+    """GCNII_DGG with the cooperative stack kernel + in-place h0 / adjacency-value gradient accumulation (the default)
+    against the same model with every layer as its own autograd node and autograd summing the gradients
+    (DGGB_NO_STACK / DGGB_NO_GRAD_SHARE), for DGG-layer counts that put the stack boundary at layer 0, 1 and 2:
+    log-probabilities and every parameter gradient."""
+    import argparse
+
+    import model as models
+    from dgg_b200 import functional as K
+
+    n, f, c = 700, 64, 5
+    gen = torch.Generator().manual_seed(10 * n_dgg + nl)
+    m = n * 4
+    i, j = torch.randint(0, n, (m,), generator=gen), torch.randint(0, n, (m,), generator=gen)
+    keep = i != j
+    a = torch.sparse_coo_tensor(torch.stack([torch.cat([i[keep], j[keep]]), torch.cat([j[keep], i[keep]])]),
+                                torch.ones(2 * int(keep.sum())), (n, n)).coalesce()
+    adj = torch.sparse_coo_tensor(a.indices(), torch.ones(a._nnz()), (n, n)).coalesce().cuda()
+    x = torch.rand(n, f, generator=gen).cuda()
+    args = argparse.Namespace(extra_edge_dim=2, extra_k_dim=1, dgg_hard=False, deg_mean=3.9, deg_std=5.3,
+                              dgg_mode_edge_net="u-v-deg", dgg_mode_k_net="x", dgg_mode_k_select="k_times_edge_prob",
+                              debug_step=3, perturb_edge_prob=False, symmetric_noise=True, stochastic_k=False,
+                              dgg_adj_input="input_adj", n_dgg_layers=n_dgg)
+    torch.manual_seed(1)
+    net = models.GCNII_DGG(nfeat=f, nlayers=nl, nhidden=64, nclass=c, dropout=0.5, lamda=0.5, alpha=0.1, variant=False,
+                           args=args).cuda().eval()          # eval: no dropout / noise draws, gradients still flow
+    wl = torch.randn(n, c, generator=gen).cuda()
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        out = net(x, adj)
+        (out * wl).sum().backward()
+        return out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    out_a, g_a = run()
+    monkeypatch.setattr(K, "_NO_STACK", True)
+    monkeypatch.setattr(K, "_NO_GRAD_SHARE", True)
+    out_b, g_b = run()
+    torch.testing.assert_close(out_a, out_b, rtol=1e-4, atol=1e-5)
+    assert g_a.keys() == g_b.keys() and len(g_a) > nl
+    for k in g_a:
+        torch.testing.assert_close(g_a[k], g_b[k], rtol=2e-3, atol=1e-5 + 2e-4 * float(g_b[k].abs().max()), msg=k)
