@@ -429,6 +429,21 @@ def run_ours(args, rank, local_rank, world):
         return
 
     roofline = kernel_roofline(m, dsets, shape)
+    try:    # the whole step against the same peak: algorithmic bytes of its launches / the replayed step time
+        step_keys = [k for k in roofline["others"]
+                     if k.startswith(("linear_tf32x3_kernel<chained y>", "gemm_tn_tf32x3_kernel: dWn",
+                                      "linear_tf32x3_kernel: d pre", "dgg_fwd_fused2_kernel", "dgg_bwd_fused2_kernel"))]
+        if len(step_keys) == 5 and world == 1:
+            sb = sum(roofline["others"][k]["algorithmic_bytes"] for k in step_keys)
+            # the edge kernels' gathered rows are L2-resident at this size: second figure with their COMPULSORY bytes
+            sc = sum(roofline["others"][k].get("compulsory_bytes", roofline["others"][k]["algorithmic_bytes"])
+                     for k in step_keys)
+            st = ms / args.steps * 1e-3
+            roofline["step"] = dict(algorithmic_bytes=int(sb), compulsory_bytes=int(sc), ms=st * 1e3,
+                                    gbps=sb / st / 1e9, frac=sb / st / 1e9 / roofline["peak"],
+                                    frac_compulsory=sc / st / 1e9 / roofline["peak"], launches=step_keys)
+    except Exception as e:      # reporting only
+        roofline["step"] = dict(error=repr(e)[:120])
     epoch = full_model_epoch(dsets, shape, dev) if world == 1 else None
     if epoch is not None and not os.environ.get("DGGB_BENCH_NO_CONFIGS"):
         epoch["configs"] = config_epochs(dev, dsets)
