@@ -818,6 +818,7 @@ static int dispatch_vec(int f, Fn&& fn) {
 // y[k] / s_out[k] are the per-layer outputs the backward needs (next input / ReLU mask, theta * s for dW).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStackMaxLayers = 96;
+constexpr int kStackChunks = 16;   // overflow chunks of long rows a CTA spreads over its warps (two per warp)
 
 struct StackArgs {
   const int32_t* rowptr;
@@ -867,10 +868,12 @@ template <int Q>
 __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 1)      // 4 CTAs per SM: 4 736 rows resident
     gcnii_stack_fwd_kernel(const __grid_constant__ StackArgs A) {
   extern __shared__ __align__(16) float sm[];
+  __shared__ int s_beg[kSpmmWarps], s_end[kSpmmWarps];
   const int f = A.f, ff = f * f;
   float* Wbuf = sm;                                   // [2][f][f]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* srow = sm + 2 * ff + warp * f;
+  float* ovf = sm + 2 * ff + kSpmmWarps * f;          // [kStackChunks][f] partial sums of spread-out overflow chunks
   const int i = blockIdx.x * kSpmmWarps + warp;
   const bool ok = i < A.n;
   // layer 0's W travels while the row's static data is fetched
@@ -879,14 +882,53 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 
   const int beg = ok ? __ldg(A.rowptr + i) : 0, end = ok ? __ldg(A.rowptr + i + 1) : 0;
   const int c_l = (beg + lane < end) ? __ldg(A.col + beg + lane) : 0;       // the row's first 32 entries: registers
   const float a_l = (beg + lane < end) ? __ldg(A.val + beg + lane) : 0.f;
+  if (lane == 0) {
+    s_beg[warp] = beg;
+    s_end[warp] = end;
+  }
   // Aggregation layout: LPE = f / 4 lanes per entry (one float4 column chunk each), EPS = 32 / LPE entries per step,
-  // eight steps in flight: 16 neighbour rows at f = 64.  (With lane == column and 8 rows in flight a 60-entry row took
-  // eight dependent L2 round trips per layer, and every layer of the whole grid waited for that one warp at the barrier:
-  // clock64 trace, 1 350 cycles per round, 12-17 k cycles of barrier wait for a warp with a 2-entry row.)
-  constexpr int LPE = 8 * Q, EPS = 32 / LPE, kU = DGGB_STACK_U;
+  // eight steps in flight: one ROUND = OWN = 8 EPS neighbour rows (16 at f = 64).  (With lane == column and 8 rows in
+  // flight a 60-entry row took eight dependent L2 round trips per layer, and every layer of the whole grid waited for
+  // that one warp at the barrier: clock64 trace, profiles/r02f_hot_lines.md.)
+  constexpr int LPE = 8 * Q, EPS = 32 / LPE, kU = DGGB_STACK_U, OWN = kU * EPS;
   const int sub = lane / LPE, cl = lane % LPE;
-  float4 h04 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ok && sub == 0) h04 = __ldg(reinterpret_cast<const float4*>(A.h0 + (size_t)i * f) + cl);
+  float h0v[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) h0v[q] = ok ? __ldg(A.h0 + (size_t)i * f + lane + 32 * q) : 0.f;
+  __syncthreads();
+  // A long row's entries beyond its first round are cut into chunks of OWN entries that the CTA's warps share (chunk c
+  // -> warp c % 8; up to kStackChunks per CTA, the rest stays with the owner): a 60-entry row is two rounds of the
+  // layer's critical path instead of four.  The table is static over the layers: each warp keeps its (at most two)
+  // helper chunks' entries in registers.
+  int my_base = 0, my_cov = 0;                        // this row's chunks are ovf[my_base .. my_base + my_cov)
+  int hc_len[2] = {0, 0}, hc_col[2] = {0, 0};
+  float hc_val[2] = {0.f, 0.f};
+  {
+    int base = 0;
+#pragma unroll
+    for (int v = 0; v < kSpmmWarps; ++v) {
+      const int dv = s_end[v] - s_beg[v];
+      const int nch = dv > OWN ? (dv - OWN + OWN - 1) / OWN : 0;
+      const int cov = max(0, min(nch, kStackChunks - base));
+      if (v == warp) {
+        my_base = base;
+        my_cov = cov;
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = warp + kSpmmWarps * t;          // the chunk this warp helps with
+        if (c >= base && c < base + cov) {
+          const int e0 = s_beg[v] + OWN * (1 + c - base);
+          hc_len[t] = min(OWN, s_end[v] - e0);
+          hc_col[t] = lane < hc_len[t] ? __ldg(A.col + e0 + lane) : 0;
+          hc_val[t] = lane < hc_len[t] ? __ldg(A.val + e0 + lane) : 0.f;
+        }
+      }
+      base += cov;
+    }
+  }
+  const int own_cnt = min(end - beg, OWN);
+  const int tail_beg = beg + OWN * (1 + my_cov);      // entries nobody helps with (more than kStackChunks chunks per CTA)
   const size_t plane = (size_t)A.n * f;
   for (int k = 0; k < A.layers; ++k) {
     const float* Ws = Wbuf + (k & 1) * ff;
@@ -899,24 +941,16 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 
 #ifdef DGGB_STACK_TRACE
     long long t0 = clock64(), t1 = 0, t2 = 0, t3 = 0, ta = 0, tb = 0;
 #endif
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = beg; e0 < end; e0 += kWarp) {
-      int cc = c_l;
-      float aa = a_l;
-      if (e0 != beg) {                                // rows longer than 32 entries: the rest comes from memory
-        const int e = e0 + lane;
-        cc = (e < end) ? __ldg(A.col + e) : 0;
-        aa = (e < end) ? __ldg(A.val + e) : 0.f;
-      }
-      const int cnt = min(kWarp, end - e0);
-      for (int k0 = 0; k0 < cnt; k0 += kU * EPS) {
+    // one gather pass over <= 32 entries held by the lanes (cc, aa): rounds of OWN entries, partial sums per entry slot
+    auto gather = [&](int cc, float aa, int cnt, float4& acc) {
+      for (int k0 = 0; k0 < cnt; k0 += OWN) {
         float4 xv[kU];
         float av[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-          // slots beyond the row issue NO load: pointing them at "row 0, weight 0" made every warp of the grid hit the
-          // same two L2 lines ~14 times per layer -- 46 k requests on one line, 12-15 k cycles per gather round
-          // (clock64 trace) where a round trip is ~1 k
+          // slots beyond the entries issue NO load: pointing them at "row 0, weight 0" made every warp of the grid hit
+          // the same two L2 lines ~14 times per layer -- 46 k requests on one line, 12-15 k cycles per round where a
+          // round trip is ~1 k (clock64 trace)
           const int j = k0 + u * EPS + sub;
           const int v = __shfl_sync(0xffffffffu, cc, j & 31);
           const float a = __shfl_sync(0xffffffffu, aa, j & 31);
@@ -930,37 +964,60 @@ __global__ void __launch_bounds__(kSpmmWarps* kWarp, Q <= 2 ? DGGB_STACK_MINB : 
           acc.z = fmaf(av[u], xv[u].z, acc.z); acc.w = fmaf(av[u], xv[u].w, acc.w);
         }
       }
+    };
+    auto slot_sum = [&](float4& acc) {                // the EPS entry slots of a step hold partial sums
+#pragma unroll
+      for (int o = LPE; o < kWarp; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+    };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather(c_l, a_l, own_cnt, acc);                   // the row's first round
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {                     // chunks of the CTA's long rows (warp-uniform conditions)
+      if (hc_len[t] > 0) {
+        float4 acc_o = make_float4(0.f, 0.f, 0.f, 0.f);
+        gather(hc_col[t], hc_val[t], hc_len[t], acc_o);
+        slot_sum(acc_o);
+        if (sub == 0) reinterpret_cast<float4*>(ovf + (size_t)(warp + kSpmmWarps * t) * f)[cl] = acc_o;
+      }
+    }
+    for (int e0 = tail_beg; e0 < end; e0 += kWarp) {  // what is left of a very long row stays with its owner
+      const int e = e0 + lane;
+      gather((e < end) ? __ldg(A.col + e) : 0, (e < end) ? __ldg(A.val + e) : 0.f, min(kWarp, end - e0), acc);
     }
 #ifdef DGGB_STACK_TRACE
     ta = clock64();
 #endif
-#pragma unroll
-    for (int o = LPE; o < kWarp; o <<= 1) {           // the EPS entry slots of a step hold partial sums
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    const float theta = A.theta[k], beta = 1.f - theta;
-    if (sub == 0) {
-      const float4 s4 = make_float4(fmaf(A.c2, h04.x, A.c1 * acc.x), fmaf(A.c2, h04.y, A.c1 * acc.y),
-                                    fmaf(A.c2, h04.z, A.c1 * acc.z), fmaf(A.c2, h04.w, A.c1 * acc.w));
-      reinterpret_cast<float4*>(srow)[cl] = s4;
-      if (A.s_out && ok)
-        reinterpret_cast<float4*>(A.s_out + (size_t)k * plane + (size_t)i * f)[cl] =
-            make_float4(theta * s4.x, theta * s4.y, theta * s4.z, theta * s4.w);
-    }
+    slot_sum(acc);
+    if (sub == 0) reinterpret_cast<float4*>(srow)[cl] = acc;      // the row's own partial sum
 #ifdef DGGB_STACK_TRACE
     tb = clock64();
 #endif
-    __syncwarp();
+    if (k + 1 < A.layers) asm volatile("cp.async.wait_group 1;" ::: "memory");   // W of THIS layer has landed
+    else cp_async_wait_all();
+    __syncthreads();                                  // W, every warp's partial sums and the helpers' chunk sums
+    const float theta = A.theta[k], beta = 1.f - theta;
     float sv[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) sv[q] = srow[lane + 32 * q];
+    for (int q = 0; q < Q; ++q) {
+      const int c = lane + 32 * q;
+      float raw = srow[c];
+      for (int t = 0; t < my_cov; ++t) raw += ovf[(size_t)(my_base + t) * f + c];
+      sv[q] = fmaf(A.c2, h0v[q], A.c1 * raw);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int c = lane + 32 * q;
+      srow[c] = sv[q];
+      if (A.s_out && ok) A.s_out[(size_t)k * plane + (size_t)i * f + c] = theta * sv[q];
+    }
+    __syncwarp();
 #ifdef DGGB_STACK_TRACE
     t1 = clock64();
 #endif
-    if (k + 1 < A.layers) asm volatile("cp.async.wait_group 1;" ::: "memory");   // W of THIS layer has landed
-    else cp_async_wait_all();
-    __syncthreads();
     float d[1][Q];
     dense_rows<Q, 1>(srow, f, Ws, f, f, lane, d);
     if (ok) {
@@ -1134,7 +1191,7 @@ extern "C" int dggb_spmm_edge_bwd(const int32_t* erow, const int32_t* col, const
 }
 
 static int stack_capacity_blocks(int f, size_t* smem_out) {
-  const size_t smem = (size_t)(2 * f * f + kSpmmWarps * f) * sizeof(float);
+  const size_t smem = (size_t)(2 * f * f + kSpmmWarps * f + kStackChunks * f) * sizeof(float);
   if (smem_out) *smem_out = smem;
   int occ = 0, dev = 0, sms = kNumSMs;
   cudaGetDevice(&dev);

@@ -594,7 +594,7 @@ def test_grad_share_over_a_layer_stack_matches_autograd_sums():
 
 
 @pytest.mark.parametrize("n,f,nl,deg,use_keep", [(3327, 64, 7, 4, True), (1000, 32, 3, 50, False), (999, 128, 4, 3, True),
-                                                  (4000, 64, 2, 8, False)])
+                                                  (4000, 64, 2, 8, False), (1500, 64, 3, 70, True), (900, 128, 3, 30, False)])
 def test_gcnii_stack_matches_the_layer_by_layer_path(n, f, nl, deg, use_keep):
     """The cooperative one-launch forward of a run of GCNII layers (grid barrier between layers, rows longer than 32
     entries included) and its looped backward against the same layers as separate spmm_gemm calls: outputs and the
